@@ -1,0 +1,126 @@
+"""CPU: pins the oracle restatement against vectors produced by the reference's own sources
+(tests/golden/make_golden.py) and against independent formulations."""
+import types
+
+import pytest
+import torch
+
+from wcmc_b200.synth import make_batch
+
+
+def _close(a, b, rtol=1e-5, atol=1e-7):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("non_local", [True, False])
+def test_feature_mse_matches_reference(golden, oracle, tag, non_local):
+    g = golden["fmse_%s_nl%d" % (tag, non_local)]
+    p = g["p"].clone().requires_grad_(True)
+    torch.manual_seed(g["seed"])
+    loss = oracle.ref.feature_mse(p, g["ref"], non_local=non_local)
+    loss.backward()
+    _close(loss, g["loss"])
+    _close(p.grad, g["grad"], rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_grs_matches_reference(golden, oracle, tag):
+    g = golden["grs_%s" % tag]
+    p = g["p"].clone().requires_grad_(True)
+    torch.manual_seed(g["seed"])
+    loss = oracle.ref.grs_loss(p, g["ref"])
+    loss.backward()
+    _close(loss, g["loss"])
+    _close(p.grad, g["grad"], rtol=1e-4, atol=1e-8)
+
+
+def test_relative_mse_matches_reference(golden, oracle):
+    g = golden["relmse"]
+    _close(oracle.ref.relative_mse(g["im"], g["ref"]), g["loss"])
+
+
+def test_pathnet_wiring_matches_reference(golden, oracle):
+    g = golden["pathnet"]
+    torch.manual_seed(g["seed"])
+    net = oracle.PathNet(ic=36, outc=3)
+    assert str(net) == g["str"]
+    assert sorted(net.state_dict().keys()) == g["keys"]
+    batch = make_batch(batch=1, spp=2, size=16, seed=g["data_seed"])
+    with torch.no_grad():
+        out = net(batch)
+    _close(out, g["out"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["wcmc", "wcmc_m10r01", "vanilla"])
+def test_train_step_matches_reference_interface(golden, oracle, tag):
+    g = golden["itf_" + tag]
+    cfg = g["cfg"]
+    torch.manual_seed(0)
+    llpm = cfg["use_llpm_buf"]
+    models = {"dncnn": oracle.KPCN(g["n_in"])}
+    if llpm:
+        models["backbone_diffuse"] = oracle.PathNet(ic=36, outc=cfg["outc"])
+        models["backbone_specular"] = oracle.PathNet(ic=36, outc=cfg["outc"])
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    batch = make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=llpm)
+    for m in models.values():
+        m.train()
+    torch.manual_seed(g["perm_seed"])
+    loss, out, _ = oracle.ref.kpcn_train_step(models, optims, batch, use_llpm_buf=llpm,
+                                              manif_learn=cfg["manif_learn"], w_manif=0.1,
+                                              disentangle=cfg["opt"])
+    for k, v in loss.items():
+        _close(v, g["losses"]["m_" + k], rtol=1e-4, atol=1e-7)
+    for name, m in models.items():
+        sums = torch.stack([p.detach().double().sum() for p in m.parameters()])
+        _close(sums, g["param_sums"][name], rtol=1e-5, atol=1e-5)
+        gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()])
+        _close(gs, g["grad_abs_sums"][name], rtol=1e-3, atol=1e-6)
+    for m in models.values():
+        m.eval()
+    rad, _, relmse = oracle.ref.kpcn_validate(models, batch, use_llpm_buf=llpm,
+                                              disentangle=cfg["opt"])
+    _close(rad, g["val_radiance"], rtol=1e-4, atol=1e-6)
+    _close(relmse, g["m_val"], rtol=1e-4, atol=1e-7)
+
+
+def test_kernel_weighting_vs_explicit_loops(oracle):
+    """Independent formulation of SURVEY Appendix A.5 (scalar loops) vs the unfold oracle."""
+    g = torch.Generator().manual_seed(3)
+    b, c, h, w, k = 1, 2, 6, 7, 5
+    data = torch.randn(b, c, h, w, generator=g)
+    wts = torch.rand(b, k, k, h, w, generator=g)
+    out, sw = oracle.modules.kernel_weighting(data, wts)
+    r = k // 2
+    exp = torch.zeros_like(out)
+    for y in range(h):
+        for x in range(w):
+            for dy in range(k):
+                for dx in range(k):
+                    yy, xx = y + dy - r, x + dx - r
+                    if 0 <= yy < h and 0 <= xx < w:
+                        exp[0, :, y, x] += wts[0, dy, dx, y, x] * data[0, :, yy, xx]
+    _close(out, exp, rtol=1e-5, atol=1e-6)
+    _close(sw, wts.sum((1, 2)))
+
+
+def test_kpcn_shapes_and_gradcheck_small(oracle):
+    torch.manual_seed(0)
+    net = oracle.KPCN(34, ksize=5, depth=2, width=4).double()
+    batch = {k: v.double() for k, v in make_batch(batch=1, size=14, seed=1, paths=False).items()}
+    out = net(batch)
+    assert out["radiance"].shape == (1, 3, 6, 6)
+    # fp64 gradcheck of kernel-apply + softmax
+    ka = oracle.modules.KernelApply()
+    data = torch.randn(1, 2, 4, 4, dtype=torch.double)
+    logits = torch.randn(1, 9, 4, 4, dtype=torch.double, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda z: ka(data, z)[0], (logits,), atol=1e-6)
+
+
+def test_crop_like_matches_reference_rule(oracle):
+    x = torch.arange(128 * 128.).view(1, 1, 128, 128)
+    t = torch.zeros(1, 1, 92, 92)
+    assert torch.equal(oracle.modules.crop_like(x, t), x[..., 18:110, 18:110])
+    t = torch.zeros(1, 1, 91, 90)  # odd deltas: crop = delta//2, crop2 = delta - crop
+    assert torch.equal(oracle.modules.crop_like(x, t), x[..., 18:109, 19:109])
