@@ -1,0 +1,107 @@
+/* libwcmc.so -- C ABI of the B200-native (sm_100a) backend for WCMC's KPCN hot path.
+ *
+ * The reference (Mephisto405/WCMC) is pure Python; its only native boundary on this path is the
+ * Halide `kernel_weighting` extension of the un-vendored `sbmc` package plus the cuDNN / ATen
+ * calls behind torch.nn.  This header is the boundary that replaces them: every
+ * entry point cites the reference call site whose arithmetic it takes over.  The Python host
+ * side (wcmc_b200/, loaded with ctypes) mirrors sbmc.KPCN / sbmc.modules / support.networks /
+ * support.losses / support.interfaces on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the library never allocates, never synchronises and only touches the stream passed in
+ *     (`stream` is a cudaStream_t passed as void*);
+ *   - return value 0 = WCMC_OK, negative = error; wcmc_last_error() gives the message
+ *     (thread local);
+ *   - "NHWC bf16" = activations stored (N, H, W, Cs) in bfloat16 with a channel stride Cs that
+ *     is a multiple of 8 and a logical channel count padded with zeros to a multiple of 16;
+ *   - sm_100a only: wcmc_init() fails with WCMC_EARCH elsewhere.  There is no CPU fallback.
+ */
+#ifndef WCMC_H_
+#define WCMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WCMC_OK 0
+#define WCMC_ESHAPE (-1)  /* unsupported / inconsistent shape argument */
+#define WCMC_EALIGN (-2)  /* pointer or stride alignment */
+#define WCMC_EARCH (-3)   /* device is not sm_100 */
+#define WCMC_ECUDA (-4)   /* CUDA runtime / driver error (message has the details) */
+#define WCMC_EWORKSPACE (-5)
+
+#define WCMC_ACT_LINEAR 0
+#define WCMC_ACT_RELU 1
+#define WCMC_ACT_LEAKY 2
+
+const char* wcmc_last_error(void);
+const char* wcmc_version(void);
+/* Checks that `device` is a compute-capability-10.x GPU and prepares per-process state. */
+int wcmc_init(int device);
+
+/* ---- layout conversion (boundary between torch NCHW fp32 tensors and the NHWC bf16 pipeline) --
+ * dst[n,h,w,dst_coff+c] = bf16(src[n,c,h,w]) for c < C; channels C..c_fill-1 are written as 0. */
+int wcmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int dst_cs,
+                               int dst_coff, int c_fill, void* stream);
+/* dst[n,c,h,w] (fp32, contiguous) (+)= src[n,h,w,src_coff+c] */
+int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int src_cs,
+                               int src_coff, int accumulate, void* stream);
+
+/* ---- weights: torch (Cout, Cin, k, k) fp32  ->  packed bf16 operands of the conv kernels ------
+ * fwd  : dst[co][ky*k+kx][ci]            = w[co][ci][ky][kx]   (cout_p x k*k x cin_p, zero padded)
+ * dgrad: dst[ci][(k-1-ky)*k+(k-1-kx)][co] = w[co][ci][ky][kx]  (cin_p  x k*k x cout_p)           */
+int wcmc_pack_weights(const float* w, void* dst_fwd, void* dst_dgrad, int cout, int cin, int ksize,
+                      int cout_p, int cin_p, void* stream);
+
+/* ---- K1/K2: convolution forward / data gradient (tcgen05 implicit GEMM) -----------------------
+ * Replaces nn.Conv2d(+ReLU) inside sbmc.modules.ConvChain (used at
+ * /root/reference/support/networks.py:18-24 and by sbmc.KPCN, train_kpcn.py:213).
+ *   y = act(conv(x, w) + bias) [* (mask > 0 ? 1 : slope)]
+ * x: NHWC bf16 (N,H,W,x_cs), channels [x_coff, x_coff+cin_p); w_packed: see wcmc_pack_weights;
+ * bias: fp32[cout_p] or NULL; y: NHWC (N,Ho,Wo,y_cs) bf16 or fp32 (y_fp32), channels
+ * [y_coff, y_coff+cout_p), Ho = H + 2*pad - ksize + 1.  mask (optional, NHWC bf16 with the
+ * spatial size of y) fuses the activation derivative of the previous layer into a dgrad.
+ * flags: 0 for production (bits are test knobs: bit0 descriptor base-offset mode,
+ * bits 4-5 force m tiles, bits 8-15 force n tile).                                           */
+int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                const void* w_packed, int cout_p, const float* bias, int ksize, int pad, void* y,
+                int y_cs, int y_coff, int y_fp32, int act, const void* mask, int mask_cs,
+                int mask_coff, float slope, int flags, void* stream);
+
+/* ---- K3: convolution weight gradient (tcgen05, MN-major operands, split-K) --------------------
+ * Autograd of nn.Conv2d w.r.t. its weight (reference: `L_diffuse.backward()`,
+ * /root/reference/support/interfaces.py:237-238).
+ *   dw[co][ci][ky][kx] (torch layout, fp32) (+)= sum_{n,oy,ox} dy[n,oy,ox,co] * x[n,oy+ky-pad,ox+kx-pad,ci]
+ * x, dy: NHWC bf16 as for wcmc_conv2d (dy has the conv's OUTPUT spatial size).  workspace holds
+ * the split-K partial sums; size it with wcmc_conv2d_wgrad_workspace().                         */
+size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, int cout_p, int ksize, int pad);
+int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                      const void* dy, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
+                      float* dw, int cout, int cin, int accumulate, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* db[co] (+)= sum over all pixels of dy[pix][dy_coff+co] */
+int wcmc_bias_grad(const void* dy, int npix, int dy_cs, int dy_coff, int cout, float* db,
+                   int accumulate, void* stream);
+
+/* ---- K4/K5: softmax + 21x21 kernel-apply (replaces sbmc.modules.KernelApply and the Halide
+ * `kernel_weighting` op; called by sbmc.KPCN.forward) ------------
+ * logits: NHWC fp32 (N,H,W,l_cs), first k*k channels used (k = 21: l_cs = 448)
+ * data  : NCHW fp32 (N,C,H,W), C <= 4;   out: NCHW fp32 (N,C,H,W)
+ *   out[n,c,y,x] = sum_{dy,dx} softmax(logits[n,y,x,:])[dy*k+dx] * data0[n,c,y+dy-k/2,x+dx-k/2]
+ * stats (N,H,W,2) fp32 receives (row max, 1/sum exp) for the backward pass (may be NULL).   */
+int wcmc_kernel_apply_fwd(const float* logits, int l_cs, const float* data, float* out,
+                          float* stats, int N, int C, int H, int W, int ksize, void* stream);
+/* d_logits[n,y,x,k] = p_k * (sum_c g_c v_{c,k} - sum_c g_c out_c); written as NHWC
+ * (N,H,W,dl_cs) in bf16 (dl_bf16) or fp32, channels k*k..dl_cs-1 zeroed.                      */
+int wcmc_kernel_apply_bwd(const float* logits, int l_cs, const float* data, const float* out,
+                          const float* stats, const float* grad_out, void* d_logits, int dl_cs,
+                          int dl_bf16, int N, int C, int H, int W, int ksize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCMC_H_ */

@@ -1,0 +1,360 @@
+// K1/K2: halo-resident implicit-GEMM convolution on tcgen05 (forward and data-gradient).
+//
+// Replaces the cuDNN calls behind `nn.Conv2d` in sbmc.modules.ConvChain (the un-vendored
+// dependency of /root/reference/support/networks.py:18-24 and train_kpcn.py:213); see
+// SURVEY.md Appendix A.1/A.2 for the layer shapes.
+//
+//   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, oy+ky-pad, ox+kx-pad, ci] * w[co, ky, kx, ci] )
+//
+// Data layout: activations NHWC bf16 with the channel count padded to a multiple of 16;
+// weights packed as bf16 [cout_p][k*k][cin_p].  The data gradient is the same kernel run on
+// dY with pad' = k-1-pad and tap-flipped / transposed weights, with the ReLU mask of the
+// layer input fused in the epilogue.
+//
+// Mapping to the GEMM:  M = 128 output pixels (an 8-wide x 16-tall box), N = cout tile
+// (<= 128), K = cin per tap.  A CTA owns a region of `mt` M-tiles side by side.  For every
+// 64-channel chunk the (16+k-1) x (8*mt+k-1) input halo is brought into shared memory ONCE
+// by a single 4-D TMA box (128-byte swizzle, zero fill outside the image = conv padding).
+// Every tap's A operand is then just a shifted window of that halo: the UMMA shared-memory
+// descriptor starts at pixel (ky, kx+8t) of the halo and uses the halo row pitch as its
+// stride-byte-offset, so the k*k-fold re-read of the activations never leaves the SM.
+// Weights stream through a 4-stage TMA ring.  Accumulators live in TMEM (double buffered:
+// the epilogue of one region overlaps the MMAs of the next).
+//
+// Warp roles (224 threads): w0 halo producer | w1 weight producer | w2 TMEM alloc + MMA
+// issuer | w3..w6 epilogue (TMEM -> regs -> bias/act/mask -> global).
+#include "common.cuh"
+
+namespace wcmc {
+
+constexpr int kPlaneSlots = 3;
+constexpr int kBStages = 4;
+constexpr int kPlaneBytes = 51200;   // 20 x 20 halo pixels x 128 B (k = 5, mt = 2)
+constexpr int kBStageBytes = 16384;  // 128 rows x 128 B
+constexpr int kConvThreads = 224;
+constexpr int kConvSmem = kPlaneSlots * kPlaneBytes + kBStages * kBStageBytes + 1024 + 256;
+
+struct ConvParams {
+    int N, Ho, Wo;
+    int ksize, pad;
+    int cin_p, nch;
+    int cout_p, nt, n_tiles;
+    int mt, regions_x, regions_y, total_items;
+    int halo_w, halo_h;
+    void* out;
+    int out_cs, out_coff, out_fp32;
+    const float* bias;
+    int act;
+    const __nv_bfloat16* mask;
+    int mask_cs, mask_coff;
+    float slope;
+    int flags;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                  const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* planes = smem;
+    uint8_t* bst = smem + kPlaneSlots * kPlaneBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bst + kBStages * kBStageBytes);
+    uint64_t* plane_full = bars;
+    uint64_t* plane_empty = bars + kPlaneSlots;
+    uint64_t* b_full = bars + 2 * kPlaneSlots;
+    uint64_t* b_empty = b_full + kBStages;
+    uint64_t* acc_full = b_empty + kBStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmx);
+        tma_prefetch_desc(&tmw);
+        for (int i = 0; i < kPlaneSlots; ++i) {
+            mbar_init(&plane_full[i], 1);
+            mbar_init(&plane_empty[i], 1);
+        }
+        for (int i = 0; i < kBStages; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int taps = p.ksize * p.ksize;
+    const int region_w = 8 * p.mt;
+    const uint32_t plane_bytes = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
+    const uint32_t b_bytes = static_cast<uint32_t>(p.nt * 128);
+
+    if (warp == 0) {
+        // ---------------- halo producer ----------------
+        if (lane == 0) {
+            int ps = 0, ph = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int r = item / p.n_tiles;
+                int rx = r % p.regions_x;
+                int ry = (r / p.regions_x) % p.regions_y;
+                int n = r / (p.regions_x * p.regions_y);
+                for (int c = 0; c < p.nch; ++c) {
+                    mbar_wait(&plane_empty[ps], ph ^ 1);
+                    mbar_expect_tx(&plane_full[ps], plane_bytes);
+                    tma_load_4d(planes + ps * kPlaneBytes, &tmx, &plane_full[ps], c * 64,
+                                rx * region_w - p.pad, ry * 16 - p.pad, n);
+                    if (++ps == kPlaneSlots) { ps = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+            int bs = 0, ph = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int n0 = (item % p.n_tiles) * p.nt;
+                for (int c = 0; c < p.nch; ++c) {
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&b_empty[bs], ph ^ 1);
+                        mbar_expect_tx(&b_full[bs], b_bytes);
+                        tma_load_3d(bst + bs * kBStageBytes, &tmw, &b_full[bs], c * 64, tap, n0);
+                        if (++bs == kBStages) { bs = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.nt, 0, 0);
+            const uint32_t sbo = static_cast<uint32_t>(p.halo_w * 128);
+            int ps = 0, pph = 0, bs = 0, bph = 0, it = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + buf * 256;
+                uint32_t accum = 0;
+                for (int c = 0; c < p.nch; ++c) {
+                    mbar_wait(&plane_full[ps], pph);
+                    tc_fence_after();
+                    const uint32_t plane_addr = smem_u32(planes + ps * kPlaneBytes);
+                    int nk = (p.cin_p - c * 64) >> 4;
+                    if (nk > 4) nk = 4;
+                    int ky = 0, kx = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&b_full[bs], bph);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(bst + bs * kBStageBytes);
+                        for (int t = 0; t < p.mt; ++t) {
+                            const uint32_t a_addr =
+                                plane_addr + static_cast<uint32_t>((ky * p.halo_w + kx + 8 * t) * 128);
+                            const uint32_t boff = (p.flags & 1) ? ((a_addr >> 7) & 7) : 0;
+                            for (int j = 0; j < nk; ++j) {
+                                uint64_t ad = make_sdesc_sw128(a_addr + 32 * j, 16, sbo, boff);
+                                uint64_t bd = make_sdesc_sw128(b_addr + 32 * j, 16, 1024, 0);
+                                umma_bf16(d_base + t * 128, ad, bd, idesc, accum | (j > 0));
+                            }
+                        }
+                        accum = 1;
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == kBStages) { bs = 0; bph ^= 1; }
+                        if (++kx == p.ksize) { kx = 0; ++ky; }
+                    }
+                    umma_commit(&plane_empty[ps]);
+                    if (++ps == kPlaneSlots) { ps = 0; pph ^= 1; }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue ----------------
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int ty = m >> 3, tx = m & 7;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const int buf = it & 1;
+            int r = item / p.n_tiles;
+            const int n0 = (item % p.n_tiles) * p.nt;
+            const int rx = r % p.regions_x;
+            const int ry = (r / p.regions_x) % p.regions_y;
+            const int n = r / (p.regions_x * p.regions_y);
+            int ncc = (p.cout_p - n0) >> 4;
+            if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            for (int t = 0; t < p.mt; ++t) {
+                const int oy = ry * 16 + ty;
+                const int ox = rx * region_w + 8 * t + tx;
+                const bool valid = (oy < p.Ho) && (ox < p.Wo);
+                const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
+                const uint32_t taddr =
+                    tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
+                for (int cc = 0; cc < ncc; ++cc) {
+                    uint32_t v[16];
+                    __syncwarp();
+                    tmem_ld16(taddr + cc * 16, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                    const int ch = n0 + cc * 16;
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias != nullptr) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 b = __ldg(b4 + i);
+                            f[4 * i + 0] += b.x;
+                            f[4 * i + 1] += b.y;
+                            f[4 * i + 2] += b.z;
+                            f[4 * i + 3] += b.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
+                    if (p.mask != nullptr) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(
+                            p.mask + pix * p.mask_cs + p.mask_coff + ch);
+                        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                        uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            f[2 * i] *= (bf16_lo(mw[i]) > 0.f) ? 1.f : p.slope;
+                            f[2 * i + 1] *= (bf16_hi(mw[i]) > 0.f) ? 1.f : p.slope;
+                        }
+                    }
+                    if (p.out_fp32) {
+                        float4* op = reinterpret_cast<float4*>(
+                            static_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(
+                            static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+                        op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                           pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                        op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                                           pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                    }
+                    }  // valid
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace wcmc
+
+using namespace wcmc;
+
+static int pick_nt(int cout_p) {
+    if (cout_p <= 128) return cout_p;
+    for (int nt = 128; nt >= 64; nt -= 16)
+        if (cout_p % nt == 0) return nt;
+    return 128;
+}
+
+extern "C" int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                           const void* w_packed, int cout_p, const float* bias, int ksize, int pad,
+                           void* y, int y_cs, int y_coff, int y_fp32, int act, const void* mask,
+                           int mask_cs, int mask_coff, float slope, int flags, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "conv2d: ksize %d not in {1,3,5}", ksize);
+    WCMC_REQUIRE(pad >= 0 && pad < ksize, WCMC_ESHAPE, "conv2d: bad pad %d", pad);
+    WCMC_REQUIRE(cin_p % 16 == 0 && cout_p % 16 == 0 && cin_p > 0 && cout_p > 0, WCMC_ESHAPE,
+                 "conv2d: cin_p (%d) and cout_p (%d) must be positive multiples of 16", cin_p, cout_p);
+    WCMC_REQUIRE(x_cs % 8 == 0 && x_coff % 8 == 0 && x_coff + cin_p <= x_cs, WCMC_ESHAPE,
+                 "conv2d: input channel stride/offset (%d,%d) must be multiples of 8", x_cs, x_coff);
+    WCMC_REQUIRE(y_cs % 8 == 0 && y_coff % 8 == 0 && y_coff + cout_p <= y_cs, WCMC_ESHAPE,
+                 "conv2d: output channel stride/offset (%d,%d) invalid", y_cs, y_coff);
+    WCMC_REQUIRE(mask == nullptr || (mask_cs % 8 == 0 && mask_coff % 8 == 0), WCMC_ESHAPE,
+                 "conv2d: mask channel stride/offset must be multiples of 8");
+    WCMC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+                 WCMC_EALIGN, "conv2d: pointers must be 16-byte aligned");
+    const int Ho = H + 2 * pad - ksize + 1, Wo = W + 2 * pad - ksize + 1;
+    WCMC_REQUIRE(Ho > 0 && Wo > 0 && N > 0, WCMC_ESHAPE, "conv2d: empty output");
+
+    ConvParams p;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.ksize = ksize; p.pad = pad;
+    p.cin_p = cin_p; p.nch = (cin_p + 63) / 64;
+    p.cout_p = cout_p;
+    p.nt = pick_nt(cout_p);
+    if ((flags >> 8) & 0xFF) p.nt = ((flags >> 8) & 0xFF);   // test override: n tile
+    WCMC_REQUIRE(p.nt % 16 == 0 && p.nt >= 16 && p.nt <= 128, WCMC_ESHAPE, "conv2d: bad n tile %d", p.nt);
+    p.n_tiles = (cout_p + p.nt - 1) / p.nt;
+    const int sms = wcmc_num_sms();
+    // Two M tiles per region (B streamed once for 256 pixels) unless that leaves SMs idle.
+    int mt = 2;
+    {
+        long items2 = static_cast<long>(N) * ((Wo + 15) / 16) * ((Ho + 15) / 16) * p.n_tiles;
+        if (items2 < 2L * sms) mt = 1;
+    }
+    if ((flags >> 4) & 3) mt = (flags >> 4) & 3;              // test override: m tiles
+    p.mt = mt;
+    p.regions_x = (Wo + 8 * mt - 1) / (8 * mt);
+    p.regions_y = (Ho + 15) / 16;
+    p.total_items = N * p.regions_x * p.regions_y * p.n_tiles;
+    p.halo_w = 8 * mt + ksize - 1;
+    p.halo_h = 16 + ksize - 1;
+    p.out = y; p.out_cs = y_cs; p.out_coff = y_coff; p.out_fp32 = y_fp32;
+    p.bias = bias; p.act = act;
+    p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
+    p.slope = slope; p.flags = flags;
+
+    CUtensorMap tmx, tmw;
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(cin_p), static_cast<uint64_t>(W),
+                            static_cast<uint64_t>(H), static_cast<uint64_t>(N)};
+        uint64_t strides[3] = {static_cast<uint64_t>(x_cs) * 2, static_cast<uint64_t>(x_cs) * 2 * W,
+                               static_cast<uint64_t>(x_cs) * 2 * W * H};
+        uint32_t box[4] = {64, static_cast<uint32_t>(p.halo_w), static_cast<uint32_t>(p.halo_h), 1};
+        int rc = wcmc_encode_tmap_bf16(&tmx, static_cast<const __nv_bfloat16*>(x) + x_coff, 4, dims,
+                                       strides, box, 1);
+        if (rc) return rc;
+    }
+    {
+        const int taps = ksize * ksize;
+        uint64_t dims[3] = {static_cast<uint64_t>(cin_p), static_cast<uint64_t>(taps),
+                            static_cast<uint64_t>(cout_p)};
+        uint64_t strides[2] = {static_cast<uint64_t>(cin_p) * 2, static_cast<uint64_t>(cin_p) * 2 * taps};
+        uint32_t box[3] = {64, 1, static_cast<uint32_t>(p.nt)};
+        int rc = wcmc_encode_tmap_bf16(&tmw, w_packed, 3, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        attr_set = true;
+    }
+    int grid = p.total_items < sms ? p.total_items : sms;
+    conv_igemm_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(tmx, tmw, p);
+    WCMC_LAUNCH_CHECK();
+    return WCMC_OK;
+}

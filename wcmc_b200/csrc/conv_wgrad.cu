@@ -1,0 +1,289 @@
+// K3: convolution weight gradient on tcgen05 with MN-major operands and split-K.
+//
+//   dW[tap][co][ci] = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy+ky-pad, ox+kx-pad, ci]
+//
+// (autograd of nn.Conv2d inside sbmc.modules.ConvChain; reference call sites
+// /root/reference/support/interfaces.py:237-238 `L_diffuse.backward(); L_specular.backward()`.)
+//
+// GEMM view: M = cout (128 per tile), N = cin tile (<= 128), K = pixels.  Both operands are
+// "MN-major": dy and x are NHWC, i.e. the M / N index (channel) is the contiguous one, so a TMA
+// box [pixels][64 channels] with 128-byte swizzle is directly a canonical MN-major SW128 UMMA
+// operand (8 pixels = one 1024-byte swizzle atom; 64-channel blocks are LBO apart).  One
+// K-step (16 pixels) = two rows of the 8-pixel-wide tile.  As in the forward kernel the input
+// halo is loaded once per pixel tile and every tap addresses a shifted window of it through the
+// descriptor start address, so one halo load feeds `tpg` taps (as many as fit in 512 TMEM
+// columns).  Work item = (cout tile, cin tile, tap group, K split); partial sums go to a
+// workspace [split][tap][cout_p][cin_p] with plain coalesced stores and are reduced (and
+// transposed to torch's (cout,cin,k,k) layout) by wcmc_wgrad_finalize -- deterministic, no atomics.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace wcmc {
+
+constexpr int kWgStages = 2;
+constexpr int kWgAPlane = 16384;  // 16 x 8 pixels x 128 B
+constexpr int kWgBPlaneMax = 30720;  // 20 x 12 pixels x 128 B (k = 5)
+constexpr int kWgStageBytes = 2 * kWgAPlane + 2 * kWgBPlaneMax;  // 94208
+constexpr int kWgThreads = 192;
+constexpr int kWgSmem = kWgStages * kWgStageBytes + 1024 + 128;
+
+struct WgradParams {
+    int N, Ho, Wo;
+    int ksize, pad, taps;
+    int cin_p, cout_p;
+    int nt, ci_tiles, m_tiles;
+    int cstride, tpg, tap_groups;
+    int nsplit;
+    int tiles_x, tiles_y, total_tiles;
+    int halo_w, halo_h, b_plane;  // b_plane: bytes between the two 64-channel halo planes
+    int a_planes, b_planes;
+    float* ws;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constant__ CUtensorMap tmx,
+                  const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kWgStages;
+    uint64_t* acc_full = empty + kWgStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // decode the work item
+    int item = blockIdx.x;
+    const int split = item % p.nsplit; item /= p.nsplit;
+    const int tg = item % p.tap_groups; item /= p.tap_groups;
+    const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+    const int mtile = item;
+    const int tap0 = tg * p.tpg;
+    const int ntap = min(p.tpg, p.taps - tap0);
+    const int ci0 = cit * p.nt, co0 = mtile * 128;
+    const int my_tiles = (p.total_tiles - split + p.nsplit - 1) / p.nsplit;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmdy);
+        tma_prefetch_desc(&tmx);
+        for (int i = 0; i < kWgStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const uint32_t stage_tx = static_cast<uint32_t>(p.a_planes * kWgAPlane +
+                                                    p.b_planes * p.halo_w * p.halo_h * 128);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = split + i * p.nsplit;
+                const int tx = tile % p.tiles_x;
+                const int ty = (tile / p.tiles_x) % p.tiles_y;
+                const int n = tile / (p.tiles_x * p.tiles_y);
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], stage_tx);
+                uint8_t* st = smem + s * kWgStageBytes;
+                for (int pl = 0; pl < p.a_planes; ++pl)
+                    tma_load_4d(st + pl * kWgAPlane, &tmdy, &full[s], co0 + pl * 64, tx * 8, ty * 16, n);
+                for (int pl = 0; pl < p.b_planes; ++pl)
+                    tma_load_4d(st + 2 * kWgAPlane + pl * p.b_plane, &tmx, &full[s], ci0 + pl * 64,
+                                tx * 8 - p.pad, ty * 16 - p.pad, n);
+                if (++s == kWgStages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.nt, 1, 1);
+            const uint32_t b_sbo = static_cast<uint32_t>(p.halo_w * 128);
+            int s = 0, ph = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + s * kWgStageBytes);
+                const uint32_t b_base = a_base + 2 * kWgAPlane;
+                int ky = tap0 / p.ksize, kx = tap0 % p.ksize;
+                for (int tl = 0; tl < ntap; ++tl) {
+                    const uint32_t d = tmem_base + tl * p.cstride;
+#pragma unroll 1
+                    for (int j = 0; j < 8; ++j) {
+                        uint64_t ad = make_sdesc_sw128(a_base + j * 2048, kWgAPlane, 1024, 0);
+                        uint64_t bd = make_sdesc_sw128(
+                            b_base + static_cast<uint32_t>(((2 * j + ky) * p.halo_w + kx) * 128),
+                            static_cast<uint32_t>(p.b_plane), b_sbo, 0);
+                        umma_bf16(d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                    }
+                    if (++kx == p.ksize) { kx = 0; ++ky; }
+                }
+                umma_commit(&empty[s]);
+                if (++s == kWgStages) { s = 0; ph ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // epilogue: TMEM lane = cout row, columns = (tap, cin)
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        int ncc = (p.cin_p - ci0) >> 4;
+        if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
+        for (int tl = 0; tl < ntap; ++tl) {
+            const int tap = tap0 + tl;
+            float* dst = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * p.cout_p + co) * p.cin_p + ci0;
+            for (int cc = 0; cc < ncc; ++cc) {
+                uint32_t v[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * p.cstride + cc * 16, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0;
+                }
+                if (co < p.cout_p) {
+                    float4* o = reinterpret_cast<float4*>(dst + cc * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// out[co][ci][tap] (+)= sum_split ws[split][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int cout,
+                                    int cin, int taps, int cout_p, int cin_p, int accumulate) {
+    const long total = static_cast<long>(cout) * cin * taps;
+    const long slab = static_cast<long>(taps) * cout_p * cin_p;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        // iterate in workspace order (ci fastest) for coalesced reads
+        int ci = static_cast<int>(i % cin);
+        int co = static_cast<int>((i / cin) % cout);
+        int tap = static_cast<int>(i / (static_cast<long>(cin) * cout));
+        const float* src = ws + (static_cast<long>(tap) * cout_p + co) * cin_p + ci;
+        float s = 0.f;
+        for (int k = 0; k < nsplit; ++k) s += src[k * slab];
+        float* d = dw + (static_cast<long>(co) * cin + ci) * taps + tap;
+        *d = accumulate ? (*d + s) : s;
+    }
+}
+
+}  // namespace wcmc
+
+using namespace wcmc;
+
+static int wgrad_plan(int N, int Ho, int Wo, int cin_p, int cout_p, int ksize, WgradParams* p) {
+    p->taps = ksize * ksize;
+    p->cin_p = cin_p;
+    p->cout_p = cout_p;
+    int nt = cin_p;
+    if (nt > 128) {
+        nt = 128;
+        for (int c = 128; c >= 64; c -= 16)
+            if (cin_p % c == 0) { nt = c; break; }
+    }
+    p->nt = nt;
+    p->ci_tiles = (cin_p + nt - 1) / nt;
+    p->m_tiles = (cout_p + 127) / 128;
+    p->cstride = nt <= 32 ? 32 : (nt <= 64 ? 64 : 128);
+    p->tpg = std::min(p->taps, 512 / p->cstride);
+    p->tap_groups = (p->taps + p->tpg - 1) / p->tpg;
+    p->tiles_x = (Wo + 7) / 8;
+    p->tiles_y = (Ho + 15) / 16;
+    p->total_tiles = N * p->tiles_x * p->tiles_y;
+    int base_items = p->m_tiles * p->ci_tiles * p->tap_groups;
+    int nsplit = wcmc_num_sms() / base_items;
+    nsplit = std::max(1, std::min(nsplit, p->total_tiles));
+    p->nsplit = nsplit;
+    p->halo_w = 8 + ksize - 1;
+    p->halo_h = 16 + ksize - 1;
+    p->b_plane = ((p->halo_w * p->halo_h * 128 + 1023) / 1024) * 1024;
+    p->a_planes = 2;
+    p->b_planes = (nt + 63) / 64;
+    return 0;
+}
+
+extern "C" size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, int cout_p, int ksize, int pad) {
+    WgradParams p;
+    const int Ho = H + 2 * pad - ksize + 1, Wo = W + 2 * pad - ksize + 1;
+    wgrad_plan(N, Ho, Wo, cin_p, cout_p, ksize, &p);
+    return static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
+}
+
+extern "C" int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                                 const void* dy, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
+                                 float* dw, int cout, int cin, int accumulate, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "wgrad: ksize %d not in {1,3,5}", ksize);
+    WCMC_REQUIRE(pad >= 0 && pad < ksize, WCMC_ESHAPE, "wgrad: bad pad %d", pad);
+    WCMC_REQUIRE(cin_p % 16 == 0 && cout_p % 16 == 0 && cin_p > 0 && cout_p > 0, WCMC_ESHAPE,
+                 "wgrad: cin_p (%d) / cout_p (%d) must be positive multiples of 16", cin_p, cout_p);
+    WCMC_REQUIRE(x_cs % 8 == 0 && x_coff % 8 == 0 && dy_cs % 8 == 0 && dy_coff % 8 == 0, WCMC_ESHAPE,
+                 "wgrad: channel strides/offsets must be multiples of 8");
+    WCMC_REQUIRE(cout <= cout_p && cin <= cin_p, WCMC_ESHAPE, "wgrad: logical channels exceed padded");
+    const int Ho = H + 2 * pad - ksize + 1, Wo = W + 2 * pad - ksize + 1;
+    WCMC_REQUIRE(Ho > 0 && Wo > 0 && N > 0, WCMC_ESHAPE, "wgrad: empty output");
+    WgradParams p;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.ksize = ksize; p.pad = pad;
+    wgrad_plan(N, Ho, Wo, cin_p, cout_p, ksize, &p);
+    size_t need = static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
+    WCMC_REQUIRE(workspace != nullptr && workspace_bytes >= need, WCMC_EWORKSPACE,
+                 "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+    p.ws = static_cast<float*>(workspace);
+
+    CUtensorMap tmdy, tmx;
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(cout_p), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                            static_cast<uint64_t>(N)};
+        uint64_t strides[3] = {static_cast<uint64_t>(dy_cs) * 2, static_cast<uint64_t>(dy_cs) * 2 * Wo,
+                               static_cast<uint64_t>(dy_cs) * 2 * Wo * Ho};
+        uint32_t box[4] = {64, 8, 16, 1};
+        int rc = wcmc_encode_tmap_bf16(&tmdy, static_cast<const __nv_bfloat16*>(dy) + dy_coff, 4, dims, strides,
+                                       box, 1);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(cin_p), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(N)};
+        uint64_t strides[3] = {static_cast<uint64_t>(x_cs) * 2, static_cast<uint64_t>(x_cs) * 2 * W,
+                               static_cast<uint64_t>(x_cs) * 2 * W * H};
+        uint32_t box[4] = {64, static_cast<uint32_t>(p.halo_w), static_cast<uint32_t>(p.halo_h), 1};
+        int rc = wcmc_encode_tmap_bf16(&tmx, static_cast<const __nv_bfloat16*>(x) + x_coff, 4, dims, strides, box,
+                                       1);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        WCMC_CHECK_CUDA(
+            cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        attr_set = true;
+    }
+    const int grid = p.m_tiles * p.ci_tiles * p.tap_groups * p.nsplit;
+    conv_wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(tmdy, tmx, p);
+    WCMC_LAUNCH_CHECK();
+    long total = static_cast<long>(cout) * cin * p.taps;
+    int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, p.nsplit, cout, cin, p.taps, cout_p, cin_p,
+                                                    accumulate);
+    WCMC_LAUNCH_CHECK();
+    return WCMC_OK;
+}

@@ -1,0 +1,76 @@
+// Host-side runtime of libwcmc.so: error state, device check, TMA tensor-map encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void wcmc_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* wcmc_last_error(void) { return g_err; }
+extern "C" const char* wcmc_version(void) { return "wcmc-b200 0.1 (sm_100a)"; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_sms = 0;
+static std::mutex g_mu;
+
+extern "C" int wcmc_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaDeviceProp prop;
+    WCMC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    WCMC_REQUIRE(prop.major == 10, WCMC_EARCH,
+                 "wcmc_init: device %d is sm_%d%d; libwcmc.so is sm_100a only (no fallback)", device,
+                 prop.major, prop.minor);
+    g_sms = prop.multiProcessorCount;
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WCMC_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        WCMC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, WCMC_ECUDA,
+                     "wcmc_init: cuTensorMapEncodeTiled not available from the driver");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    return WCMC_OK;
+}
+
+int wcmc_num_sms() { return g_sms > 0 ? g_sms : 148; }
+
+int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+    WCMC_REQUIRE(g_encode != nullptr, WCMC_ECUDA, "wcmc_init() has not been called");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                          const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wcmc_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box "
+                       "[%u,%u,%u,%u] stride0 %llu base %p",
+                       static_cast<int>(r), rank, (unsigned long long)dims[0],
+                       (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                       (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], rank > 1 ? box[1] : 0,
+                       rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+                       (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), base);
+        return WCMC_ECUDA;
+    }
+    return WCMC_OK;
+}

@@ -1,0 +1,231 @@
+"""ctypes binding of libwcmc.so (the C ABI declared in include/wcmc.h).
+
+The product path fails loudly when the CUDA library is missing or the device is not sm_100:
+there is no CPU fallback and nothing here ever imports ``oracle/``.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwcmc.so")
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/wcmc.h (tests check this).
+SIGNATURES = {
+    "wcmc_last_error": (ctypes.c_char_p, []),
+    "wcmc_version": (ctypes.c_char_p, []),
+    "wcmc_init": (c_int, [c_int]),
+    "wcmc_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "wcmc_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "wcmc_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+                    + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
+    "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
+    "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]
+                          + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
+    "wcmc_kernel_apply_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+}
+
+
+class WcmcError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libwcmc.so (no device needed); raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise WcmcError("%s not found: run `make` (or __graft_entry__.build()) first; "
+                                "there is no CPU fallback" % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise WcmcError("%s failed (%d): %s" % (what, rc, load().wcmc_last_error().decode()))
+
+
+def init(device=None):
+    lib = load()
+    if not torch.cuda.is_available():
+        raise WcmcError("wcmc_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _inited_devices:
+        _check(lib.wcmc_init(dev), "wcmc_init")
+        _inited_devices.add(dev)
+    return lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+# ------------------------------------------------------------------------------------------------
+# thin typed wrappers (torch tensors in, torch tensors out); all run on the current stream
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(src, dst=None, dst_coff=0, c_fill=None):
+    """src (N,C,H,W) fp32 -> dst (N,H,W,Cs) bf16, channels [dst_coff, dst_coff+c_fill)."""
+    lib = init(src.device)
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    n, c, h, w = src.shape
+    if c_fill is None:
+        c_fill = pad16(c)
+    if dst is None:
+        dst = torch.empty((n, h, w, c_fill), dtype=torch.bfloat16, device=src.device)
+    assert dst.dtype == torch.bfloat16 and dst.is_contiguous() and dst.shape[:3] == (n, h, w)
+    _check(lib.wcmc_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.data_ptr(), n, c, h, w, dst.shape[3], dst_coff,
+                                          c_fill, _stream()), "nchw_f32_to_nhwc_bf16")
+    return dst
+
+
+def nhwc_to_nchw(src, c, src_coff=0, out=None, accumulate=False):
+    lib = init(src.device)
+    assert src.dtype == torch.bfloat16 and src.is_contiguous()
+    n, h, w, cs = src.shape
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+        accumulate = False
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, c, h, w)
+    _check(lib.wcmc_nhwc_bf16_to_nchw_f32(src.data_ptr(), out.data_ptr(), n, c, h, w, cs, src_coff,
+                                          int(accumulate), _stream()), "nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def pack_weights(w, cout_p=None, cin_p=None, fwd=True, dgrad=True):
+    """torch (Cout,Cin,k,k) fp32 -> (fwd [cout_p,k*k,cin_p], dgrad [cin_p,k*k,cout_p]) bf16."""
+    lib = init(w.device)
+    w = w.detach()
+    assert w.dtype == torch.float32
+    w = w.contiguous()
+    cout, cin, k, k2 = w.shape
+    assert k == k2
+    cout_p = cout_p or pad16(cout)
+    cin_p = cin_p or pad16(cin)
+    f = torch.empty((cout_p, k * k, cin_p), dtype=torch.bfloat16, device=w.device) if fwd else None
+    d = torch.empty((cin_p, k * k, cout_p), dtype=torch.bfloat16, device=w.device) if dgrad else None
+    _check(lib.wcmc_pack_weights(w.data_ptr(), _p(f), _p(d), cout, cin, k, cout_p, cin_p, _stream()),
+           "pack_weights")
+    return f, d
+
+
+def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_fp32=False, x_coff=0, cin_p=None,
+           mask=None, mask_coff=0, slope=0.0, flags=0):
+    """x (N,H,W,Cs) bf16 NHWC; w_packed (cout_p, k*k, cin_p) bf16; returns NHWC output."""
+    lib = init(x.device)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    n, h, w, xcs = x.shape
+    cout_p, taps, wcin = w_packed.shape
+    assert taps == ksize * ksize
+    cin_p = cin_p or wcin
+    assert cin_p == wcin, "packed weight cin_p %d != %d" % (wcin, cin_p)
+    ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout_p), dtype=torch.float32 if out_fp32 else torch.bfloat16,
+                          device=x.device)
+    assert out.is_contiguous() and tuple(out.shape[:3]) == (n, ho, wo)
+    assert out.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= cout_p
+    if mask is not None:
+        assert mask.dtype == torch.bfloat16 and mask.is_contiguous() and tuple(mask.shape[:3]) == (n, ho, wo)
+    _check(lib.wcmc_conv2d(x.data_ptr(), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), cout_p, _p(bias),
+                           ksize, pad, out.data_ptr(), out.shape[3], out_coff, int(out_fp32), act, _p(mask),
+                           0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream()),
+           "conv2d")
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=0, out=None, accumulate=False):
+    """dw (cout,cin,k,k) fp32 (+)= sum dy (x) x ; x (N,H,W,Cs) / dy (N,Ho,Wo,Cs') bf16 NHWC."""
+    lib = init(x.device)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    n, h, w, xcs = x.shape
+    ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
+    assert tuple(dy.shape[:3]) == (n, ho, wo), (dy.shape, (n, ho, wo))
+    if out is None:
+        out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
+        accumulate = False
+    assert out.is_contiguous() and out.dtype == torch.float32
+    need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
+    ws = _workspace(need, x.device)
+    _check(lib.wcmc_conv2d_wgrad(x.data_ptr(), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), dy.shape[3], dy_coff,
+                                 cout_p, ksize, pad, out.data_ptr(), cout, cin, int(accumulate), ws.data_ptr(),
+                                 ws.numel(), _stream()), "conv2d_wgrad")
+    return out
+
+
+def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False):
+    lib = init(dy.device)
+    assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    npix = dy.shape[0] * dy.shape[1] * dy.shape[2]
+    if out is None:
+        out = torch.empty((cout,), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    _check(lib.wcmc_bias_grad(dy.data_ptr(), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate),
+                              _stream()), "bias_grad")
+    return out
+
+
+def kernel_apply_fwd(logits_nhwc, data, ksize, want_stats=True):
+    """logits (N,H,W,Cs>=k*k) fp32 NHWC, data (N,C,H,W) fp32 -> out (N,C,H,W), stats (N,H,W,2)."""
+    lib = init(data.device)
+    assert logits_nhwc.dtype == torch.float32 and logits_nhwc.is_contiguous()
+    assert data.dtype == torch.float32 and data.is_contiguous()
+    n, c, h, w = data.shape
+    assert tuple(logits_nhwc.shape[:3]) == (n, h, w)
+    out = torch.empty_like(data)
+    stats = torch.empty((n, h, w, 2), dtype=torch.float32, device=data.device) if want_stats else None
+    _check(lib.wcmc_kernel_apply_fwd(logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
+                                     out.data_ptr(), _p(stats), n, c, h, w, ksize, _stream()), "kernel_apply_fwd")
+    return out, stats
+
+
+def kernel_apply_bwd(logits_nhwc, data, out, stats, grad_out, ksize, dl_cs=None, bf16=True):
+    lib = init(data.device)
+    n, c, h, w = data.shape
+    grad_out = grad_out.contiguous()
+    assert grad_out.dtype == torch.float32
+    dl_cs = dl_cs or logits_nhwc.shape[3]
+    dl = torch.empty((n, h, w, dl_cs), dtype=torch.bfloat16 if bf16 else torch.float32, device=data.device)
+    _check(lib.wcmc_kernel_apply_bwd(logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
+                                     out.data_ptr(), stats.data_ptr(), grad_out.data_ptr(), dl.data_ptr(), dl_cs,
+                                     int(bf16), n, c, h, w, ksize, _stream()), "kernel_apply_bwd")
+    return dl
