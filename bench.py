@@ -1,0 +1,260 @@
+"""bench.py -- KPCN+WCMC training throughput on B200 (BASELINE.json: configs[1] at N=1, weak
+scaling B=8 per GPU for N>1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = KPCNInterface.preprocess + train_batch on one batch of 8 synthetic 128x128 patches
+with 8 spp (PathNet x2 -> p-buffer -> KPCN diffuse/specular -> L1 + path-disentangling loss ->
+two backward passes -> clip -> Adam x3).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH, SPP, SIZE, OUTC = 8, 8, 128, 3
+METRIC, UNIT = "KPCN+WCMC train patches/s", "patches/s"
+WORKLOAD = "configs[1]: KPCN + path embedding network + path disentangling loss, batch 8 of 128x128 patches, 8 spp"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_oracle_models():
+    import torch
+    from tests._oracle_loader import load_oracle
+    o = load_oracle()
+    torch.manual_seed(0)
+    models = {"dncnn": o.KPCN(35 + OUTC + 1), "backbone_diffuse": o.PathNet(36, outc=OUTC),
+              "backbone_specular": o.PathNet(36, outc=OUTC)}
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    return o, models, optims
+
+
+def cpu_reference_steps(sample_batch, warmup, steps):
+    """The reference's CPU path for this step.  sbmc (KPCN / ConvChain / Autoencoder / KernelApply)
+    is un-vendored, so the oracle port (pure PyTorch fp32, oneDNN) is what can run; it is driven on
+    all host cores.  Returns (patches/s, threads, seconds per step)."""
+    import torch
+    from wcmc_b200.synth import make_batch
+    o, models, optims = build_oracle_models()
+    batch = make_batch(batch=sample_batch, spp=SPP, size=SIZE, seed=1234)
+    for _ in range(warmup):
+        o.ref.kpcn_train_step(models, optims, batch, use_llpm_buf=True, manif_learn=True, w_manif=0.1)
+    t0 = time.time()
+    for _ in range(steps):
+        o.ref.kpcn_train_step(models, optims, batch, use_llpm_buf=True, manif_learn=True, w_manif=0.1)
+    dt = (time.time() - t0) / max(steps, 1)
+    return sample_batch / dt, torch.get_num_threads(), dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = 1
+    val, threads, dt = cpu_reference_steps(sample, args.warmup, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "oracle port of the reference step on host cores; each step is a "
+                                                     "bounded sample of %d patch (same 128x128, 8 spp shapes)" % sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d step(s) of batch %d (128x128, 8 spp) after %d warm-up" %
+                                       (args.steps, sample, args.warmup)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from wcmc_b200 import ddp, dropin, lib
+    from wcmc_b200.synth import make_batch
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dropin.install()
+    lib.init(local)
+    from sbmc import KPCN
+    from support.interfaces import KPCNInterface
+    from support.losses import FeatureMSE, RelativeMSE
+    from support.networks import PathNet
+
+    torch.manual_seed(0)
+    models = {"dncnn": KPCN(35 + OUTC + 1).cuda(), "backbone_diffuse": PathNet(ic=36, outc=OUTC).cuda(),
+              "backbone_specular": PathNet(ic=36, outc=OUTC).cuda()}
+    ddp.broadcast_parameters(models)
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        l_manif = FeatureMSE(non_local=True)
+    loss_funcs = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+                  "l_test": RelativeMSE(), "l_manif": l_manif}
+    itf = KPCNInterface(models, optims, loss_funcs, types.SimpleNamespace(model_name="bench"), use_llpm_buf=True,
+                        manif_learn=True, w_manif=0.1, train_branches=True, disentanglement_option="m11r11")
+    sync = ddp.GradAllReduce()
+    if world > 1:
+        itf.grad_sync = sync
+    host = {k: v.pin_memory() for k, v in make_batch(batch=BATCH, spp=SPP, size=SIZE, seed=1234 + rank).items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    itf.to_train_mode()
+
+    def step(batch):
+        itf.preprocess(batch)
+        itf.train_batch(batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(args.warmup):
+        step(dev)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = lib.LAUNCHES["count"]
+    ms_step = timed(lambda: step(dev), args.steps)
+    launches = (lib.LAUNCHES["count"] - n0) // args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # live per-kernel device time (CUDA events on the launching stream) over a second timed pass
+    lib.profile_start()
+    timed(lambda: step(dev), args.steps)
+    prof = lib.profile_stop()
+
+    # end to end: pinned host batch -> device every step, loss read back every step
+    dev2 = {k: torch.empty_like(v, device="cuda") for k, v in host.items()}
+
+    def e2e_step():
+        for k in host:
+            dev2[k].copy_(host[k], non_blocking=True)
+        step(dev2)
+        return float(itf.m_losses["m_l_total"])  # device -> host read of the step's loss
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    total_ms = sum(v[1] for v in prof.values()) or 1.0
+    n_c, ms_c, fl_c = prof.get("conv2d", (0, 1.0, 0.0))
+    n_w, ms_w, fl_w = prof.get("conv2d_wgrad", (0, 1.0, 0.0))
+    achieved = fl_c / (ms_c * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    kernels = {k: {"calls_per_step": v[0] // args.steps, "ms_per_step": round(v[1] / args.steps, 4),
+                   "share_of_kernel_time": round(v[1] / total_ms, 4)} for k, v in sorted(prof.items())}
+    for name, key, unit in (("conv2d", "tflops", 1e12), ("conv2d_wgrad", "tflops", 1e12),
+                            ("kernel_apply_fwd", "gbs", 1e9), ("kernel_apply_bwd", "gbs", 1e9)):
+        if name in prof and prof[name][1] > 0:
+            kernels[name][key] = round(prof[name][2] / (prof[name][1] * 1e-3) / unit, 1)
+    line = {
+        "metric": METRIC, "value": BATCH * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH, "spp": SPP,
+                   "patch": SIZE, "pnet_out_size": OUTC, "parallelism": "dp%d" % world,
+                   "l2": "inputs_exceed_l2 (%.0f MB of step inputs + %.0f MB of saved activations > 126 MB L2)"
+                         % (h2d_bytes / 1e6, 700.0),
+                   "precision": "bf16 operands, fp32 accumulate / master weights / losses"},
+        "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"kernel": "conv_igemm_kernel (conv fwd + dgrad, tcgen05)", "bound": "tensor",
+                     "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": pk_src + " (sustained)",
+                     "launches_per_step": n_c // args.steps,
+                     "share_of_step_kernel_time": round(ms_c / total_ms, 4)},
+        "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        val, threads, dt = cpu_reference_steps(2, 1, 2)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "2 timed steps of batch 2 (same 128x128, 8 spp patches) after 1 warm-up; "
+                                          "%.1f s/step" % dt}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -54,8 +54,10 @@ int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H,
 /* ---- weights: torch (Cout, Cin, k, k) fp32  ->  packed bf16 operands of the conv kernels ------
  * fwd  : dst[co][ky*k+kx][ci]            = w[co][ci][ky][kx]   (cout_p x k*k x cin_p, zero padded)
  * dgrad: dst[ci][(k-1-ky)*k+(k-1-kx)][co] = w[co][ci][ky][kx]  (cin_p  x k*k x cout_p)           */
-int wcmc_pack_weights(const float* w, void* dst_fwd, void* dst_dgrad, int cout, int cin, int ksize,
-                      int cout_p, int cin_p, void* stream);
+/* dst_bias[cout_p] = bias zero padded (bias may be NULL -> zeros); any dst may be NULL.        */
+int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* dst_dgrad,
+                      float* dst_bias, int cout, int cin, int ksize, int cout_p, int cin_p,
+                      void* stream);
 
 /* ---- K1/K2: convolution forward / data gradient (tcgen05 implicit GEMM) -----------------------
  * Replaces nn.Conv2d(+ReLU) inside sbmc.modules.ConvChain (used at
@@ -65,8 +67,8 @@ int wcmc_pack_weights(const float* w, void* dst_fwd, void* dst_dgrad, int cout, 
  * bias: fp32[cout_p] or NULL; y: NHWC (N,Ho,Wo,y_cs) bf16 or fp32 (y_fp32), channels
  * [y_coff, y_coff+cout_p), Ho = H + 2*pad - ksize + 1.  mask (optional, NHWC bf16 with the
  * spatial size of y) fuses the activation derivative of the previous layer into a dgrad.
- * flags: 0 for production (bits are test knobs: bit0 descriptor base-offset mode,
- * bits 4-5 force m tiles, bits 8-15 force n tile).                                           */
+ * flags: 0 for production (test knobs: bits 4-5 force m tiles per region, bits 8-15 force the
+ * n tile).                                                                                    */
 int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                 const void* w_packed, int cout_p, const float* bias, int ksize, int pad, void* y,
                 int y_cs, int y_coff, int y_fp32, int act, const void* mask, int mask_cs,
@@ -100,6 +102,33 @@ int wcmc_kernel_apply_fwd(const float* logits, int l_cs, const float* data, floa
 int wcmc_kernel_apply_bwd(const float* logits, int l_cs, const float* data, const float* out,
                           const float* stats, const float* grad_out, void* d_logits, int dl_cs,
                           int dl_bf16, int N, int C, int H, int W, int ksize, void* stream);
+
+/* ---- NHWC bf16 glue of the path-embedding network (PathNet, /root/reference/support/
+ * networks.py:29-42; U-Net = sbmc.modules.Autoencoder) ------------------
+ * Every tensor is (pixels, channel stride cs, channel offset coff); C, cs, coff multiples of 8.
+ * Writing into a channel slice of the consumer's buffer replaces torch.cat.                     */
+/* y (N,H/2,W/2) = 2x2 max pool of x (N,H,W)            (nn.MaxPool2d(2,2)) */
+int wcmc_maxpool2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int H,
+                      int W, int C, void* stream);
+/* dx (N,H,W) = (add or 0) + dy routed to the first maximum of each window (x = forward input) */
+int wcmc_maxpool2_bwd(const void* x, int x_cs, int x_coff, const void* dy, int dy_cs, int dy_coff,
+                      const void* add, int add_cs, int add_coff, void* dx, int dx_cs, int dx_coff, int N,
+                      int H, int W, int C, void* stream);
+/* y (N,2h,2w) = F.interpolate(x (N,h,w), scale 2, mode='bilinear', align_corners=False) */
+int wcmc_upsample2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int h,
+                       int w, int C, void* stream);
+int wcmc_upsample2_bwd(const void* dy, int dy_cs, int dy_coff, void* dx, int dx_cs, int dx_coff, int N,
+                       int h, int w, int C, void* stream);
+/* y[b,hw,:] = scale * sum_s x[b,s,hw,:]      (mean over samples per pixel, networks.py:36) */
+int wcmc_spp_reduce(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int B, int S,
+                    int HW, int C, float scale, void* stream);
+/* y[b,s,hw,:] = (add or 0)[b,s,hw,:] + scale * x[b,hw,:]   (broadcast over samples, networks.py:39) */
+int wcmc_spp_broadcast(const void* x, int x_cs, int x_coff, const void* add, int add_cs, int add_coff,
+                       void* y, int y_cs, int y_coff, int B, int S, int HW, int C, float scale,
+                       void* stream);
+/* dz = dy * act'(y), y = activation output (act = WCMC_ACT_RELU / WCMC_ACT_LEAKY) */
+int wcmc_act_bwd(const void* dy, int dy_cs, int dy_coff, const void* y, int y_cs, int y_coff, void* dz,
+                 int dz_cs, int dz_coff, long npix, int C, int act, float slope, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI / drop-in modules) against the oracle on the
+same seeded inputs and weights.  Tolerances are north_star's: relative L2 <= 1e-3 for denoised
+images and losses, <= 1e-2 for gradients on the bf16 tensor-core path.
+The oracle is plain PyTorch; for full-size cases it is evaluated on the GPU in fp32 (TF32 off)."""
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from wcmc_b200.synth import make_batch
+
+pytestmark = pytest.mark.gpu
+
+TOL_IMG = 1e-3
+TOL_GRAD = 1e-2
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def backend():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from wcmc_b200 import dropin, lib
+    dropin.install()
+    lib.init()
+    import sbmc
+    import support.interfaces as itf
+    import support.losses as losses
+    import support.networks as networks
+    return types.SimpleNamespace(lib=lib, sbmc=sbmc, KPCN=sbmc.KPCN, PathNet=networks.PathNet, losses=losses,
+                                 itf=itf)
+
+
+def to_cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels through the C ABI
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,cin,cout,same", [(5, 100, 100, 0), (5, 39, 100, 0), (5, 100, 441, 0), (3, 64, 64, 1),
+                                             (3, 384, 128, 1), (1, 36, 64, 0), (1, 128, 3, 0)])
+def test_conv_fwd_dgrad_wgrad_vs_fp64(backend, k, cin, cout, same):
+    lib = backend.lib
+    g = torch.Generator(device="cuda").manual_seed(k * 1000 + cin)
+    n, h, w = 2, 44, 36
+    pad = k // 2 if same else 0
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, device="cuda", generator=g)
+    xd = x.double().requires_grad_(True)
+    wd_ = wt.double().requires_grad_(True)
+    ref = F.conv2d(xd, wd_, b.double(), padding=pad)
+    dy = torch.randn(ref.shape, device="cuda", generator=g).bfloat16().float()
+    gx, gw = torch.autograd.grad(ref, (xd, wd_), dy.double())
+    wf, wdg, bp = lib.pack_weights(wt, b, want_bias=True)
+    xn = lib.nchw_to_nhwc(x)
+    y = lib.conv2d(xn, wf, bp, k, pad, act=0, out_fp32=True)
+    assert rel(y[..., :cout].permute(0, 3, 1, 2), ref) < 2e-5
+    dyn = lib.nchw_to_nhwc(dy)
+    dx = lib.conv2d(dyn, wdg, None, k, k - 1 - pad, act=0, out_fp32=True)
+    assert rel(dx[..., :cin].permute(0, 3, 1, 2), gx) < 2e-5
+    dw = lib.conv2d_wgrad(xn, dyn, cout, cin, k, pad, lib.pad16(cin), lib.pad16(cout))
+    assert rel(dw, gw) < 2e-5
+    db = lib.bias_grad(dyn, cout)
+    assert rel(db, dy.double().sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("mt,nt", [(1, 0), (2, 0), (2, 64), (1, 48)])
+def test_conv_tilings_agree(backend, mt, nt):
+    lib = backend.lib
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(3, 48, 37, 29, device="cuda", generator=g)
+    wt = torch.randn(96, 48, 3, 3, device="cuda", generator=g) * 0.05
+    wf, _ = lib.pack_weights(wt)
+    xn = lib.nchw_to_nhwc(x)
+    base = lib.conv2d(xn, wf, None, 3, 1, act=1, out_fp32=True)
+    alt = lib.conv2d(xn, wf, None, 3, 1, act=1, out_fp32=True, flags=(mt << 4) | (nt << 8))
+    assert torch.equal(base, alt)
+
+
+@pytest.mark.parametrize("k,c,shape", [(21, 3, (2, 37, 45)), (21, 3, (8, 92, 92)), (5, 1, (1, 9, 70)), (3, 4, (2, 8, 32))])
+def test_kernel_apply_vs_oracle(backend, oracle, k, c, shape):
+    lib = backend.lib
+    n, h, w = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    taps = k * k
+    cs = (taps + 7) // 8 * 8
+    logits = torch.randn(n, h, w, cs, device="cuda", generator=g) * 3
+    data = torch.rand(n, c, h, w, device="cuda", generator=g) * 4
+    gout = torch.randn(n, c, h, w, device="cuda", generator=g)
+    z = logits[..., :taps].permute(0, 3, 1, 2).contiguous().double().requires_grad_(True)
+    ref, _ = oracle.modules.KernelApply()(data.double(), z)
+    (gz,) = torch.autograd.grad(ref, z, gout.double())
+    out, stats = lib.kernel_apply_fwd(logits, data, k)
+    assert rel(out, ref) < 1e-5
+    dl = lib.kernel_apply_bwd(logits, data, out, stats, gout, k, bf16=False)
+    assert rel(dl[..., :taps], gz.permute(0, 2, 3, 1)) < 1e-5
+    assert float(dl[..., taps:].abs().max()) == 0.0 if cs > taps else True
+    dlb = lib.kernel_apply_bwd(logits, data, out, stats, gout, k, bf16=True)
+    assert rel(dlb[..., :taps].float(), gz.permute(0, 2, 3, 1)) < 4e-3
+    # property: a softmax-weighted gather of a constant image is that constant inside, and never
+    # exceeds the data range anywhere (zero padding only darkens)
+    ones = torch.full_like(data, 2.5)
+    o2, _ = lib.kernel_apply_fwd(logits, ones, k)
+    r = k // 2
+    if h > 2 * r and w > 2 * r:
+        assert torch.allclose(o2[..., r:h - r, r:w - r], ones[..., r:h - r, r:w - r], rtol=1e-5)
+    assert float(o2.max()) <= 2.5 * (1 + 1e-5) and float(o2.min()) >= 0.0
+
+
+def test_glue_kernels_vs_torch(backend):
+    lib = backend.lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 16, 12, 20, device="cuda", generator=g).bfloat16().float()
+    xn = lib.nchw_to_nhwc(x)
+    # max pool fwd / bwd
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 2, 2)
+    got = lib.nhwc_to_nchw(lib.maxpool2_fwd(xn, 16), 16)
+    assert torch.equal(got, ref)
+    dy = torch.randn(ref.shape, device="cuda", generator=g).bfloat16().float()
+    (gx,) = torch.autograd.grad(ref, xr, dy)
+    add = torch.randn(x.shape, device="cuda", generator=g).bfloat16().float()
+    gotb = lib.nhwc_to_nchw(lib.maxpool2_bwd(xn, lib.nchw_to_nhwc(dy), 16, add=lib.nchw_to_nhwc(add)), 16)
+    assert rel(gotb, gx + add) < 4e-3
+    # bilinear 2x fwd / bwd
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    got = lib.nhwc_to_nchw(lib.upsample2_fwd(xn, 16), 16)
+    assert rel(got, ref) < 4e-3
+    dy = torch.randn(ref.shape, device="cuda", generator=g).bfloat16().float()
+    (gx,) = torch.autograd.grad(ref, xr, dy)
+    gotb = lib.nhwc_to_nchw(lib.upsample2_bwd(lib.nchw_to_nhwc(dy), 16), 16)
+    assert rel(gotb, gx) < 4e-3
+    # spp reduce / broadcast
+    b, s = 1, 2
+    red = lib.nhwc_to_nchw(lib.spp_reduce(xn, b, s, 16, 0.5), 16)
+    assert rel(red, x.view(b, s, 16, 12, 20).mean(1)) < 4e-3
+    bc = lib.nhwc_to_nchw(lib.spp_broadcast(lib.nchw_to_nhwc(red), b, s, 16, 2.0, add=xn), 16)
+    assert rel(bc, x + 2.0 * red.bfloat16().float().repeat(s, 1, 1, 1)) < 4e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# modules against the oracle
+# ---------------------------------------------------------------------------------------------
+def _grads(model):
+    return {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def _compare_grads(ours, ref, tol=TOL_GRAD):
+    assert sorted(ours) == sorted(ref)
+    worst = max(rel(ours[k], ref[k]) for k in ours)
+    flat_o = torch.cat([ours[k].flatten() for k in sorted(ours)])
+    flat_r = torch.cat([ref[k].flatten() for k in sorted(ref)])
+    assert rel(flat_o, flat_r) < tol, "global grad rel-L2 %.3e" % rel(flat_o, flat_r)
+    return worst
+
+
+@pytest.mark.parametrize("size,batch,n_in", [(48, 2, 34), (128, 8, 39)])
+def test_kpcn_matches_oracle(backend, oracle, size, batch, n_in):
+    torch.manual_seed(0)
+    ref = oracle.KPCN(n_in).cuda()
+    ours = backend.KPCN(n_in).cuda()
+    ours.load_state_dict(ref.state_dict())
+    data = to_cuda(make_batch(batch=batch, size=size, seed=3, paths=False))
+    if n_in > 34:
+        g = torch.Generator().manual_seed(9)
+        extra = torch.rand(batch, n_in - 34, size, size, generator=g).cuda()
+        data["kpcn_diffuse_in"] = torch.cat([data["kpcn_diffuse_in"], extra], 1)
+        data["kpcn_specular_in"] = torch.cat([data["kpcn_specular_in"], extra * 0.5], 1)
+    xo = data["kpcn_diffuse_in"].clone().requires_grad_(True)
+    xr = data["kpcn_diffuse_in"].clone().requires_grad_(True)
+    out_o = ours(dict(data, kpcn_diffuse_in=xo))
+    out_r = ref(dict(data, kpcn_diffuse_in=xr))
+    for key in ("radiance", "diffuse", "specular"):
+        assert out_o[key].shape == out_r[key].shape
+        assert rel(out_o[key], out_r[key]) < TOL_IMG, key
+    tgt = torch.rand_like(out_r["radiance"])
+    F.l1_loss(out_o["diffuse"], tgt).backward(retain_graph=True)
+    F.l1_loss(out_o["specular"], tgt).backward()
+    F.l1_loss(out_r["diffuse"], tgt).backward(retain_graph=True)
+    F.l1_loss(out_r["specular"], tgt).backward()
+    _compare_grads(_grads(ours), _grads(ref))
+    assert rel(xo.grad, xr.grad) < TOL_GRAD
+
+
+@pytest.mark.parametrize("size,batch,spp,outc", [(16, 1, 2, 3), (32, 2, 3, 4), (128, 2, 8, 3)])
+def test_pathnet_matches_oracle(backend, oracle, size, batch, spp, outc):
+    torch.manual_seed(0)
+    ref = oracle.PathNet(36, outc=outc).cuda()
+    ours = backend.PathNet(36, outc=outc).cuda()
+    ours.load_state_dict(ref.state_dict())
+    data = to_cuda(make_batch(batch=batch, spp=spp, size=size, seed=4))
+    po, pr = ours(data), ref(data)
+    assert po.shape == pr.shape == (batch, spp, outc, size, size)
+    assert rel(po, pr) < 4e-3   # bf16 activations through 20 layers; the step-level bar is below
+    w = torch.randn_like(pr)
+    (po * w).mean().backward()
+    (pr * w).mean().backward()
+    _compare_grads(_grads(ours), _grads(ref), tol=2e-2)
+
+
+def _build(KPCN, PathNet, n_in, llpm, outc):
+    torch.manual_seed(0)
+    models = {"dncnn": KPCN(n_in)}
+    if llpm:
+        models["backbone_diffuse"] = PathNet(ic=36, outc=outc)
+        models["backbone_specular"] = PathNet(ic=36, outc=outc)
+    return models
+
+
+@pytest.mark.parametrize("tag", ["wcmc", "wcmc_m10r01", "vanilla"])
+def test_train_step_matches_reference_golden(backend, oracle, golden, tag):
+    """KPCNInterface.train_batch + validate_batch on the GPU backend against the vectors the
+    REFERENCE's own interfaces.py / losses.py produced (tests/golden/make_golden.py)."""
+    g = golden["itf_" + tag]
+    cfg = g["cfg"]
+    llpm = cfg["use_llpm_buf"]
+    ref_models = _build(oracle.KPCN, oracle.PathNet, g["n_in"], llpm, cfg["outc"])
+    models = _build(backend.KPCN, backend.PathNet, g["n_in"], llpm, cfg["outc"])
+    for k in models:
+        models[k].load_state_dict(ref_models[k].state_dict())
+        models[k].cuda()
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    loss_funcs = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+                  "l_test": backend.losses.RelativeMSE()}
+    if cfg["manif_learn"]:
+        loss_funcs["l_manif"] = backend.losses.FeatureMSE(non_local=True)
+    itf = backend.itf.KPCNInterface(models, optims, loss_funcs, types.SimpleNamespace(model_name="t"),
+                                    use_llpm_buf=llpm, manif_learn=cfg["manif_learn"], w_manif=0.1,
+                                    train_branches=True, disentanglement_option=cfg["opt"])
+    batch = to_cuda(make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=llpm))
+    itf.to_train_mode()
+    itf.preprocess(batch)
+    torch.manual_seed(g["perm_seed"])
+    itf.train_batch(batch)
+    for k, v in g["losses"].items():
+        assert rel(itf.m_losses[k].cpu(), v) < TOL_IMG, k
+    for name, m in models.items():
+        gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()]).cpu()
+        assert rel(gs, g["grad_abs_sums"][name]) < TOL_GRAD, name
+        sums = torch.stack([p.detach().double().sum() for p in m.parameters()]).cpu()
+        torch.testing.assert_close(sums, g["param_sums"][name], rtol=1e-3, atol=2e-2)
+    itf.to_eval_mode()
+    with torch.no_grad():
+        rad, _ = itf.validate_batch(batch)
+    assert rel(rad.cpu(), g["val_radiance"]) < TOL_IMG
+    assert rel(itf.m_losses["m_val"].cpu(), g["m_val"]) < 5e-3
+
+
+def test_full_size_wcmc_step_vs_oracle(backend, oracle):
+    """BASELINE configs[1]: B=8, S=8, 128^2, C=3 (n_in=39), FeatureMSE non-local, w_manif 0.1."""
+    ref_models = _build(oracle.KPCN, oracle.PathNet, 39, True, 3)
+    models = _build(backend.KPCN, backend.PathNet, 39, True, 3)
+    for k in models:
+        models[k].load_state_dict(ref_models[k].state_dict())
+        models[k].cuda()
+        ref_models[k].cuda()
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    ref_optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in ref_models.items()}
+    loss_funcs = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+                  "l_test": backend.losses.RelativeMSE(), "l_manif": backend.losses.FeatureMSE(non_local=True)}
+    itf = backend.itf.KPCNInterface(models, optims, loss_funcs, types.SimpleNamespace(model_name="t"),
+                                    use_llpm_buf=True, manif_learn=True, w_manif=0.1, train_branches=True)
+    batch = to_cuda(make_batch(batch=8, spp=8, size=128, seed=1234))
+    itf.to_train_mode()
+    itf.preprocess(batch)
+    torch.manual_seed(77)
+    itf.train_batch(batch)
+    torch.manual_seed(77)
+    loss, _, _ = oracle.ref.kpcn_train_step(ref_models, ref_optims, batch, use_llpm_buf=True, manif_learn=True,
+                                            w_manif=0.1)
+    for k, v in loss.items():
+        assert rel(itf.m_losses["m_" + k], v) < TOL_IMG, k
+    for name in models:
+        worst = _compare_grads(_grads(models[name]), _grads(ref_models[name]), tol=TOL_GRAD)
+        print(name, "worst per-tensor grad rel-L2", worst)
+        po = torch.cat([p.detach().flatten() for p in models[name].parameters()])
+        pr = torch.cat([p.detach().flatten() for p in ref_models[name].parameters()])
+        assert rel(po, pr) < 5e-3, name
+    itf.to_eval_mode()
+    with torch.no_grad():
+        rad, _ = itf.validate_batch(batch)
+        rad_ref, _, relmse_ref = oracle.ref.kpcn_validate(ref_models, batch, use_llpm_buf=True)
+    assert rel(rad, rad_ref) < TOL_IMG
+    assert rel(itf.m_losses["m_val"], relmse_ref) < TOL_IMG
+    # size-independent properties: radiance recombination and finite gradients everywhere
+    for m in models.values():
+        for p in m.parameters():
+            assert torch.isfinite(p).all()

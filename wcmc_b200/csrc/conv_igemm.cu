@@ -165,9 +165,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                         for (int t = 0; t < p.mt; ++t) {
                             const uint32_t a_addr =
                                 plane_addr + static_cast<uint32_t>((ky * p.halo_w + kx + 8 * t) * 128);
-                            const uint32_t boff = (p.flags & 1) ? ((a_addr >> 7) & 7) : 0;
                             for (int j = 0; j < nk; ++j) {
-                                uint64_t ad = make_sdesc_sw128(a_addr + 32 * j, 16, sbo, boff);
+                                uint64_t ad = make_sdesc_sw128(a_addr + 32 * j, 16, sbo, 0);
                                 uint64_t bd = make_sdesc_sw128(b_addr + 32 * j, 16, 1024, 0);
                                 umma_bf16(d_base + t * 128, ad, bd, idesc, accum | (j > 0));
                             }

@@ -57,11 +57,15 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ d
     }
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                                    __nv_bfloat16* __restrict__ dgrad, int cout, int cin, int ks, int cout_p,
+__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad,
+                                    float* __restrict__ bias_p, int cout, int cin, int ks, int cout_p,
                                     int cin_p) {
     const int taps = ks * ks;
     const long total = static_cast<long>(cout_p) * taps * cin_p;
+    if (bias_p != nullptr && blockIdx.x == 0)
+        for (int c = threadIdx.x; c < cout_p; c += blockDim.x)
+            bias_p[c] = (bias != nullptr && c < cout) ? bias[c] : 0.f;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
         if (fwd != nullptr) {  // fwd[co][tap][ci]
@@ -154,16 +158,17 @@ extern "C" int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, in
     return WCMC_OK;
 }
 
-extern "C" int wcmc_pack_weights(const float* w, void* dst_fwd, void* dst_dgrad, int cout, int cin, int ksize,
-                                 int cout_p, int cin_p, void* stream_) {
+extern "C" int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* dst_dgrad,
+                                 float* dst_bias, int cout, int cin, int ksize, int cout_p, int cin_p,
+                                 void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin && ksize > 0, WCMC_ESHAPE,
                  "pack_weights: bad shape");
     long total = static_cast<long>(cout_p) * cin_p * ksize * ksize;
     int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
-    pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(dst_fwd),
-                                                    static_cast<__nv_bfloat16*>(dst_dgrad), cout, cin, ksize,
-                                                    cout_p, cin_p);
+    pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, bias, static_cast<__nv_bfloat16*>(dst_fwd),
+                                                    static_cast<__nv_bfloat16*>(dst_dgrad), dst_bias, cout, cin,
+                                                    ksize, cout_p, cin_p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

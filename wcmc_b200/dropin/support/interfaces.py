@@ -1,0 +1,266 @@
+"""B200 drop-in for the KPCN train / validate step of /root/reference/support/interfaces.py
+(`BaseInterface` :18-77, `KPCNInterface` :80-333).
+
+Same constructor, public methods, attributes and `m_losses` keys as the reference, so
+`train_kpcn.py` drives it unchanged.  Differences are host-side only:
+  * the per-loss `isfinite` checks (six device->host syncs per step in the reference, :255-257)
+    are folded into ONE sync per step;
+  * `grad_sync`, when set (wcmc_b200.ddp), runs between the two backward passes and the gradient
+    clipping, which is where a data-parallel all-reduce has to sit (:237-238 -> :261 -> :271).
+"""
+import os
+from abc import ABCMeta, abstractmethod
+
+import torch
+import torch.nn as nn
+
+from support.utils import crop_like
+
+_DISENTANGLE = ("m11r11", "m10r01", "m11r01", "m10r11")
+
+
+class BaseInterface(metaclass=ABCMeta):
+    def __init__(self, models, optims, loss_funcs, args, visual=False, use_llpm_buf=False, manif_learn=False,
+                 w_manif=0.1):
+        self.models, self.optims, self.loss_funcs, self.args = models, optims, loss_funcs, args
+        self.visual, self.use_llpm_buf, self.manif_learn, self.w_manif = visual, use_llpm_buf, manif_learn, w_manif
+        self.iters = 0
+        self.m_losses = {}
+        self.best_err = 1e10
+        self.fixed_batch = None
+
+    @abstractmethod
+    def to_train_mode(self):
+        pass
+
+    @abstractmethod
+    def preprocess(self, batch=None):
+        pass
+
+    @abstractmethod
+    def train_batch(self, batch):
+        pass
+
+    @abstractmethod
+    def _manifold_forward(self, batch):
+        return {}
+
+    @abstractmethod
+    def _regress_forward(self, batch):
+        return {}
+
+    @abstractmethod
+    def _backward(self, batch, out, p_buffers):
+        return {}
+
+    @abstractmethod
+    def _logging(self, loss_dict):
+        pass
+
+    @abstractmethod
+    def _optimization(self):
+        pass
+
+    @abstractmethod
+    def to_eval_mode(self):
+        pass
+
+    @abstractmethod
+    def validate_batch(self, batch):
+        pass
+
+    @abstractmethod
+    def get_epoch_summary(self, mode, norm):
+        return 0.0
+
+
+def _half(p_buffers, lo):
+    c = p_buffers["diffuse"].shape[2]
+    sl = slice(0, c // 2) if lo else slice(c // 2, None)
+    return {k: v[:, :, sl] for k, v in p_buffers.items()}
+
+
+def _with_pbuffer(batch, p_buffers):
+    """New batch whose KPCN inputs carry [mean_S(p) | var_S(p).mean(C)/S] (interfaces.py:165-180).
+    The mean keeps its graph (gradients reach PathNet through the regression branch); the
+    variance channel is detached, as in the reference."""
+    new = {k: batch[k] for k in ("target_total", "target_diffuse", "target_specular", "kpcn_diffuse_buffer",
+                                 "kpcn_specular_buffer", "kpcn_albedo")}
+    for name in ("diffuse", "specular"):
+        p = p_buffers[name]
+        var = p.var(1).mean(1, keepdim=True).detach() / p.shape[1]
+        new["kpcn_%s_in" % name] = torch.cat([batch["kpcn_%s_in" % name], p.mean(1), var], 1)
+    return new
+
+
+class KPCNInterface(BaseInterface):
+    def __init__(self, models, optims, loss_funcs, args, visual=False, use_llpm_buf=False, manif_learn=False,
+                 w_manif=0.1, train_branches=True, disentanglement_option="m11r11"):
+        if manif_learn:
+            assert "backbone_diffuse" in models, "argument `models` dictionary should contain `'backbone_diffuse'` key."
+            assert "backbone_specular" in models, "argument `models` dictionary should contain `'backbone_specular'` key."
+        assert "dncnn" in models, "argument `models` dictionary should contain `'dncnn'` key."
+        if train_branches:
+            assert "l_diffuse" in loss_funcs
+            assert "l_specular" in loss_funcs
+        if manif_learn:
+            assert "l_manif" in loss_funcs
+        assert "l_recon" in loss_funcs
+        assert "l_test" in loss_funcs
+        assert disentanglement_option in _DISENTANGLE
+        super().__init__(models, optims, loss_funcs, args, visual, use_llpm_buf, manif_learn, w_manif)
+        self.train_branches = train_branches
+        self.disentanglement_option = disentanglement_option
+        self.grad_sync = None  # optional callable(models): data-parallel gradient all-reduce
+
+    def __str__(self):
+        return "KPCNInterface"
+
+    # ---- modes ---------------------------------------------------------------------------------
+    def to_train_mode(self):
+        for name, model in self.models.items():
+            model.train()
+            assert "optim_" + name in self.optims, "`optim_%s`: an optimization algorithm is not defined." % name
+
+    def to_eval_mode(self):
+        for model in self.models.values():
+            model.eval()
+        self.m_losses["m_val"] = torch.tensor(0.0)
+
+    def preprocess(self, batch=None):
+        for key in ("target_total", "target_diffuse", "target_specular", "kpcn_diffuse_in", "kpcn_specular_in",
+                    "kpcn_diffuse_buffer", "kpcn_specular_buffer", "kpcn_albedo"):
+            assert key in batch
+        if self.use_llpm_buf:
+            assert "paths" in batch
+        self.iters += 1
+
+    # ---- forward pieces ------------------------------------------------------------------------
+    def _manifold_forward(self, batch):
+        return {"diffuse": self.models["backbone_diffuse"](batch),
+                "specular": self.models["backbone_specular"](batch)}
+
+    def _regress_forward(self, batch):
+        return self.models["dncnn"](batch)
+
+    def _dump_pbuffers(self, p_buffers):
+        """Every 1000 iterations the reference writes a PNG of the first 3 embedding channels
+        (interfaces.py:130-137).  Kept as a best-effort side effect."""
+        out_dir = "../LLPM_results"
+        if not os.path.isdir(out_dir):
+            return
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            return
+        for name in ("diffuse", "specular"):
+            img = p_buffers[name].detach()[0, :, :3].mean(0).clamp(0.0, 1.0).permute(1, 2, 0).cpu().numpy()
+            plt.imsave("%s/pbuf_%s_%s.png" % (out_dir, self.args.model_name, name), img)
+
+    def _split(self, p_buffers):
+        """-> (p_buffers fed to the regression, p_buffers fed to the manifold loss)   (:139-163)"""
+        assert p_buffers["diffuse"].shape[2] >= 2
+        opt = self.disentanglement_option
+        reg = _half(p_buffers, lo=True) if opt in ("m10r01", "m11r01") else p_buffers
+        man = _half(p_buffers, lo=False) if opt in ("m10r01", "m10r11") else p_buffers
+        return reg, man
+
+    # ---- one optimisation step -----------------------------------------------------------------
+    def train_batch(self, batch, grad_hook_mode=False):
+        out_manif = None
+        if self.use_llpm_buf:
+            self.models["backbone_diffuse"].zero_grad()
+            self.models["backbone_specular"].zero_grad()
+            p_buffers = self._manifold_forward(batch)
+            if self.iters % 1000 == 1:
+                self._dump_pbuffers(p_buffers)
+            p_reg, out_manif = self._split(p_buffers)
+            batch = _with_pbuffer(batch, p_reg)
+        self.models["dncnn"].zero_grad()
+        out = self._regress_forward(batch)
+        loss_dict = self._backward(batch, out, out_manif)
+        if grad_hook_mode:  # gradients only; no logging, no parameter update
+            return
+        self._logging(loss_dict)
+        self._optimization()
+
+    def _backward(self, batch, out, p_buffers):
+        assert "radiance" in out and "diffuse" in out and "specular" in out
+        total, diffuse, specular = out["radiance"], out["diffuse"], out["specular"]
+        losses = {}
+        tgt_total = crop_like(batch["target_total"], total)
+        if self.train_branches:
+            branch_loss = {}
+            for name, pred in (("diffuse", diffuse), ("specular", specular)):
+                tgt = crop_like(batch["target_" + name], pred)
+                loss = self.loss_funcs["l_" + name](pred, tgt)
+                if self.manif_learn:
+                    l_manif = self.loss_funcs["l_manif"](crop_like(p_buffers[name], pred), tgt)
+                    losses["l_manif_" + name] = l_manif.detach()
+                    # the reference adds in place AFTER taking `.detach()` of the branch loss, so the
+                    # logged l_diffuse / l_specular include the weighted manifold term (:221-232)
+                    loss = loss + l_manif * self.w_manif
+                losses["l_" + name] = loss.detach()
+                branch_loss[name] = loss
+            branch_loss["diffuse"].backward()
+            branch_loss["specular"].backward()
+            with torch.no_grad():
+                losses["l_total"] = self.loss_funcs["l_recon"](total, tgt_total).detach()
+        else:
+            l_total = self.loss_funcs["l_recon"](total, tgt_total)
+            losses["l_total"] = l_total.detach()
+            l_total.backward()
+        with torch.no_grad():
+            losses["rmse"] = self.loss_funcs["l_test"](total, tgt_total).detach()
+        # keep the reference's key order (l_diffuse, l_specular, l_manif_*, l_total, rmse)
+        order = ["l_diffuse", "l_specular", "l_manif_diffuse", "l_manif_specular", "l_total", "rmse"]
+        return {k: losses[k] for k in order if k in losses}
+
+    def _logging(self, loss_dict):
+        keys = list(loss_dict)
+        vals = torch.stack([loss_dict[k].reshape(()) for k in keys])
+        finite = torch.isfinite(vals)
+        if not bool(finite.all()):  # the single host sync of the step
+            bad = keys[int((~finite).nonzero()[0])]
+            raise RuntimeError("%s: Non-finite loss at train time." % bad)
+        if self.grad_sync is not None:
+            self.grad_sync(self.models)
+        for model in self.models.values():
+            nn.utils.clip_grad_value_(model.parameters(), clip_value=1.0)
+        for k in keys:
+            if "m_" + k not in self.m_losses:
+                self.m_losses["m_" + k] = torch.tensor(0.0, device=loss_dict[k].device)
+            self.m_losses["m_" + k] += loss_dict[k]
+
+    def _optimization(self):
+        for name in self.models:
+            self.optims["optim_" + name].step()
+
+    # ---- validation ----------------------------------------------------------------------------
+    def validate_batch(self, batch):
+        p_buffers = None
+        if self.use_llpm_buf:
+            p_buffers = self._manifold_forward(batch)
+            assert p_buffers["diffuse"].shape[2] >= 2
+            if self.disentanglement_option in ("m10r01", "m11r01"):
+                p_buffers = _half(p_buffers, lo=True)
+            batch = _with_pbuffer(batch, p_buffers)
+        out = self._regress_forward(batch)
+        tgt_total = crop_like(batch["target_total"], out["radiance"])
+        l_total = self.loss_funcs["l_test"](out["radiance"], tgt_total)
+        if self.m_losses["m_val"].device != l_total.device:
+            self.m_losses["m_val"] = self.m_losses["m_val"].to(l_total.device)
+        self.m_losses["m_val"] += l_total.detach()
+        return out["radiance"], p_buffers
+
+    def get_epoch_summary(self, mode, norm):
+        if mode == "train":
+            print("[][][]", end=" ")
+            for key in self.m_losses:
+                if key == "m_val":
+                    continue
+                print("%s: %.3fE-3" % (key, self.m_losses[key] / (norm * 2) * 1000), end="\t")
+                self.m_losses[key] = torch.tensor(0.0, device=self.m_losses[key].device)
+            print("")
+            return -1.0
+        return self.m_losses["m_val"].item() / (norm * 2)

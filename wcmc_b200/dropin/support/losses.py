@@ -1,0 +1,101 @@
+"""B200 drop-in for the hot-path losses of /root/reference/support/losses.py.
+
+FeatureMSE (path disentangling loss, losses.py:9-113), GlobalRelativeSimilarityLoss (:116-211) and
+RelativeMSE (:245-264).  RNG contract kept from the reference: the pairing permutations come from
+the CPU default generator, `randperm(S*H*W)` then `randperm(B*S*H*W)` per call (losses.py:35, :50),
+so a seeded run pairs exactly the same samples as the reference.
+"""
+import math
+
+import torch
+
+__all__ = ["GlobalRelativeSimilarityLoss", "FeatureMSE", "RelativeMSE"]
+
+
+def _tonemap_gamma(img):
+    img = torch.clamp(img, min=0)
+    return (img / (1 + img)) ** 0.454545
+
+
+def _rows(p_buffer, t):
+    """(B,S,C,H,W), tone-mapped ref (B,3,H,W) -> rows (B, S*H*W, C) and (B, S*H*W, 3), (s,h,w) order."""
+    b, s, c, h, w = p_buffer.shape
+    r = t.permute(0, 2, 3, 1).unsqueeze(1).expand(b, s, h, w, 3).reshape(b, s * h * w, 3)
+    p = p_buffer.permute(0, 1, 3, 4, 2).reshape(b, s * h * w, c)
+    return p, r
+
+
+def _displacement(p, r, idx, dim):
+    idx = idx.to(p.device, non_blocking=True)
+    d_p = 0.5 * (p - p.index_select(dim, idx)).pow(2).sum(-1)
+    d_r = 0.5 * (r - r.index_select(dim, idx)).pow(2).sum(-1)
+    return d_p - d_r
+
+
+def _check_finite(*tensors):
+    ok = torch.stack([torch.isfinite(t).all() for t in tensors]).all()
+    if not bool(ok):
+        raise RuntimeError("Infinite loss at train time.")
+
+
+class FeatureMSE(torch.nn.Module):
+    """Path disentangling loss: for random sample pairs (i, pi(i)) penalise
+    (1/2|p_i - p_j|^2 - 1/2|t_i - t_j|^2)^2, once with pairs inside each patch and (non_local)
+    once with pairs across the whole batch."""
+
+    def __init__(self, color="rgb", non_local=True):
+        super().__init__()
+        if color != "rgb":
+            raise NotImplementedError("color='hls' is never selected by the reference scripts")
+        self.color = color
+        self.non_local = non_local
+        print("FeatureMSE locality: %s" % ("Non-local" if non_local else "Local"))
+
+    def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
+        b, s, c, h, w = p_buffer.shape
+        t = _tonemap_gamma(ref)
+        _check_finite(p_buffer, t)
+        p, r = _rows(p_buffer, t)
+        if idx_patch is None:
+            idx_patch = torch.randperm(s * h * w)
+        loss_p = 0.5 * _displacement(p, r, idx_patch, 1).pow(2).mean()
+        if not self.non_local:
+            return loss_p + loss_p
+        if idx_batch is None:
+            idx_batch = torch.randperm(b * s * h * w)
+        loss_b = 0.5 * _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0).pow(2).mean()
+        return loss_p + loss_b
+
+
+class GlobalRelativeSimilarityLoss(torch.nn.Module):
+    """(LSE(alpha * [d_p, d_b, -d_p, -d_b, 0]) - log(1 + 4N)) / sqrt(alpha)   (losses.py:185-211)."""
+
+    def __init__(self, alpha=2, color="rgb"):
+        super().__init__()
+        self.color = color
+        self.alpha = alpha
+
+    def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
+        _check_finite(p_buffer, ref)
+        b, s, c, h, w = p_buffer.shape
+        p, r = _rows(p_buffer, _tonemap_gamma(ref))
+        if idx_patch is None:
+            idx_patch = torch.randperm(s * h * w)
+        if idx_batch is None:
+            idx_batch = torch.randperm(b * s * h * w)
+        d_p = _displacement(p, r, idx_patch, 1).reshape(-1)
+        d_b = _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0)
+        zero = torch.zeros(1, dtype=p.dtype, device=p.device)
+        ex = self.alpha * torch.cat([d_p, d_b, -d_p, -d_b, zero], 0)
+        return (torch.logsumexp(ex, 0) - math.log(1 + 4 * b * s * h * w)) / math.sqrt(self.alpha)
+
+
+class RelativeMSE(torch.nn.Module):
+    """0.5 * mean((im - ref)^2 / (ref^2 + eps))   (losses.py:245-264)."""
+
+    def __init__(self, eps=1e-2):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, im, ref):
+        return 0.5 * torch.mean((im - ref) ** 2 / (ref ** 2 + self.eps))

@@ -25,7 +25,7 @@ SIGNATURES = {
     "wcmc_init": (c_int, [c_int]),
     "wcmc_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "wcmc_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
-    "wcmc_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
                     + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
@@ -34,11 +34,58 @@ SIGNATURES = {
     "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
     "wcmc_kernel_apply_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "wcmc_maxpool2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
+    "wcmc_maxpool2_bwd": (c_int, [c_void_p, c_int, c_int] * 4 + [c_int] * 4 + [c_void_p]),
+    "wcmc_upsample2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
+    "wcmc_upsample2_bwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
+    "wcmc_spp_reduce": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_float, c_void_p]),
+    "wcmc_spp_broadcast": (c_int, [c_void_p, c_int, c_int] * 3 + [c_int] * 4 + [c_float, c_void_p]),
+    "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_void_p]),
 }
 
 
 class WcmcError(RuntimeError):
     pass
+
+
+# ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
+LAUNCHES = {"count": 0}
+_profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2}
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """-> {name: (n_calls, total_ms, total_algorithmic_work)}; synchronises the device."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, work, e0, e1 in rec or []:
+        n, ms, wk = out.get(name, (0, 0.0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1), wk + work)
+    return out
+
+
+def _run(fn, what, work, *args):
+    """Calls one C-ABI entry point; counts its kernel launches; optionally brackets it with CUDA
+    events on the launching stream (bench.py's live per-kernel timing)."""
+    LAUNCHES["count"] += _KERNELS_PER_CALL.get(what, 1)
+    if _profile is None:
+        rc = fn(*args)
+    else:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.append((what, work, e0, e1))
+    if rc != 0:
+        raise WcmcError("%s failed (%d): %s" % (what, rc, load().wcmc_last_error().decode()))
 
 
 def load():
@@ -99,8 +146,9 @@ def nchw_to_nhwc(src, dst=None, dst_coff=0, c_fill=None):
     if dst is None:
         dst = torch.empty((n, h, w, c_fill), dtype=torch.bfloat16, device=src.device)
     assert dst.dtype == torch.bfloat16 and dst.is_contiguous() and dst.shape[:3] == (n, h, w)
-    _check(lib.wcmc_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.data_ptr(), n, c, h, w, dst.shape[3], dst_coff,
-                                          c_fill, _stream()), "nchw_f32_to_nhwc_bf16")
+    _run(lib.wcmc_nchw_f32_to_nhwc_bf16, "nchw_f32_to_nhwc_bf16", src.numel() * 4.0 + n * h * w * c_fill * 2.0,
+         src.data_ptr(), dst.data_ptr(), n, c, h, w, dst.shape[3], dst_coff,
+                                          c_fill, _stream())
     return dst
 
 
@@ -112,13 +160,15 @@ def nhwc_to_nchw(src, c, src_coff=0, out=None, accumulate=False):
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
         accumulate = False
     assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, c, h, w)
-    _check(lib.wcmc_nhwc_bf16_to_nchw_f32(src.data_ptr(), out.data_ptr(), n, c, h, w, cs, src_coff,
-                                          int(accumulate), _stream()), "nhwc_bf16_to_nchw_f32")
+    _run(lib.wcmc_nhwc_bf16_to_nchw_f32, "nhwc_bf16_to_nchw_f32", out.numel() * 6.0,
+         src.data_ptr(), out.data_ptr(), n, c, h, w, cs, src_coff,
+                                          int(accumulate), _stream())
     return out
 
 
-def pack_weights(w, cout_p=None, cin_p=None, fwd=True, dgrad=True):
-    """torch (Cout,Cin,k,k) fp32 -> (fwd [cout_p,k*k,cin_p], dgrad [cin_p,k*k,cout_p]) bf16."""
+def pack_weights(w, bias=None, cout_p=None, cin_p=None, fwd=True, dgrad=True, want_bias=False):
+    """torch (Cout,Cin,k,k) fp32 -> (fwd [cout_p,k*k,cin_p], dgrad [cin_p,k*k,cout_p]) bf16
+    [, zero-padded fp32 bias [cout_p] when ``want_bias``]."""
     lib = init(w.device)
     w = w.detach()
     assert w.dtype == torch.float32
@@ -129,13 +179,20 @@ def pack_weights(w, cout_p=None, cin_p=None, fwd=True, dgrad=True):
     cin_p = cin_p or pad16(cin)
     f = torch.empty((cout_p, k * k, cin_p), dtype=torch.bfloat16, device=w.device) if fwd else None
     d = torch.empty((cin_p, k * k, cout_p), dtype=torch.bfloat16, device=w.device) if dgrad else None
-    _check(lib.wcmc_pack_weights(w.data_ptr(), _p(f), _p(d), cout, cin, k, cout_p, cin_p, _stream()),
-           "pack_weights")
+    bp = torch.empty((cout_p,), dtype=torch.float32, device=w.device) if want_bias else None
+    if bias is not None:
+        bias = bias.detach().contiguous()
+        assert bias.dtype == torch.float32 and bias.numel() == cout
+    _run(lib.wcmc_pack_weights, "pack_weights", w.numel() * 8.0,
+         w.data_ptr(), _p(bias), _p(f), _p(d), _p(bp), cout, cin, k, cout_p, cin_p,
+                                 _stream())
+    if want_bias:
+        return f, d, bp
     return f, d
 
 
 def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_fp32=False, x_coff=0, cin_p=None,
-           mask=None, mask_coff=0, slope=0.0, flags=0):
+           mask=None, mask_coff=0, slope=0.0, flags=0, cin=None, cout=None):
     """x (N,H,W,Cs) bf16 NHWC; w_packed (cout_p, k*k, cin_p) bf16; returns NHWC output."""
     lib = init(x.device)
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
@@ -154,10 +211,10 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_fp32=
         assert bias.dtype == torch.float32 and bias.numel() >= cout_p
     if mask is not None:
         assert mask.dtype == torch.bfloat16 and mask.is_contiguous() and tuple(mask.shape[:3]) == (n, ho, wo)
-    _check(lib.wcmc_conv2d(x.data_ptr(), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), cout_p, _p(bias),
+    _run(lib.wcmc_conv2d, "conv2d", 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
+         x.data_ptr(), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), cout_p, _p(bias),
                            ksize, pad, out.data_ptr(), out.shape[3], out_coff, int(out_fp32), act, _p(mask),
-                           0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream()),
-           "conv2d")
+                           0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream())
     return out
 
 
@@ -186,9 +243,10 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
     assert out.is_contiguous() and out.dtype == torch.float32
     need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
     ws = _workspace(need, x.device)
-    _check(lib.wcmc_conv2d_wgrad(x.data_ptr(), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), dy.shape[3], dy_coff,
+    _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", 2.0 * n * ho * wo * ksize * ksize * cin * cout,
+         x.data_ptr(), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), dy.shape[3], dy_coff,
                                  cout_p, ksize, pad, out.data_ptr(), cout, cin, int(accumulate), ws.data_ptr(),
-                                 ws.numel(), _stream()), "conv2d_wgrad")
+                                 ws.numel(), _stream())
     return out
 
 
@@ -199,8 +257,9 @@ def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False):
     if out is None:
         out = torch.empty((cout,), dtype=torch.float32, device=dy.device)
         accumulate = False
-    _check(lib.wcmc_bias_grad(dy.data_ptr(), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate),
-                              _stream()), "bias_grad")
+    _run(lib.wcmc_bias_grad, "bias_grad", npix * cout * 2.0,
+         dy.data_ptr(), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate),
+                              _stream())
     return out
 
 
@@ -213,8 +272,9 @@ def kernel_apply_fwd(logits_nhwc, data, ksize, want_stats=True):
     assert tuple(logits_nhwc.shape[:3]) == (n, h, w)
     out = torch.empty_like(data)
     stats = torch.empty((n, h, w, 2), dtype=torch.float32, device=data.device) if want_stats else None
-    _check(lib.wcmc_kernel_apply_fwd(logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
-                                     out.data_ptr(), _p(stats), n, c, h, w, ksize, _stream()), "kernel_apply_fwd")
+    _run(lib.wcmc_kernel_apply_fwd, "kernel_apply_fwd", n * h * w * (ksize * ksize * 4.0 + c * 8.0),
+         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
+                                     out.data_ptr(), _p(stats), n, c, h, w, ksize, _stream())
     return out, stats
 
 
@@ -225,7 +285,98 @@ def kernel_apply_bwd(logits_nhwc, data, out, stats, grad_out, ksize, dl_cs=None,
     assert grad_out.dtype == torch.float32
     dl_cs = dl_cs or logits_nhwc.shape[3]
     dl = torch.empty((n, h, w, dl_cs), dtype=torch.bfloat16 if bf16 else torch.float32, device=data.device)
-    _check(lib.wcmc_kernel_apply_bwd(logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
+    _run(lib.wcmc_kernel_apply_bwd, "kernel_apply_bwd", n * h * w * (ksize * ksize * (4.0 + (2.0 if bf16 else 4.0)) + c * 12.0 + 8.0),
+         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
                                      out.data_ptr(), stats.data_ptr(), grad_out.data_ptr(), dl.data_ptr(), dl_cs,
-                                     int(bf16), n, c, h, w, ksize, _stream()), "kernel_apply_bwd")
+                                     int(bf16), n, c, h, w, ksize, _stream())
     return dl
+
+
+# ---- NHWC bf16 glue (PathNet / U-Net); tensors are (.., Cs) bf16 contiguous, slices by (coff, C) ----
+def _nhwc(t):
+    assert t.dtype == torch.bfloat16 and t.is_contiguous(), "expected contiguous bf16 NHWC tensor"
+    return t
+
+
+def maxpool2_fwd(x, c, x_coff=0, out=None, out_coff=0):
+    lib = init(x.device)
+    n, h, w, xcs = _nhwc(x).shape
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    _run(lib.wcmc_maxpool2_fwd, "maxpool2_fwd", 0.0,
+         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h, w,
+                                 c, _stream())
+    return out
+
+
+def maxpool2_bwd(x, dy, c, x_coff=0, dy_coff=0, add=None, add_coff=0, out=None, out_coff=0):
+    lib = init(x.device)
+    n, h, w, xcs = _nhwc(x).shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _run(lib.wcmc_maxpool2_bwd, "maxpool2_bwd", 0.0,
+         x.data_ptr(), xcs, x_coff, _nhwc(dy).data_ptr(), dy.shape[3], dy_coff, _p(add),
+                                 0 if add is None else add.shape[3], add_coff, _nhwc(out).data_ptr(), out.shape[3],
+                                 out_coff, n, h, w, c, _stream())
+    return out
+
+
+def upsample2_fwd(x, c, x_coff=0, out=None, out_coff=0):
+    lib = init(x.device)
+    n, h, w, xcs = _nhwc(x).shape
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    _run(lib.wcmc_upsample2_fwd, "upsample2_fwd", 0.0,
+         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h, w,
+                                  c, _stream())
+    return out
+
+
+def upsample2_bwd(dy, c, dy_coff=0, out=None, out_coff=0):
+    lib = init(dy.device)
+    n, hh, ww, dcs = _nhwc(dy).shape
+    h, w = hh // 2, ww // 2
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
+    _run(lib.wcmc_upsample2_bwd, "upsample2_bwd", 0.0,
+         dy.data_ptr(), dcs, dy_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h,
+                                  w, c, _stream())
+    return out
+
+
+def spp_reduce(x, b, s, c, scale, x_coff=0, out=None, out_coff=0):
+    """x (B*S,H,W,Cs) -> out (B,H,W,.) = scale * sum over S."""
+    lib = init(x.device)
+    bs, h, w, xcs = _nhwc(x).shape
+    assert bs == b * s
+    if out is None:
+        out = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _run(lib.wcmc_spp_reduce, "spp_reduce", 0.0,
+         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, b, s,
+                               h * w, c, float(scale), _stream())
+    return out
+
+
+def spp_broadcast(x, b, s, c, scale=1.0, x_coff=0, add=None, add_coff=0, out=None, out_coff=0):
+    """out (B*S,H,W,.) slice = (add or 0) + scale * x (B,H,W,.) broadcast over S."""
+    lib = init(x.device)
+    bb, h, w, xcs = _nhwc(x).shape
+    assert bb == b
+    if out is None:
+        out = torch.empty((b * s, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _run(lib.wcmc_spp_broadcast, "spp_broadcast", 0.0,
+         x.data_ptr(), xcs, x_coff, _p(add), 0 if add is None else add.shape[3], add_coff,
+                                  _nhwc(out).data_ptr(), out.shape[3], out_coff, b, s, h * w, c, float(scale),
+                                  _stream())
+    return out
+
+
+def act_bwd(dy, y, c, act, slope=0.01, dy_coff=0, y_coff=0, out=None, out_coff=0):
+    lib = init(dy.device)
+    npix = dy.shape[0] * dy.shape[1] * dy.shape[2]
+    if out is None:
+        out = torch.empty(tuple(dy.shape[:3]) + (c,), dtype=torch.bfloat16, device=dy.device)
+    _run(lib.wcmc_act_bwd, "act_bwd", 0.0,
+         _nhwc(dy).data_ptr(), dy.shape[3], dy_coff, _nhwc(y).data_ptr(), y.shape[3], y_coff,
+                            _nhwc(out).data_ptr(), out.shape[3], out_coff, npix, c, act, float(slope), _stream())
+    return out

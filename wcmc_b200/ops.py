@@ -1,0 +1,362 @@
+"""Host-side operators of the B200 backend: autograd Functions that drive libwcmc.so.
+
+Public tensors stay in the reference's contract (NCHW fp32, `support/datasets.py:760-793`);
+inside a Function everything is NHWC bf16 with channels padded to 16 and "concatenation" is a
+channel-slice write (see include/wcmc.h).  Three fused operators cover the hot path:
+
+  ConvChainFn    sbmc.modules.ConvChain                       
+  KPCNBranchFn   ConvChain(9 x 5x5) -> softmax -> 21x21 kernel-apply   (sbmc.KPCN branch, A.2/A.4)
+  PathNetFn      embedding MLP -> spp mean -> U-Net -> broadcast -> final MLP
+                 (/root/reference/support/networks.py:29-42)
+  AutoencoderFn  the U-Net alone (sbmc.modules.Autoencoder, A.3)
+
+Precision policy: bf16 operands, fp32 accumulation (TMEM), fp32 master weights / optimiser, fp32
+logits + softmax + kernel-apply, fp32 PathNet output; gradients travel in bf16 between layers and
+are accumulated in fp32.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib
+
+ACT = {"linear": 0, None: 0, "relu": 1, "leaky_relu": 2}
+LEAKY_SLOPE = 0.01
+
+
+@dataclass
+class LayerSpec:
+    cin: int
+    cout: int
+    ksize: int
+    pad: int
+    act: int  # 0 linear, 1 relu, 2 leaky
+
+    @property
+    def cin_p(self):
+        return lib.pad16(self.cin)
+
+    @property
+    def cout_p(self):
+        return lib.pad16(self.cout)
+
+
+@dataclass
+class Slice:
+    """Channel slice [coff, coff+c) of an NHWC bf16 (or fp32) tensor."""
+    t: torch.Tensor
+    coff: int
+    c: int
+
+
+def pack_chain(layers: List[LayerSpec], params, need_dgrad=True):
+    """params = [w0, b0, w1, b1, ...] (torch layout fp32) -> [(w_fwd, w_dgrad, bias_p)]."""
+    packed = []
+    for i, l in enumerate(layers):
+        w, b = params[2 * i], params[2 * i + 1]
+        packed.append(lib.pack_weights(w, b, cout_p=l.cout_p, cin_p=l.cin_p, dgrad=need_dgrad, want_bias=True))
+    return packed
+
+
+def chain_forward(x: Slice, layers, packed, out: Optional[Slice] = None, last_fp32=False):
+    """Runs the conv stack; returns the list of activations [x, y0, y1, ...] as Slices."""
+    acts = [x]
+    cur = x
+    for i, l in enumerate(layers):
+        wf, _, bp = packed[i]
+        last = i == len(layers) - 1
+        assert cur.c == l.cin, "chain input has %d channels, layer %d expects %d" % (cur.c, i, l.cin)
+        if last and out is not None:
+            y = lib.conv2d(cur.t, wf, bp, l.ksize, l.pad, act=l.act, slope=LEAKY_SLOPE, x_coff=cur.coff, out=out.t,
+                           out_coff=out.coff, out_fp32=out.t.dtype == torch.float32, cin=l.cin, cout=l.cout)
+            cur = Slice(y, out.coff, l.cout)
+        else:
+            y = lib.conv2d(cur.t, wf, bp, l.ksize, l.pad, act=l.act, slope=LEAKY_SLOPE, x_coff=cur.coff,
+                           out_fp32=last and last_fp32, cin=l.cin, cout=l.cout)
+            cur = Slice(y, 0, l.cout)
+        acts.append(cur)
+    return acts
+
+
+def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=True):
+    """dz = gradient w.r.t. the PRE-activation output of the last layer (bf16 NHWC slice).
+    Returns (dx Slice or None, [dw0, db0, dw1, db1, ...])."""
+    grads = [None] * (2 * len(layers))
+    for i in range(len(layers) - 1, -1, -1):
+        l = layers[i]
+        xin = acts[i]
+        if want_param_grads:
+            grads[2 * i] = lib.conv2d_wgrad(xin.t, dz.t, l.cout, l.cin, l.ksize, l.pad, l.cin_p, l.cout_p,
+                                            x_coff=xin.coff, dy_coff=dz.coff)
+            grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff)
+        if i == 0 and not need_dx:
+            return None, grads
+        wd = packed[i][1]
+        mask = None
+        slope = 0.0
+        if i > 0 and layers[i - 1].act != 0:
+            mask = xin
+            slope = LEAKY_SLOPE if layers[i - 1].act == 2 else 0.0
+        d = lib.conv2d(dz.t, wd, None, l.ksize, l.ksize - 1 - l.pad, act=0, x_coff=dz.coff,
+                       mask=None if mask is None else mask.t, mask_coff=0 if mask is None else mask.coff,
+                       slope=slope, cin=l.cout, cout=l.cin)
+        dz = Slice(d, 0, l.cin)
+    return dz, grads
+
+
+def _to_nhwc(x, c_fill=None):
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    return Slice(lib.nchw_to_nhwc(x, c_fill=c_fill), 0, x.shape[1])
+
+
+def _grad_nhwc(g, c_fill):
+    """fp32 NCHW gradient -> bf16 NHWC (channels padded with zeros)."""
+    return _to_nhwc(g, c_fill)
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvChain
+# ------------------------------------------------------------------------------------------------
+class ConvChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, layers, *params):
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        packed = pack_chain(layers, params, need_dgrad=need)
+        xin = _to_nhwc(x, layers[0].cin_p)
+        acts = chain_forward(xin, layers, packed)
+        y = acts[-1]
+        out = lib.nhwc_to_nchw(y.t, layers[-1].cout, y.coff)
+        ctx.layers = layers
+        ctx.need_dx = x.requires_grad
+        if need:
+            ctx.acts = acts
+            ctx.packed = packed
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        layers = ctx.layers
+        last = layers[-1]
+        dy = _grad_nhwc(g, last.cout_p)
+        dz = _act_bwd_full(dy, ctx.acts[-1], last)
+        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx)
+        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff) if dx is not None else None
+        ctx.acts = ctx.packed = None
+        return (gx, None) + tuple(grads)
+
+
+def _act_bwd_full(dy: Slice, y: Slice, layer: LayerSpec):
+    """dy covers the padded channel range of `layer`'s output; applies the output activation's
+    derivative (no-op for linear)."""
+    if layer.act == 0:
+        return dy
+    d = lib.act_bwd(dy.t, y.t, layer.cout_p, layer.act, LEAKY_SLOPE, dy_coff=dy.coff, y_coff=y.coff)
+    return Slice(d, 0, dy.c)
+
+
+# ------------------------------------------------------------------------------------------------
+# KPCN branch: conv chain -> softmax -> kernel apply
+# ------------------------------------------------------------------------------------------------
+class KPCNBranchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, data, ksize, layers, *params):
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        packed = pack_chain(layers, params, need_dgrad=need)
+        xin = _to_nhwc(x, layers[0].cin_p)
+        acts = chain_forward(xin, layers, packed, last_fp32=True)
+        logits = acts[-1].t  # (N,Ho,Wo,cout_p) fp32
+        data = data.contiguous().float()
+        assert tuple(data.shape[-2:]) == tuple(logits.shape[1:3]), "data and kernels must share spatial size"
+        out, stats = lib.kernel_apply_fwd(logits, data, ksize, want_stats=need)
+        ctx.layers, ctx.ksize, ctx.need_dx = layers, ksize, x.requires_grad
+        if need:
+            ctx.acts, ctx.packed, ctx.aux = acts, packed, (data, stats)
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        layers = ctx.layers
+        data, stats = ctx.aux
+        (out,) = ctx.saved_tensors
+        logits = ctx.acts[-1].t
+        dl = lib.kernel_apply_bwd(logits, data, out, stats, g.contiguous().float(), ctx.ksize,
+                                  dl_cs=layers[-1].cout_p, bf16=True)
+        dz = Slice(dl, 0, layers[-1].cout)
+        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx)
+        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff) if dx is not None else None
+        ctx.acts = ctx.packed = ctx.aux = None
+        return (gx, None, None, None) + tuple(grads)
+
+
+class KernelApplyFn(torch.autograd.Function):
+    """Stand-alone softmax + kernel-apply on an NCHW logits tensor (module-level API)."""
+
+    @staticmethod
+    def forward(ctx, data, kernels, ksize):
+        n, k2, h, w = kernels.shape
+        cs = (k2 + 7) // 8 * 8
+        logits = torch.zeros((n, h, w, cs), dtype=torch.float32, device=kernels.device)
+        logits[..., :k2] = kernels.permute(0, 2, 3, 1)
+        data = data.contiguous().float()
+        need = torch.is_grad_enabled() and kernels.requires_grad
+        out, stats = lib.kernel_apply_fwd(logits, data, ksize, want_stats=need)
+        ctx.k2 = k2
+        ctx.ksize = ksize
+        if need:
+            ctx.save_for_backward(logits, data, out, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, data, out, stats = ctx.saved_tensors
+        dl = lib.kernel_apply_bwd(logits, data, out, stats, g.contiguous().float(), ctx.ksize, bf16=False)
+        return None, dl[..., :ctx.k2].permute(0, 3, 1, 2), None
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net (sbmc.modules.Autoencoder) on NHWC bf16 buffers
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class UNetSpec:
+    """One level of the recursive U-Net: `left` chain, then (unless last) pool -> next -> up ->
+    cat([up, left]) -> `right` chain.  Parameter order: left, next..., right."""
+    left: List[LayerSpec]
+    right: Optional[List[LayerSpec]] = None
+    nxt: Optional["UNetSpec"] = None
+
+    def n_params(self):
+        n = 2 * len(self.left)
+        if self.nxt is not None:
+            n += self.nxt.n_params() + 2 * len(self.right)
+        return n
+
+
+def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True):
+    """Returns (output Slice, ctx).  params is the flat [w,b,...] list in spec order."""
+    nl = 2 * len(spec.left)
+    p_left = pack_chain(spec.left, params[:nl], need_dgrad)
+    if spec.nxt is None:
+        acts = chain_forward(x, spec.left, p_left)
+        return acts[-1], dict(acts_left=acts, p_left=p_left)
+    n, h, w, _ = x.t.shape
+    assert h % 2 == 0 and w % 2 == 0, "U-Net levels need even spatial sizes (got %dx%d)" % (h, w)
+    c_left = spec.left[-1].cout
+    c_up = spec.right[0].cin - c_left
+    assert c_up % 8 == 0 and c_left % 8 == 0
+    cat = torch.empty((n, h, w, c_up + c_left), dtype=torch.bfloat16, device=x.t.device)
+    acts_left = chain_forward(x, spec.left, p_left, out=Slice(cat, c_up, c_left))
+    pooled = lib.maxpool2_fwd(cat, c_left, x_coff=c_up)
+    nn_ = spec.nxt.n_params()
+    y_next, ctx_next = unet_forward(spec.nxt, Slice(pooled, 0, c_left), params[nl:nl + nn_], need_dgrad)
+    assert y_next.c == c_up
+    lib.upsample2_fwd(y_next.t, c_up, x_coff=y_next.coff, out=cat, out_coff=0)
+    p_right = pack_chain(spec.right, params[nl + nn_:], need_dgrad)
+    acts_right = chain_forward(Slice(cat, 0, c_up + c_left), spec.right, p_right)
+    ctx = dict(acts_left=acts_left, p_left=p_left, cat=cat, pooled=pooled, ctx_next=ctx_next, y_next=y_next,
+               acts_right=acts_right, p_right=p_right, c_up=c_up, c_left=c_left)
+    return acts_right[-1], ctx
+
+
+def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True):
+    """dy = gradient w.r.t. the (post-activation) output.  Returns (dx Slice, flat grads)."""
+    if spec.nxt is None:
+        dz = _act_bwd_full(dy, ctx["acts_left"][-1], spec.left[-1])
+        return chain_backward(dz, ctx["acts_left"], spec.left, ctx["p_left"], need_dx)
+    c_up, c_left = ctx["c_up"], ctx["c_left"]
+    dz = _act_bwd_full(dy, ctx["acts_right"][-1], spec.right[-1])
+    d_cat, g_right = chain_backward(dz, ctx["acts_right"], spec.right, ctx["p_right"], True)
+    d_up = lib.upsample2_bwd(d_cat.t, c_up, dy_coff=d_cat.coff)
+    d_pool, g_next = unet_backward(spec.nxt, ctx["ctx_next"], Slice(d_up, 0, c_up), True)
+    d_left = lib.maxpool2_bwd(ctx["cat"], d_pool.t, c_left, x_coff=c_up, dy_coff=d_pool.coff, add=d_cat.t,
+                              add_coff=d_cat.coff + c_up)
+    left_out = ctx["acts_left"][-1]
+    dzl = _act_bwd_full(Slice(d_left, 0, c_left), left_out, spec.left[-1])
+    dx, g_left = chain_backward(dzl, ctx["acts_left"], spec.left, ctx["p_left"], need_dx)
+    return dx, g_left + g_next + g_right
+
+
+class AutoencoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        xin = _to_nhwc(x, spec.left[0].cin_p)
+        y, uctx = unet_forward(spec, xin, list(params), need)
+        ctx.spec, ctx.need_dx, ctx.cin = spec, x.requires_grad, x.shape[1]
+        ctx.uctx = uctx if need else None
+        return lib.nhwc_to_nchw(y.t, y.c, y.coff)
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        c_out = g.shape[1]
+        dy = _grad_nhwc(g, lib.pad16(c_out))
+        dx, grads = unet_backward(spec, ctx.uctx, dy, ctx.need_dx)
+        gx = lib.nhwc_to_nchw(dx.t, ctx.cin, dx.coff) if dx is not None else None
+        ctx.uctx = None
+        return (gx, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# PathNet (support/networks.py:29-42)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PathNetSpec:
+    embedding: List[LayerSpec]
+    unet: UNetSpec
+    final: List[LayerSpec]
+
+
+class PathNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, paths, spec, *params):
+        b, s, nf, h, w = paths.shape
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        ne, nu = 2 * len(spec.embedding), spec.unet.n_params()
+        p_emb = pack_chain(spec.embedding, params[:ne], need)
+        p_fin = pack_chain(spec.final, params[ne + nu:], need)
+        c_emb = spec.embedding[-1].cout
+        c_prop = spec.final[0].cin - c_emb
+        x = _to_nhwc(paths.reshape(b * s, nf, h, w), spec.embedding[0].cin_p)
+        both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=torch.bfloat16, device=paths.device)
+        acts_emb = chain_forward(x, spec.embedding, p_emb, out=Slice(both, 0, c_emb))
+        reduced = lib.spp_reduce(both, b, s, c_emb, 1.0 / s)
+        prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
+        assert prop.c == c_prop
+        lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
+        acts_fin = chain_forward(Slice(both, 0, c_emb + c_prop), spec.final, p_fin, last_fp32=True)
+        outc = spec.final[-1].cout
+        y = acts_fin[-1].t  # (B*S,H,W,outc_p) fp32
+        out = y[..., :outc].permute(0, 3, 1, 2).reshape(b, s, outc, h, w).contiguous()
+        ctx.spec, ctx.dims = spec, (b, s, h, w, c_emb, c_prop, outc)
+        if need:
+            ctx.saved = (acts_emb, p_emb, uctx, acts_fin, p_fin)
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        b, s, h, w, c_emb, c_prop, outc = ctx.dims
+        acts_emb, p_emb, uctx, acts_fin, p_fin = ctx.saved
+        (out,) = ctx.saved_tensors
+        last = spec.final[-1]
+        g = g.reshape(b * s, outc, h, w).float()
+        o = out.reshape(b * s, outc, h, w)
+        if last.act == 1:
+            g = g * (o > 0)
+        elif last.act == 2:
+            g = torch.where(o > 0, g, g * LEAKY_SLOPE)
+        dz = _grad_nhwc(g, last.cout_p)
+        d_both, g_fin = chain_backward(dz, acts_fin, spec.final, p_fin, True)
+        d_prop = lib.spp_reduce(d_both.t, b, s, c_prop, 1.0, x_coff=d_both.coff + c_emb)
+        d_red, g_unet = unet_backward(spec.unet, uctx, Slice(d_prop, 0, c_prop), True)
+        dz_emb = lib.spp_broadcast(d_red.t, b, s, c_emb, 1.0 / s, x_coff=d_red.coff, add=d_both.t,
+                                   add_coff=d_both.coff)
+        dze = _act_bwd_full(Slice(dz_emb, 0, c_emb), acts_emb[-1], spec.embedding[-1])
+        _, g_emb = chain_backward(dze, acts_emb, spec.embedding, p_emb, False)
+        ctx.saved = None
+        return (None, None) + tuple(g_emb) + tuple(g_unet) + tuple(g_fin)
