@@ -34,6 +34,11 @@ extern "C" {
 #define WCMC_ECUDA (-4)   /* CUDA runtime / driver error (message has the details) */
 #define WCMC_EWORKSPACE (-5)
 
+/* storage types of activations / packed weights / gradients */
+#define WCMC_BF16 0
+#define WCMC_F16 1
+#define WCMC_F32 2
+
 #define WCMC_ACT_LINEAR 0
 #define WCMC_ACT_RELU 1
 #define WCMC_ACT_LEAKY 2
@@ -44,19 +49,22 @@ const char* wcmc_version(void);
 int wcmc_init(int device);
 
 /* ---- layout conversion (boundary between torch NCHW fp32 tensors and the NHWC bf16 pipeline) --
- * dst[n,h,w,dst_coff+c] = bf16(src[n,c,h,w]) for c < C; channels C..c_fill-1 are written as 0. */
-int wcmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int dst_cs,
-                               int dst_coff, int c_fill, void* stream);
+ * dst[n,h,w,dst_coff+c] = half(src[n,c,h,w]) for c < C; channels C..c_fill-1 are written as 0.
+ * dst_dtype / src_dtype: WCMC_BF16 or WCMC_F16.  `scale` (device pointer to one float, may be
+ * NULL) multiplies every value: the backward pass keeps its 16-bit gradients multiplied by a
+ * per-call loss scale s (s on the way in, 1/s on the way out) so fp16 gradients never underflow. */
+int wcmc_nchw_f32_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int H, int W,
+                          int dst_cs, int dst_coff, int c_fill, const float* scale, void* stream);
 /* dst[n,c,h,w] (fp32, contiguous) (+)= src[n,h,w,src_coff+c] */
-int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int src_cs,
-                               int src_coff, int accumulate, void* stream);
+int wcmc_nhwc_to_nchw_f32(const void* src, int src_dtype, float* dst, int N, int C, int H, int W,
+                          int src_cs, int src_coff, int accumulate, const float* scale, void* stream);
 
 /* ---- weights: torch (Cout, Cin, k, k) fp32  ->  packed bf16 operands of the conv kernels ------
  * fwd  : dst[co][ky*k+kx][ci]            = w[co][ci][ky][kx]   (cout_p x k*k x cin_p, zero padded)
  * dgrad: dst[ci][(k-1-ky)*k+(k-1-kx)][co] = w[co][ci][ky][kx]  (cin_p  x k*k x cout_p)           */
 /* dst_bias[cout_p] = bias zero padded (bias may be NULL -> zeros); any dst may be NULL.        */
 int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* dst_dgrad,
-                      float* dst_bias, int cout, int cin, int ksize, int cout_p, int cin_p,
+                      float* dst_bias, int dtype, int cout, int cin, int ksize, int cout_p, int cin_p,
                       void* stream);
 
 /* ---- K1/K2: convolution forward / data gradient (tcgen05 implicit GEMM) -----------------------
@@ -64,14 +72,15 @@ int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* ds
  * /root/reference/support/networks.py:18-24 and by sbmc.KPCN, train_kpcn.py:213).
  *   y = act(conv(x, w) + bias) [* (mask > 0 ? 1 : slope)]
  * x: NHWC bf16 (N,H,W,x_cs), channels [x_coff, x_coff+cin_p); w_packed: see wcmc_pack_weights;
- * bias: fp32[cout_p] or NULL; y: NHWC (N,Ho,Wo,y_cs) bf16 or fp32 (y_fp32), channels
+ * x_dtype / w_dtype: WCMC_BF16 or WCMC_F16 and equal (tcgen05.mma kind::f16 traps on mixed formats);
+ * bias: fp32[cout_p] or NULL; y: NHWC (N,Ho,Wo,y_cs) in y_dtype (bf16 / f16 / f32), channels
  * [y_coff, y_coff+cout_p), Ho = H + 2*pad - ksize + 1.  mask (optional, NHWC bf16 with the
  * spatial size of y) fuses the activation derivative of the previous layer into a dgrad.
  * flags: 0 for production (test knobs: bits 4-5 force m tiles per region, bits 8-15 force the
  * n tile).                                                                                    */
-int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                const void* w_packed, int cout_p, const float* bias, int ksize, int pad, void* y,
-                int y_cs, int y_coff, int y_fp32, int act, const void* mask, int mask_cs,
+int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
+                void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask, int mask_cs,
                 int mask_coff, float slope, int flags, void* stream);
 
 /* ---- K3: convolution weight gradient (tcgen05, MN-major operands, split-K) --------------------
@@ -79,15 +88,16 @@ int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int ci
  * /root/reference/support/interfaces.py:237-238).
  *   dw[co][ci][ky][kx] (torch layout, fp32) (+)= sum_{n,oy,ox} dy[n,oy,ox,co] * x[n,oy+ky-pad,ox+kx-pad,ci]
  * x, dy: NHWC bf16 as for wcmc_conv2d (dy has the conv's OUTPUT spatial size).  workspace holds
- * the split-K partial sums; size it with wcmc_conv2d_wgrad_workspace().                         */
+ * the split-K partial sums; size it with wcmc_conv2d_wgrad_workspace().  `scale` (device float
+ * or NULL) multiplies the result (un-does the loss scale carried by dy).                        */
 size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, int cout_p, int ksize, int pad);
-int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                      const void* dy, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
-                      float* dw, int cout, int cin, int accumulate, void* workspace,
+int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                      const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
+                      float* dw, int cout, int cin, int accumulate, const float* scale, void* workspace,
                       size_t workspace_bytes, void* stream);
-/* db[co] (+)= sum over all pixels of dy[pix][dy_coff+co] */
-int wcmc_bias_grad(const void* dy, int npix, int dy_cs, int dy_coff, int cout, float* db,
-                   int accumulate, void* stream);
+/* db[co] (+)= scale * sum over all pixels of dy[pix][dy_coff+co]   (scale: device float or NULL) */
+int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs, int dy_coff, int cout, float* db,
+                   int accumulate, const float* scale, void* stream);
 
 /* ---- K4/K5: softmax + 21x21 kernel-apply (replaces sbmc.modules.KernelApply and the Halide
  * `kernel_weighting` op; called by sbmc.KPCN.forward) ------------
@@ -97,38 +107,41 @@ int wcmc_bias_grad(const void* dy, int npix, int dy_cs, int dy_coff, int cout, f
  * stats (N,H,W,2) fp32 receives (row max, 1/sum exp) for the backward pass (may be NULL).   */
 int wcmc_kernel_apply_fwd(const float* logits, int l_cs, const float* data, float* out,
                           float* stats, int N, int C, int H, int W, int ksize, void* stream);
-/* d_logits[n,y,x,k] = p_k * (sum_c g_c v_{c,k} - sum_c g_c out_c); written as NHWC
- * (N,H,W,dl_cs) in bf16 (dl_bf16) or fp32, channels k*k..dl_cs-1 zeroed.                      */
+/* d_logits[n,y,x,k] = scale * p_k * (sum_c g_c v_{c,k} - sum_c g_c out_c); written as NHWC
+ * (N,H,W,dl_cs) in dl_dtype (bf16 / f16 / f32), channels k*k..dl_cs-1 zeroed.                  */
 int wcmc_kernel_apply_bwd(const float* logits, int l_cs, const float* data, const float* out,
                           const float* stats, const float* grad_out, void* d_logits, int dl_cs,
-                          int dl_bf16, int N, int C, int H, int W, int ksize, void* stream);
+                          int dl_dtype, int N, int C, int H, int W, int ksize, const float* scale,
+                          void* stream);
 
 /* ---- NHWC bf16 glue of the path-embedding network (PathNet, /root/reference/support/
  * networks.py:29-42; U-Net = sbmc.modules.Autoencoder) ------------------
  * Every tensor is (pixels, channel stride cs, channel offset coff); C, cs, coff multiples of 8.
+ * `dtype` (WCMC_BF16 / WCMC_F16) is the storage type of every 16-bit tensor of the call
+ * (activations and gradients use the same type: the tensor cores do not mix f16 with bf16).
  * Writing into a channel slice of the consumer's buffer replaces torch.cat.                     */
 /* y (N,H/2,W/2) = 2x2 max pool of x (N,H,W)            (nn.MaxPool2d(2,2)) */
 int wcmc_maxpool2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int H,
-                      int W, int C, void* stream);
+                      int W, int C, int dtype, void* stream);
 /* dx (N,H,W) = (add or 0) + dy routed to the first maximum of each window (x = forward input) */
 int wcmc_maxpool2_bwd(const void* x, int x_cs, int x_coff, const void* dy, int dy_cs, int dy_coff,
                       const void* add, int add_cs, int add_coff, void* dx, int dx_cs, int dx_coff, int N,
-                      int H, int W, int C, void* stream);
+                      int H, int W, int C, int dtype, void* stream);
 /* y (N,2h,2w) = F.interpolate(x (N,h,w), scale 2, mode='bilinear', align_corners=False) */
 int wcmc_upsample2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int h,
-                       int w, int C, void* stream);
+                       int w, int C, int dtype, void* stream);
 int wcmc_upsample2_bwd(const void* dy, int dy_cs, int dy_coff, void* dx, int dx_cs, int dx_coff, int N,
-                       int h, int w, int C, void* stream);
+                       int h, int w, int C, int dtype, void* stream);
 /* y[b,hw,:] = scale * sum_s x[b,s,hw,:]      (mean over samples per pixel, networks.py:36) */
 int wcmc_spp_reduce(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int B, int S,
-                    int HW, int C, float scale, void* stream);
+                    int HW, int C, float scale, int dtype, void* stream);
 /* y[b,s,hw,:] = (add or 0)[b,s,hw,:] + scale * x[b,hw,:]   (broadcast over samples, networks.py:39) */
 int wcmc_spp_broadcast(const void* x, int x_cs, int x_coff, const void* add, int add_cs, int add_coff,
                        void* y, int y_cs, int y_coff, int B, int S, int HW, int C, float scale,
-                       void* stream);
+                       int dtype, void* stream);
 /* dz = dy * act'(y), y = activation output (act = WCMC_ACT_RELU / WCMC_ACT_LEAKY) */
 int wcmc_act_bwd(const void* dy, int dy_cs, int dy_coff, const void* y, int y_cs, int y_coff, void* dz,
-                 int dz_cs, int dz_coff, long npix, int C, int act, float slope, void* stream);
+                 int dz_cs, int dz_coff, long npix, int C, int act, float slope, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

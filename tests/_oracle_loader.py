@@ -30,3 +30,32 @@ def load_oracle():
                               PathNet=mod.PathNet)
     _cache["o"] = o
     return o
+
+
+def precision_matched(module, dtype):
+    """Makes an ORACLE module evaluate with the backend's storage precision: every Conv2d rounds its
+    input activation and its (effective) weight to `dtype` before an fp32 convolution -- exactly the
+    points where the CUDA path stores 16-bit tensors (biases, accumulation, logits, losses stay
+    fp32).  Gradients pass straight through the rounding.  Used to separate "the kernels compute the
+    wrong thing" from "a 16-bit forward flips a few ReLU masks" (precision policy)."""
+    import torch
+    import torch.nn.functional as F
+
+    def rnd(t):
+        return t + (t.to(dtype).to(t.dtype) - t).detach()
+
+    handles = []
+    for m in module.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            def fwd(x, m=m):
+                return F.conv2d(rnd(x), rnd(m.weight), m.bias, m.stride, m.padding)
+            m._orig_forward = m.forward
+            m.forward = fwd
+            handles.append(m)
+    return handles
+
+
+def restore_precision(handles):
+    for m in handles:
+        m.forward = m._orig_forward
+        del m._orig_forward

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -207,15 +208,17 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t lb
     d |= 2ull << 61;
     return d;
 }
-// Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate.
-//   [4,6) D fmt (1=f32) | [7,10) A fmt (1=bf16) | [10,13) B fmt | 15 A major | 16 B major
+// Instruction descriptor for kind::f16 (fp16 / bf16 inputs, independently per operand), fp32
+// accumulate.
+//   [4,6) D fmt (1=f32) | [7,10) A fmt (0=f16, 1=bf16) | [10,13) B fmt | 15 A major | 16 B major
 //   | [17,23) N>>3 | [24,29) M>>4      (major: 0 = K-major, 1 = MN-major)
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
-                                                             int b_mn_major) {
+// a_dtype / b_dtype use the WCMC_BF16 / WCMC_F16 codes of include/wcmc.h.
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major,
+                                                            int a_dtype, int b_dtype) {
     uint32_t d = 0;
     d |= 1u << 4;
-    d |= 1u << 7;
-    d |= 1u << 10;
+    d |= static_cast<uint32_t>(a_dtype == WCMC_BF16 ? 1 : 0) << 7;
+    d |= static_cast<uint32_t>(b_dtype == WCMC_BF16 ? 1 : 0) << 10;
     d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
     d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
     d |= static_cast<uint32_t>(N >> 3) << 17;
@@ -227,6 +230,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// dtype: WCMC_BF16 or WCMC_F16 (16-bit storage types)
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int dtype) {
+    return dtype == WCMC_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v, int dtype) {
+    if (dtype == WCMC_F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+// sign test that is valid for both 16-bit float formats: value > 0
+__device__ __forceinline__ bool h16_pos(uint32_t h) { return (h & 0x8000u) == 0 && (h & 0x7FFFu) != 0; }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -42,7 +42,8 @@ struct ConvParams {
     int mt, regions_x, regions_y, total_items;
     int halo_w, halo_h;
     void* out;
-    int out_cs, out_coff, out_fp32;
+    int out_cs, out_coff, out_dtype;
+    int x_dtype, w_dtype;
     const float* bias;
     int act;
     const __nv_bfloat16* mask;
@@ -142,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     } else if (warp == 2) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.nt, 0, 0);
+            const uint32_t idesc = make_idesc_f16(128, p.nt, 0, 0, p.x_dtype, p.w_dtype);
             const uint32_t sbo = static_cast<uint32_t>(p.halo_w * 128);
             int ps = 0, pph = 0, bs = 0, bph = 0, it = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -236,11 +237,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                         uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            f[2 * i] *= (bf16_lo(mw[i]) > 0.f) ? 1.f : p.slope;
-                            f[2 * i + 1] *= (bf16_hi(mw[i]) > 0.f) ? 1.f : p.slope;
+                            f[2 * i] *= h16_pos(mw[i] & 0xFFFFu) ? 1.f : p.slope;
+                            f[2 * i + 1] *= h16_pos(mw[i] >> 16) ? 1.f : p.slope;
                         }
                     }
-                    if (p.out_fp32) {
+                    if (p.out_dtype == WCMC_F32) {
                         float4* op = reinterpret_cast<float4*>(
                             static_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
 #pragma unroll
@@ -249,10 +250,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     } else {
                         uint4* op = reinterpret_cast<uint4*>(
                             static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
-                        op[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                           pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                        op[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                                           pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+                        const int dt = p.out_dtype;
+                        op[0] = make_uint4(pack_h2(f[0], f[1], dt), pack_h2(f[2], f[3], dt),
+                                           pack_h2(f[4], f[5], dt), pack_h2(f[6], f[7], dt));
+                        op[1] = make_uint4(pack_h2(f[8], f[9], dt), pack_h2(f[10], f[11], dt),
+                                           pack_h2(f[12], f[13], dt), pack_h2(f[14], f[15], dt));
                     }
                     }  // valid
                 }
@@ -278,12 +280,17 @@ static int pick_nt(int cout_p) {
     return 128;
 }
 
-extern "C" int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                           const void* w_packed, int cout_p, const float* bias, int ksize, int pad,
-                           void* y, int y_cs, int y_coff, int y_fp32, int act, const void* mask,
+extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                           const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
+                           void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
                            int mask_cs, int mask_coff, float slope, int flags, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "conv2d: ksize %d not in {1,3,5}", ksize);
+    WCMC_REQUIRE((x_dtype == WCMC_BF16 || x_dtype == WCMC_F16) && (w_dtype == WCMC_BF16 || w_dtype == WCMC_F16) &&
+                     (y_dtype == WCMC_BF16 || y_dtype == WCMC_F16 || y_dtype == WCMC_F32),
+                 WCMC_ESHAPE, "conv2d: bad dtypes (x %d, w %d, y %d)", x_dtype, w_dtype, y_dtype);
+    WCMC_REQUIRE(x_dtype == w_dtype, WCMC_ESHAPE,
+                 "conv2d: x and w must share one 16-bit format (tcgen05.mma kind::f16 traps on f16 x bf16)");
     WCMC_REQUIRE(pad >= 0 && pad < ksize, WCMC_ESHAPE, "conv2d: bad pad %d", pad);
     WCMC_REQUIRE(cin_p % 16 == 0 && cout_p % 16 == 0 && cin_p > 0 && cout_p > 0, WCMC_ESHAPE,
                  "conv2d: cin_p (%d) and cout_p (%d) must be positive multiples of 16", cin_p, cout_p);
@@ -321,7 +328,8 @@ extern "C" int wcmc_conv2d(const void* x, int N, int H, int W, int x_cs, int x_c
     p.total_items = N * p.regions_x * p.regions_y * p.n_tiles;
     p.halo_w = 8 * mt + ksize - 1;
     p.halo_h = 16 + ksize - 1;
-    p.out = y; p.out_cs = y_cs; p.out_coff = y_coff; p.out_fp32 = y_fp32;
+    p.out = y; p.out_cs = y_cs; p.out_coff = y_coff; p.out_dtype = y_dtype;
+    p.x_dtype = x_dtype; p.w_dtype = w_dtype;
     p.bias = bias; p.act = act;
     p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
     p.slope = slope; p.flags = flags;

@@ -38,6 +38,7 @@ struct WgradParams {
     int tiles_x, tiles_y, total_tiles;
     int halo_w, halo_h, b_plane;  // b_plane: bytes between the two 64-channel halo planes
     int a_planes, b_planes;
+    int x_dtype, dy_dtype;
     float* ws;
 };
 
@@ -106,7 +107,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.nt, 1, 1);
+            const uint32_t idesc = make_idesc_f16(128, p.nt, 1, 1, p.dy_dtype, p.x_dtype);
             const uint32_t b_sbo = static_cast<uint32_t>(p.halo_w * 128);
             int s = 0, ph = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -169,7 +170,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
 
 // out[co][ci][tap] (+)= sum_split ws[split][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int cout,
-                                    int cin, int taps, int cout_p, int cin_p, int accumulate) {
+                                    int cin, int taps, int cout_p, int cin_p, int accumulate,
+                                    const float* __restrict__ scale) {
+    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     const long total = static_cast<long>(cout) * cin * taps;
     const long slab = static_cast<long>(taps) * cout_p * cin_p;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -181,6 +184,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
         const float* src = ws + (static_cast<long>(tap) * cout_p + co) * cin_p + ci;
         float s = 0.f;
         for (int k = 0; k < nsplit; ++k) s += src[k * slab];
+        s *= sc;
         float* d = dw + (static_cast<long>(co) * cin + ci) * taps + tap;
         *d = accumulate ? (*d + s) : s;
     }
@@ -228,13 +232,18 @@ extern "C" size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, in
     return static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
 }
 
-extern "C" int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                                 const void* dy, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
-                                 float* dw, int cout, int cin, int accumulate, void* workspace,
+extern "C" int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                                 const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize,
+                                 int pad,
+                                 float* dw, int cout, int cin, int accumulate, const float* scale, void* workspace,
                                  size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "wgrad: ksize %d not in {1,3,5}", ksize);
     WCMC_REQUIRE(pad >= 0 && pad < ksize, WCMC_ESHAPE, "wgrad: bad pad %d", pad);
+    WCMC_REQUIRE((x_dtype == WCMC_BF16 || x_dtype == WCMC_F16) && (dy_dtype == WCMC_BF16 || dy_dtype == WCMC_F16),
+                 WCMC_ESHAPE, "wgrad: bad dtypes (x %d, dy %d)", x_dtype, dy_dtype);
+    WCMC_REQUIRE(x_dtype == dy_dtype, WCMC_ESHAPE,
+                 "wgrad: x and dy must share one 16-bit format (tcgen05.mma kind::f16 traps on f16 x bf16)");
     WCMC_REQUIRE(cin_p % 16 == 0 && cout_p % 16 == 0 && cin_p > 0 && cout_p > 0, WCMC_ESHAPE,
                  "wgrad: cin_p (%d) / cout_p (%d) must be positive multiples of 16", cin_p, cout_p);
     WCMC_REQUIRE(x_cs % 8 == 0 && x_coff % 8 == 0 && dy_cs % 8 == 0 && dy_coff % 8 == 0, WCMC_ESHAPE,
@@ -249,6 +258,7 @@ extern "C" int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, i
     WCMC_REQUIRE(workspace != nullptr && workspace_bytes >= need, WCMC_EWORKSPACE,
                  "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
     p.ws = static_cast<float*>(workspace);
+    p.x_dtype = x_dtype; p.dy_dtype = dy_dtype;
 
     CUtensorMap tmdy, tmx;
     {
@@ -283,7 +293,7 @@ extern "C" int wcmc_conv2d_wgrad(const void* x, int N, int H, int W, int x_cs, i
     long total = static_cast<long>(cout) * cin * p.taps;
     int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, p.nsplit, cout, cin, p.taps, cout_p, cin_p,
-                                                    accumulate);
+                                                    accumulate, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

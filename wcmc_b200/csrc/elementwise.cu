@@ -16,20 +16,21 @@ namespace wcmc {
 struct V8 {
     float f[8];
 };
-__device__ __forceinline__ V8 ld8(const __nv_bfloat16* p) {
+__device__ __forceinline__ V8 ld8(const __nv_bfloat16* p, int dt = WCMC_BF16) {
     uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     V8 v;
     uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        v.f[2 * i] = bf16_lo(w[i]);
-        v.f[2 * i + 1] = bf16_hi(w[i]);
+        float2 f = unpack_h2(w[i], dt);
+        v.f[2 * i] = f.x;
+        v.f[2 * i + 1] = f.y;
     }
     return v;
 }
-__device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v.f[0], v.f[1]), pack_bf16x2(v.f[2], v.f[3]),
-                                              pack_bf16x2(v.f[4], v.f[5]), pack_bf16x2(v.f[6], v.f[7]));
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v, int dt = WCMC_BF16) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_h2(v.f[0], v.f[1], dt), pack_h2(v.f[2], v.f[3], dt),
+                                              pack_h2(v.f[4], v.f[5], dt), pack_h2(v.f[6], v.f[7], dt));
 }
 
 #define WCMC_GRID_STRIDE(i, total)                                                          \
@@ -39,7 +40,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v) {
 // y[n,oy,ox,c] = max over the 2x2 window of x
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                     __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int N, int H, int W,
-                                    int C8) {
+                                    int C8, int dt) {
     const int Ho = H / 2, Wo = W / 2;
     const long total = static_cast<long>(N) * Ho * Wo * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -49,12 +50,12 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_c
         int oy = static_cast<int>((pix / Wo) % Ho);
         int n = static_cast<int>(pix / (static_cast<long>(Wo) * Ho));
         const __nv_bfloat16* p = x + ((static_cast<long>(n) * H + 2 * oy) * W + 2 * ox) * x_cs + x_coff + c;
-        V8 a = ld8(p), b = ld8(p + x_cs), d = ld8(p + static_cast<long>(W) * x_cs),
-           e = ld8(p + static_cast<long>(W) * x_cs + x_cs);
+        V8 a = ld8(p, dt), b = ld8(p + x_cs, dt), d = ld8(p + static_cast<long>(W) * x_cs, dt),
+           e = ld8(p + static_cast<long>(W) * x_cs + x_cs, dt);
         V8 r;
 #pragma unroll
         for (int k = 0; k < 8; ++k) r.f[k] = fmaxf(fmaxf(a.f[k], b.f[k]), fmaxf(d.f[k], e.f[k]));
-        st8(y + pix * y_cs + y_coff + c, r);
+        st8(y + pix * y_cs + y_coff + c, r, dt);
     }
 }
 
@@ -63,7 +64,7 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_c
                                     const __nv_bfloat16* __restrict__ dy, int dy_cs, int dy_coff,
                                     const __nv_bfloat16* __restrict__ add, int add_cs, int add_coff,
                                     __nv_bfloat16* __restrict__ dx, int dx_cs, int dx_coff, int N, int H, int W,
-                                    int C8) {
+                                    int C8, int dt) {
     const int Ho = H / 2, Wo = W / 2;
     const long total = static_cast<long>(N) * Ho * Wo * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -76,8 +77,8 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_c
         const long offs[4] = {base, base + 1, base + W, base + W + 1};
         V8 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = ld8(x + offs[q] * x_cs + x_coff + c);
-        V8 g = ld8(dy + pix * dy_cs + dy_coff + c);
+        for (int q = 0; q < 4; ++q) v[q] = ld8(x + offs[q] * x_cs + x_coff + c, dt);
+        V8 g = ld8(dy + pix * dy_cs + dy_coff + c, dt);
         int arg[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -91,10 +92,10 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_c
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             V8 o;
-            if (add != nullptr) o = ld8(add + offs[q] * add_cs + add_coff + c);
+            if (add != nullptr) o = ld8(add + offs[q] * add_cs + add_coff + c, dt);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o.f[k] = (add != nullptr ? o.f[k] : 0.f) + (arg[k] == q ? g.f[k] : 0.f);
-            st8(dx + offs[q] * dx_cs + dx_coff + c, o);
+            st8(dx + offs[q] * dx_cs + dx_coff + c, o, dt);
         }
     }
 }
@@ -109,7 +110,7 @@ __device__ __forceinline__ void up2_src(int o, int n_in, int& i0, int& i1, float
 // y (N,2h,2w) slice = bilinear 2x of x (N,h,w)
 __global__ void upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                      __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int N, int h, int w,
-                                     int C8) {
+                                     int C8, int dt) {
     const int H = 2 * h, W = 2 * w;
     const long total = static_cast<long>(N) * H * W * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -123,20 +124,20 @@ __global__ void upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_
         up2_src(oy, h, y0, y1, fy);
         up2_src(ox, w, x0, x1, fx);
         const __nv_bfloat16* b = x + static_cast<long>(n) * h * w * x_cs + x_coff + c;
-        V8 a00 = ld8(b + (static_cast<long>(y0) * w + x0) * x_cs), a01 = ld8(b + (static_cast<long>(y0) * w + x1) * x_cs),
-           a10 = ld8(b + (static_cast<long>(y1) * w + x0) * x_cs), a11 = ld8(b + (static_cast<long>(y1) * w + x1) * x_cs);
+        V8 a00 = ld8(b + (static_cast<long>(y0) * w + x0) * x_cs, dt), a01 = ld8(b + (static_cast<long>(y0) * w + x1) * x_cs, dt),
+           a10 = ld8(b + (static_cast<long>(y1) * w + x0) * x_cs, dt), a11 = ld8(b + (static_cast<long>(y1) * w + x1) * x_cs, dt);
         V8 r;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             r.f[k] = (1.f - fy) * ((1.f - fx) * a00.f[k] + fx * a01.f[k]) + fy * ((1.f - fx) * a10.f[k] + fx * a11.f[k]);
-        st8(y + pix * y_cs + y_coff + c, r);
+        st8(y + pix * y_cs + y_coff + c, r, dt);
     }
 }
 
 // dx (N,h,w) = adjoint of the 2x bilinear up-sampling applied to dy (N,2h,2w) slice
 __global__ void upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, int dy_coff,
                                      __nv_bfloat16* __restrict__ dx, int dx_cs, int dx_coff, int N, int h, int w,
-                                     int C8) {
+                                     int C8, int dt) {
     const int H = 2 * h, W = 2 * w;
     const long total = static_cast<long>(N) * h * w * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -160,19 +161,19 @@ __global__ void upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int d
                 up2_src(ox, w, x0, x1, fx);
                 float wx = (x0 == ix ? 1.f - fx : 0.f) + (x1 == ix ? fx : 0.f);
                 if (wx == 0.f) continue;
-                V8 g = ld8(dy + ((static_cast<long>(n) * H + oy) * W + ox) * dy_cs + dy_coff + c);
+                V8 g = ld8(dy + ((static_cast<long>(n) * H + oy) * W + ox) * dy_cs + dy_coff + c, dt);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc.f[k] = fmaf(wy * wx, g.f[k], acc.f[k]);
             }
         }
-        st8(dx + pix * dx_cs + dx_coff + c, acc);
+        st8(dx + pix * dx_cs + dx_coff + c, acc, dt);
     }
 }
 
 // y[b,pix,c] = scale * sum_s x[b,s,pix,c]          (scale = 1/S: mean over samples, networks.py:36)
 __global__ void spp_reduce_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                   __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int B, int S, long HW,
-                                  int C8, float scale) {
+                                  int C8, float scale, int dt) {
     const long total = static_cast<long>(B) * HW * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
@@ -183,13 +184,13 @@ __global__ void spp_reduce_kernel(const __nv_bfloat16* __restrict__ x, int x_cs,
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc.f[k] = 0.f;
         for (int s = 0; s < S; ++s) {
-            V8 v = ld8(x + ((b * S + s) * HW + hw) * x_cs + x_coff + c);
+            V8 v = ld8(x + ((b * S + s) * HW + hw) * x_cs + x_coff + c, dt);
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc.f[k] += v.f[k];
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc.f[k] *= scale;
-        st8(y + pix * y_cs + y_coff + c, acc);
+        st8(y + pix * y_cs + y_coff + c, acc, dt);
     }
 }
 
@@ -197,19 +198,19 @@ __global__ void spp_reduce_kernel(const __nv_bfloat16* __restrict__ x, int x_cs,
 __global__ void spp_broadcast_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                      const __nv_bfloat16* __restrict__ add, int add_cs, int add_coff,
                                      __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int B, int S, long HW,
-                                     int C8, float scale) {
+                                     int C8, float scale, int dt) {
     const long total = static_cast<long>(B) * S * HW * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
         long pix = i / C8;  // over (b,s,hw)
         long hw = pix % HW;
         long b = pix / (HW * S);
-        V8 v = ld8(x + (b * HW + hw) * x_cs + x_coff + c);
+        V8 v = ld8(x + (b * HW + hw) * x_cs + x_coff + c, dt);
         V8 o;
-        if (add != nullptr) o = ld8(add + pix * add_cs + add_coff + c);
+        if (add != nullptr) o = ld8(add + pix * add_cs + add_coff + c, dt);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.f[k] = (add != nullptr ? o.f[k] : 0.f) + scale * v.f[k];
-        st8(y + pix * y_cs + y_coff + c, o);
+        st8(y + pix * y_cs + y_coff + c, o, dt);
     }
 }
 
@@ -217,15 +218,15 @@ __global__ void spp_broadcast_kernel(const __nv_bfloat16* __restrict__ x, int x_
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, int dy_coff,
                                const __nv_bfloat16* __restrict__ y, int y_cs, int y_coff,
                                __nv_bfloat16* __restrict__ dz, int dz_cs, int dz_coff, long npix, int C8,
-                               float slope) {
+                               float slope, int dt) {
     const long total = npix * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
         long pix = i / C8;
-        V8 g = ld8(dy + pix * dy_cs + dy_coff + c), v = ld8(y + pix * y_cs + y_coff + c);
+        V8 g = ld8(dy + pix * dy_cs + dy_coff + c, dt), v = ld8(y + pix * y_cs + y_coff + c, dt);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g.f[k] *= (v.f[k] > 0.f) ? 1.f : slope;
-        st8(dz + pix * dz_cs + dz_coff + c, g);
+        st8(dz + pix * dz_cs + dz_coff + c, g, dt);
     }
 }
 
@@ -244,88 +245,88 @@ static int ew_blocks(long total) { return static_cast<int>(std::min<long>((total
     }
 
 extern "C" int wcmc_maxpool2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int H,
-                                 int W, int C, void* stream) {
+                                 int W, int C, int dtype, void* stream) {
     WCMC_EW_CHECK("maxpool2_fwd", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, WCMC_ESHAPE, "maxpool2: H, W must be even");
     long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
     maxpool2_fwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, H, W,
-        C / 8);
+        C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_maxpool2_bwd(const void* x, int x_cs, int x_coff, const void* dy, int dy_cs, int dy_coff,
                                  const void* add, int add_cs, int add_coff, void* dx, int dx_cs, int dx_coff, int N,
-                                 int H, int W, int C, void* stream) {
+                                 int H, int W, int C, int dtype, void* stream) {
     WCMC_EW_CHECK("maxpool2_bwd", C, x_cs, x_coff, dy_cs, dy_coff, add_cs, add_coff, dx_cs, dx_coff);
     WCMC_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, WCMC_ESHAPE, "maxpool2: H, W must be even");
     long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
     maxpool2_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff,
         static_cast<const __nv_bfloat16*>(add), add_cs, add_coff, static_cast<__nv_bfloat16*>(dx), dx_cs, dx_coff,
-        N, H, W, C / 8);
+        N, H, W, C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_upsample2_fwd(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int N, int h,
-                                  int w, int C, void* stream) {
+                                  int w, int C, int dtype, void* stream) {
     WCMC_EW_CHECK("upsample2_fwd", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(N > 0 && h > 0 && w > 0, WCMC_ESHAPE, "upsample2: bad shape");
     long total = static_cast<long>(N) * h * w * 4 * (C / 8);
     upsample2_fwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, h, w,
-        C / 8);
+        C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_upsample2_bwd(const void* dy, int dy_cs, int dy_coff, void* dx, int dx_cs, int dx_coff, int N,
-                                  int h, int w, int C, void* stream) {
+                                  int h, int w, int C, int dtype, void* stream) {
     WCMC_EW_CHECK("upsample2_bwd", C, dy_cs, dy_coff, dx_cs, dx_coff);
     WCMC_REQUIRE(N > 0 && h > 0 && w > 0, WCMC_ESHAPE, "upsample2: bad shape");
     long total = static_cast<long>(N) * h * w * (C / 8);
     upsample2_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<__nv_bfloat16*>(dx), dx_cs, dx_coff, N, h,
-        w, C / 8);
+        w, C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_spp_reduce(const void* x, int x_cs, int x_coff, void* y, int y_cs, int y_coff, int B, int S,
-                               int HW, int C, float scale, void* stream) {
+                               int HW, int C, float scale, int dtype, void* stream) {
     WCMC_EW_CHECK("spp_reduce", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(B > 0 && S > 0 && HW > 0, WCMC_ESHAPE, "spp_reduce: bad shape");
     long total = static_cast<long>(B) * HW * (C / 8);
     spp_reduce_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW,
-        C / 8, scale);
+        C / 8, scale, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_spp_broadcast(const void* x, int x_cs, int x_coff, const void* add, int add_cs, int add_coff,
                                   void* y, int y_cs, int y_coff, int B, int S, int HW, int C, float scale,
-                                  void* stream) {
+                                  int dtype, void* stream) {
     WCMC_EW_CHECK("spp_broadcast", C, x_cs, x_coff, add_cs, add_coff, y_cs, y_coff);
     WCMC_REQUIRE(B > 0 && S > 0 && HW > 0, WCMC_ESHAPE, "spp_broadcast: bad shape");
     long total = static_cast<long>(B) * S * HW * (C / 8);
     spp_broadcast_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(add), add_cs, add_coff,
-        static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW, C / 8, scale);
+        static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW, C / 8, scale, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_act_bwd(const void* dy, int dy_cs, int dy_coff, const void* y, int y_cs, int y_coff, void* dz,
-                            int dz_cs, int dz_coff, long npix, int C, int act, float slope, void* stream) {
+                            int dz_cs, int dz_coff, long npix, int C, int act, float slope, int dtype, void* stream) {
     WCMC_EW_CHECK("act_bwd", C, dy_cs, dy_coff, y_cs, y_coff, dz_cs, dz_coff);
     WCMC_REQUIRE(npix > 0 && (act == WCMC_ACT_RELU || act == WCMC_ACT_LEAKY), WCMC_ESHAPE, "act_bwd: bad args");
     long total = npix * (C / 8);
     act_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<const __nv_bfloat16*>(y), y_cs, y_coff,
-        static_cast<__nv_bfloat16*>(dz), dz_cs, dz_coff, npix, C / 8, act == WCMC_ACT_RELU ? 0.f : slope);
+        static_cast<__nv_bfloat16*>(dz), dz_cs, dz_coff, npix, C / 8, act == WCMC_ACT_RELU ? 0.f : slope, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

@@ -108,12 +108,14 @@ kernel_apply_fwd_kernel(const float* __restrict__ logits, int l_cs, const float*
     }
 }
 
-template <int C, bool BF16>
+template <int C, int DT>
 __global__ void __launch_bounds__(kKaThreads)
 kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float* __restrict__ data,
                         const float* __restrict__ out, const float* __restrict__ stats,
                         const float* __restrict__ gout, void* __restrict__ dlogits, int dl_cs, int N, int H,
-                        int W, int ks) {
+                        int W, int ks, const float* __restrict__ scale) {
+    constexpr bool H16 = DT != WCMC_F32;
+    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     extern __shared__ float sm[];
     const int taps = ks * ks;
     const int pitch = ka_pitch(ks);
@@ -127,7 +129,7 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = y0 + warp;
     if (y >= H) return;
-    const int stage_elems = BF16 ? dl_cs / 2 : dl_cs;  // in 4-byte words
+    const int stage_elems = H16 ? dl_cs / 2 : dl_cs;  // in 4-byte words
     uint32_t* stage = reinterpret_cast<uint32_t*>(stage_all) + warp * stage_elems;
     int off[kKaMaxSlots];
 #pragma unroll
@@ -165,10 +167,12 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
                 float a = 0.f;
 #pragma unroll
                 for (int c = 0; c < C; ++c) a = fmaf(g[c], sm[c * plane + off[j] + tx], a);
-                float d = (k < taps) ? pk * (a - go) : 0.f;
+                float d = (k < taps) ? sc * pk * (a - go) : 0.f;
                 if (k < dl_cs) {
-                    if (BF16)
+                    if (DT == WCMC_BF16)
                         reinterpret_cast<__nv_bfloat16*>(stage)[k] = __float2bfloat16_rn(d);
+                    else if (DT == WCMC_F16)
+                        reinterpret_cast<__half*>(stage)[k] = __float2half_rn(d);
                     else
                         reinterpret_cast<float*>(stage)[k] = d;
                 }
@@ -178,7 +182,7 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
         {
             const int nvec = stage_elems / 4;  // uint4 per pixel row
             uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(dlogits) +
-                                                  pix * static_cast<size_t>(dl_cs) * (BF16 ? 2 : 4));
+                                                  pix * static_cast<size_t>(dl_cs) * (H16 ? 2 : 4));
             const uint4* src = reinterpret_cast<const uint4*>(stage);
             for (int i = lane; i < nvec; i += 32) dst[i] = src[i];
         }
@@ -222,22 +226,24 @@ extern "C" int wcmc_kernel_apply_fwd(const float* logits, int l_cs, const float*
     }
 }
 
-template <int C, bool BF16>
+template <int C, int DT>
 static int launch_bwd(const float* logits, int l_cs, const float* data, const float* out, const float* stats,
-                      const float* gout, void* dl, int dl_cs, int N, int H, int W, int ks, cudaStream_t stream) {
+                      const float* gout, void* dl, int dl_cs, int N, int H, int W, int ks, const float* scale,
+                      cudaStream_t stream) {
     dim3 grid((W + kKaTileW - 1) / kKaTileW, (H + kKaTileH - 1) / kKaTileH, N);
-    size_t smem = ka_smem_bytes(C, ks, BF16 ? dl_cs / 2 : dl_cs);
-    WCMC_CHECK_CUDA(cudaFuncSetAttribute(kernel_apply_bwd_kernel<C, BF16>,
+    size_t smem = ka_smem_bytes(C, ks, DT != WCMC_F32 ? dl_cs / 2 : dl_cs);
+    WCMC_CHECK_CUDA(cudaFuncSetAttribute(kernel_apply_bwd_kernel<C, DT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kernel_apply_bwd_kernel<C, BF16><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, gout,
-                                                                         dl, dl_cs, N, H, W, ks);
+    kernel_apply_bwd_kernel<C, DT><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, gout, dl,
+                                                                       dl_cs, N, H, W, ks, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_kernel_apply_bwd(const float* logits, int l_cs, const float* data, const float* out,
                                      const float* stats, const float* grad_out, void* d_logits, int dl_cs,
-                                     int dl_bf16, int N, int C, int H, int W, int ksize, void* stream_) {
+                                     int dl_dtype, int N, int C, int H, int W, int ksize, const float* scale,
+                                     void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(ksize >= 1 && ksize <= 21 && (ksize & 1), WCMC_ESHAPE, "kernel_apply: ksize %d must be odd and <= 21", ksize);
     WCMC_REQUIRE(l_cs >= ksize * ksize && dl_cs >= ksize * ksize && dl_cs <= 448, WCMC_ESHAPE,
@@ -246,11 +252,19 @@ extern "C" int wcmc_kernel_apply_bwd(const float* logits, int l_cs, const float*
     WCMC_REQUIRE(C >= 1 && C <= 4, WCMC_ESHAPE, "kernel_apply: C=%d not in [1,4]", C);
     WCMC_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535, WCMC_ESHAPE, "kernel_apply: bad N/H/W");
     WCMC_REQUIRE(stats != nullptr, WCMC_ESHAPE, "kernel_apply_bwd: stats from the forward pass are required");
-#define WCMC_KA_BWD(CC)                                                                                      \
-    return dl_bf16 ? launch_bwd<CC, true>(logits, l_cs, data, out, stats, grad_out, d_logits, dl_cs, N, H, W, \
-                                          ksize, stream)                                                     \
-                   : launch_bwd<CC, false>(logits, l_cs, data, out, stats, grad_out, d_logits, dl_cs, N, H, W, \
-                                           ksize, stream)
+#define WCMC_KA_BWD(CC)                                                                                       \
+    switch (dl_dtype) {                                                                                       \
+        case WCMC_BF16:                                                                                       \
+            return launch_bwd<CC, WCMC_BF16>(logits, l_cs, data, out, stats, grad_out, d_logits, dl_cs, N, H, W,  \
+                                             ksize, scale, stream);                                           \
+        case WCMC_F16:                                                                                        \
+            return launch_bwd<CC, WCMC_F16>(logits, l_cs, data, out, stats, grad_out, d_logits, dl_cs, N, H, W,   \
+                                            ksize, scale, stream);                                            \
+        default:                                                                                              \
+            return launch_bwd<CC, WCMC_F32>(logits, l_cs, data, out, stats, grad_out, d_logits, dl_cs, N, H, W,   \
+                                            ksize, scale, stream);                                            \
+    }
+    WCMC_REQUIRE(dl_dtype >= 0 && dl_dtype <= 2, WCMC_ESHAPE, "kernel_apply_bwd: bad dl_dtype %d", dl_dtype);
     switch (C) {
         case 1: WCMC_KA_BWD(1);
         case 2: WCMC_KA_BWD(2);

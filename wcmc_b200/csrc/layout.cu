@@ -15,14 +15,15 @@ constexpr int kTrThreads = 256;
 // grid: (ceil(HW/32), N).  smem: c_fill x 33 floats.
 __global__ void __launch_bounds__(kTrThreads)
 nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
-                    int dst_cs, int dst_coff, int c_fill) {
+                    int dst_cs, int dst_coff, int c_fill, int dtype, const float* __restrict__ scale) {
     extern __shared__ float tile[];
+    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     const int n = blockIdx.y, p0 = blockIdx.x * kTrPix;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = p0 + lane;
     for (int c = warp; c < c_fill; c += kTrThreads / 32) {
         float v = 0.f;
-        if (c < C && p < HW) v = __ldg(src + (static_cast<size_t>(n) * C + c) * HW + p);
+        if (c < C && p < HW) v = sc * __ldg(src + (static_cast<size_t>(n) * C + c) * HW + p);
         tile[c * 33 + lane] = v;
     }
     __syncthreads();
@@ -32,27 +33,30 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
         uint32_t* drow = reinterpret_cast<uint32_t*>(dst + (static_cast<size_t>(n) * HW + p0 + pp) * dst_cs +
                                                      dst_coff);
         for (int l = lane; l < npair; l += 32)
-            drow[l] = pack_bf16x2(tile[(2 * l) * 33 + pp], tile[(2 * l + 1) * 33 + pp]);
+            drow[l] = pack_h2(tile[(2 * l) * 33 + pp], tile[(2 * l + 1) * 33 + pp], dtype);
     }
 }
 
 __global__ void __launch_bounds__(kTrThreads)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW,
-                    int src_cs, int src_coff, int accumulate) {
+                    int src_cs, int src_coff, int accumulate, int dtype, const float* __restrict__ scale) {
     extern __shared__ float tile[];
+    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     const int n = blockIdx.y, p0 = blockIdx.x * kTrPix;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int pp = warp; pp < kTrPix; pp += kTrThreads / 32) {
         if (p0 + pp >= HW) break;
         const __nv_bfloat16* srow = src + (static_cast<size_t>(n) * HW + p0 + pp) * src_cs + src_coff;
-        for (int c = lane; c < C; c += 32) tile[c * 33 + pp] = __bfloat162float(srow[c]);
+        for (int c = lane; c < C; c += 32)
+            tile[c * 33 + pp] = dtype == WCMC_F16 ? __half2float(reinterpret_cast<const __half*>(srow)[c])
+                                                  : __bfloat162float(srow[c]);
     }
     __syncthreads();
     const int p = p0 + lane;
     if (p >= HW) return;
     for (int c = warp; c < C; c += kTrThreads / 32) {
         float* d = dst + (static_cast<size_t>(n) * C + c) * HW + p;
-        float v = tile[c * 33 + lane];
+        float v = sc * tile[c * 33 + lane];
         *d = accumulate ? (*d + v) : v;
     }
 }
@@ -60,7 +64,7 @@ nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ d
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                     __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad,
                                     float* __restrict__ bias_p, int cout, int cin, int ks, int cout_p,
-                                    int cin_p) {
+                                    int cin_p, int dtype) {
     const int taps = ks * ks;
     const long total = static_cast<long>(cout_p) * taps * cin_p;
     if (bias_p != nullptr && blockIdx.x == 0)
@@ -73,7 +77,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
             int tap = static_cast<int>((i / cin_p) % taps);
             int co = static_cast<int>(i / (static_cast<long>(cin_p) * taps));
             float v = (co < cout && ci < cin) ? w[(static_cast<long>(co) * cin + ci) * taps + tap] : 0.f;
-            fwd[i] = __float2bfloat16_rn(v);
+            if (dtype == WCMC_F16) reinterpret_cast<__half*>(fwd)[i] = __float2half_rn(v);
+            else fwd[i] = __float2bfloat16_rn(v);
         }
         if (dgrad != nullptr) {  // dgrad[ci][taps-1-tap][co]
             int co = static_cast<int>(i % cout_p);
@@ -81,7 +86,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
             int ci = static_cast<int>(i / (static_cast<long>(cout_p) * taps));
             int tap = taps - 1 - tapf;
             float v = (co < cout && ci < cin) ? w[(static_cast<long>(co) * cin + ci) * taps + tap] : 0.f;
-            dgrad[i] = __float2bfloat16_rn(v);
+            if (dtype == WCMC_F16) reinterpret_cast<__half*>(dgrad)[i] = __float2half_rn(v);
+            else dgrad[i] = __float2bfloat16_rn(v);
         }
     }
 }
@@ -89,7 +95,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
 // db[c] (+)= sum_pix dy[pix][c].  grid.x CTAs each reduce a slab of pixels, then atomics.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long npix, int cs, int coff, int cout,
-                 float* __restrict__ db) {
+                 float* __restrict__ db, int dtype, const float* __restrict__ scale) {
     extern __shared__ float red[];  // [8][cout]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long per = (npix + gridDim.x - 1) / gridDim.x;
@@ -98,14 +104,16 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long npix, int cs, int co
         int c = c0 + lane;
         float s = 0.f;
         if (c < cout)
-            for (long p = b + warp; p < e; p += 8) s += __bfloat162float(dy[p * cs + coff + c]);
+            for (long p = b + warp; p < e; p += 8)
+                s += dtype == WCMC_F16 ? __half2float(reinterpret_cast<const __half*>(dy)[p * cs + coff + c])
+                                       : __bfloat162float(dy[p * cs + coff + c]);
         if (c < cout) red[warp * cout + c] = s;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < cout; c += 256) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += red[w * cout + c];
-        atomicAdd(db + c, s);
+        atomicAdd(db + c, s * (scale != nullptr ? __ldg(scale) : 1.f));
     }
 }
 
@@ -119,8 +127,8 @@ __global__ void zero_f32_kernel(float* p, long n) {
 
 using namespace wcmc;
 
-extern "C" int wcmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int dst_cs,
-                                          int dst_coff, int c_fill, void* stream_) {
+extern "C" int wcmc_nchw_f32_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int H, int W,
+                                     int dst_cs, int dst_coff, int c_fill, const float* scale, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, WCMC_ESHAPE, "nchw_to_nhwc: bad shape");
     WCMC_REQUIRE(c_fill >= C && c_fill % 2 == 0 && dst_coff % 2 == 0 && dst_cs % 2 == 0 &&
@@ -135,13 +143,13 @@ extern "C" int wcmc_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, in
         WCMC_CHECK_CUDA(cudaFuncSetAttribute(nchw_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
     nchw_to_nhwc_kernel<<<grid, kTrThreads, smem, stream>>>(src, static_cast<__nv_bfloat16*>(dst), C, HW, dst_cs,
-                                                            dst_coff, c_fill);
+                                                            dst_coff, c_fill, dst_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
-extern "C" int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int src_cs,
-                                          int src_coff, int accumulate, void* stream_) {
+extern "C" int wcmc_nhwc_to_nchw_f32(const void* src, int src_dtype, float* dst, int N, int C, int H, int W,
+                                     int src_cs, int src_coff, int accumulate, const float* scale, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, WCMC_ESHAPE, "nhwc_to_nchw: bad shape");
     WCMC_REQUIRE(src_coff + C <= src_cs, WCMC_ESHAPE, "nhwc_to_nchw: channel slice out of range");
@@ -153,13 +161,13 @@ extern "C" int wcmc_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, in
         WCMC_CHECK_CUDA(cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
     nhwc_to_nchw_kernel<<<grid, kTrThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, C, HW,
-                                                            src_cs, src_coff, accumulate);
+                                                            src_cs, src_coff, accumulate, src_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
 extern "C" int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* dst_dgrad,
-                                 float* dst_bias, int cout, int cin, int ksize, int cout_p, int cin_p,
+                                 float* dst_bias, int dtype, int cout, int cin, int ksize, int cout_p, int cin_p,
                                  void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin && ksize > 0, WCMC_ESHAPE,
@@ -168,13 +176,13 @@ extern "C" int wcmc_pack_weights(const float* w, const float* bias, void* dst_fw
     int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
     pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, bias, static_cast<__nv_bfloat16*>(dst_fwd),
                                                     static_cast<__nv_bfloat16*>(dst_dgrad), dst_bias, cout, cin,
-                                                    ksize, cout_p, cin_p);
+                                                    ksize, cout_p, cin_p, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
-extern "C" int wcmc_bias_grad(const void* dy, int npix, int dy_cs, int dy_coff, int cout, float* db,
-                              int accumulate, void* stream_) {
+extern "C" int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs, int dy_coff, int cout, float* db,
+                              int accumulate, const float* scale, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(npix > 0 && cout > 0 && dy_coff + cout <= dy_cs && cout <= 1024, WCMC_ESHAPE,
                  "bias_grad: bad shape");
@@ -184,7 +192,7 @@ extern "C" int wcmc_bias_grad(const void* dy, int npix, int dy_cs, int dy_coff, 
     }
     int blocks = std::min(296, (npix + 255) / 256);
     bias_grad_kernel<<<blocks, 256, 8 * cout * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy),
-                                                                        npix, dy_cs, dy_coff, cout, db);
+                                                                        npix, dy_cs, dy_coff, cout, db, dy_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

@@ -23,24 +23,24 @@ SIGNATURES = {
     "wcmc_last_error": (ctypes.c_char_p, []),
     "wcmc_version": (ctypes.c_char_p, []),
     "wcmc_init": (c_int, [c_int]),
-    "wcmc_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
-    "wcmc_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
-    "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
-    "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    "wcmc_nchw_f32_to_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
+    "wcmc_nhwc_to_nchw_f32": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
+    "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
                     + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
-    "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]
-                          + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
-    "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
+    "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 6 + [c_void_p]
+                          + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_int, c_void_p, c_void_p]),
     "wcmc_kernel_apply_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
-    "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
-    "wcmc_maxpool2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
-    "wcmc_maxpool2_bwd": (c_int, [c_void_p, c_int, c_int] * 4 + [c_int] * 4 + [c_void_p]),
-    "wcmc_upsample2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
-    "wcmc_upsample2_bwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_void_p]),
-    "wcmc_spp_reduce": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_float, c_void_p]),
-    "wcmc_spp_broadcast": (c_int, [c_void_p, c_int, c_int] * 3 + [c_int] * 4 + [c_float, c_void_p]),
-    "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_void_p]),
+    "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
+    "wcmc_maxpool2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 5 + [c_void_p]),
+    "wcmc_maxpool2_bwd": (c_int, [c_void_p, c_int, c_int] * 4 + [c_int] * 5 + [c_void_p]),
+    "wcmc_upsample2_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 5 + [c_void_p]),
+    "wcmc_upsample2_bwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 5 + [c_void_p]),
+    "wcmc_spp_reduce": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "wcmc_spp_broadcast": (c_int, [c_void_p, c_int, c_int] * 3 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_int, c_void_p]),
 }
 
 
@@ -133,41 +133,55 @@ def pad16(c):
     return (c + 15) // 16 * 16
 
 
+BF16, F16, F32 = 0, 1, 2
+_DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
+
+
+def _dt(t):
+    return _DT[t.dtype]
+
+
+def _h16(t):
+    assert t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(), "expected contiguous 16-bit NHWC tensor"
+    return t
+
+
 # ------------------------------------------------------------------------------------------------
-# thin typed wrappers (torch tensors in, torch tensors out); all run on the current stream
+# thin typed wrappers (torch tensors in, torch tensors out); all run on the current stream.
+# 16-bit activations may be torch.float16 or torch.bfloat16 (WCMC_F16 / WCMC_BF16); gradients are bf16.
 # ------------------------------------------------------------------------------------------------
-def nchw_to_nhwc(src, dst=None, dst_coff=0, c_fill=None):
-    """src (N,C,H,W) fp32 -> dst (N,H,W,Cs) bf16, channels [dst_coff, dst_coff+c_fill)."""
+def nchw_to_nhwc(src, dst=None, dst_coff=0, c_fill=None, dtype=torch.bfloat16, scale=None):
+    """src (N,C,H,W) fp32 -> dst (N,H,W,Cs) 16-bit, channels [dst_coff, dst_coff+c_fill)."""
     lib = init(src.device)
     assert src.dtype == torch.float32 and src.is_contiguous()
     n, c, h, w = src.shape
     if c_fill is None:
         c_fill = pad16(c)
     if dst is None:
-        dst = torch.empty((n, h, w, c_fill), dtype=torch.bfloat16, device=src.device)
-    assert dst.dtype == torch.bfloat16 and dst.is_contiguous() and dst.shape[:3] == (n, h, w)
-    _run(lib.wcmc_nchw_f32_to_nhwc_bf16, "nchw_f32_to_nhwc_bf16", src.numel() * 4.0 + n * h * w * c_fill * 2.0,
-         src.data_ptr(), dst.data_ptr(), n, c, h, w, dst.shape[3], dst_coff,
-                                          c_fill, _stream())
+        dst = torch.empty((n, h, w, c_fill), dtype=dtype, device=src.device)
+    assert _h16(dst).shape[:3] == (n, h, w)
+    _run(lib.wcmc_nchw_f32_to_nhwc, "nchw_f32_to_nhwc", src.numel() * 4.0 + n * h * w * c_fill * 2.0,
+         src.data_ptr(), dst.data_ptr(), _dt(dst), n, c, h, w, dst.shape[3], dst_coff, c_fill, _p(scale),
+         _stream())
     return dst
 
 
-def nhwc_to_nchw(src, c, src_coff=0, out=None, accumulate=False):
+def nhwc_to_nchw(src, c, src_coff=0, out=None, accumulate=False, scale=None):
     lib = init(src.device)
-    assert src.dtype == torch.bfloat16 and src.is_contiguous()
-    n, h, w, cs = src.shape
+    n, h, w, cs = _h16(src).shape
     if out is None:
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
         accumulate = False
     assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, c, h, w)
-    _run(lib.wcmc_nhwc_bf16_to_nchw_f32, "nhwc_bf16_to_nchw_f32", out.numel() * 6.0,
-         src.data_ptr(), out.data_ptr(), n, c, h, w, cs, src_coff,
-                                          int(accumulate), _stream())
+    _run(lib.wcmc_nhwc_to_nchw_f32, "nhwc_to_nchw_f32", out.numel() * 6.0,
+         src.data_ptr(), _dt(src), out.data_ptr(), n, c, h, w, cs, src_coff, int(accumulate), _p(scale),
+         _stream())
     return out
 
 
-def pack_weights(w, bias=None, cout_p=None, cin_p=None, fwd=True, dgrad=True, want_bias=False):
-    """torch (Cout,Cin,k,k) fp32 -> (fwd [cout_p,k*k,cin_p], dgrad [cin_p,k*k,cout_p]) bf16
+def pack_weights(w, bias=None, cout_p=None, cin_p=None, fwd=True, dgrad=True, want_bias=False,
+                 dtype=torch.bfloat16):
+    """torch (Cout,Cin,k,k) fp32 -> (fwd [cout_p,k*k,cin_p], dgrad [cin_p,k*k,cout_p]) in `dtype`
     [, zero-padded fp32 bias [cout_p] when ``want_bias``]."""
     lib = init(w.device)
     w = w.detach()
@@ -177,44 +191,39 @@ def pack_weights(w, bias=None, cout_p=None, cin_p=None, fwd=True, dgrad=True, wa
     assert k == k2
     cout_p = cout_p or pad16(cout)
     cin_p = cin_p or pad16(cin)
-    f = torch.empty((cout_p, k * k, cin_p), dtype=torch.bfloat16, device=w.device) if fwd else None
-    d = torch.empty((cin_p, k * k, cout_p), dtype=torch.bfloat16, device=w.device) if dgrad else None
+    f = torch.empty((cout_p, k * k, cin_p), dtype=dtype, device=w.device) if fwd else None
+    d = torch.empty((cin_p, k * k, cout_p), dtype=dtype, device=w.device) if dgrad else None
     bp = torch.empty((cout_p,), dtype=torch.float32, device=w.device) if want_bias else None
     if bias is not None:
         bias = bias.detach().contiguous()
         assert bias.dtype == torch.float32 and bias.numel() == cout
     _run(lib.wcmc_pack_weights, "pack_weights", w.numel() * 8.0,
-         w.data_ptr(), _p(bias), _p(f), _p(d), _p(bp), cout, cin, k, cout_p, cin_p,
-                                 _stream())
+         w.data_ptr(), _p(bias), _p(f), _p(d), _p(bp), _DT[dtype], cout, cin, k, cout_p, cin_p, _stream())
     if want_bias:
         return f, d, bp
     return f, d
 
 
-def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_fp32=False, x_coff=0, cin_p=None,
-           mask=None, mask_coff=0, slope=0.0, flags=0, cin=None, cout=None):
-    """x (N,H,W,Cs) bf16 NHWC; w_packed (cout_p, k*k, cin_p) bf16; returns NHWC output."""
+def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype=None, x_coff=0, mask=None,
+           mask_coff=0, slope=0.0, flags=0, cin=None, cout=None):
+    """x (N,H,W,Cs) 16-bit NHWC; w_packed (cout_p, k*k, cin_p) 16-bit; returns the NHWC output
+    (dtype `out_dtype`, default = x's dtype; torch.float32 for the logits layer)."""
     lib = init(x.device)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous()
-    n, h, w, xcs = x.shape
-    cout_p, taps, wcin = w_packed.shape
+    n, h, w, xcs = _h16(x).shape
+    cout_p, taps, cin_p = _h16(w_packed).shape
     assert taps == ksize * ksize
-    cin_p = cin_p or wcin
-    assert cin_p == wcin, "packed weight cin_p %d != %d" % (wcin, cin_p)
     ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
     if out is None:
-        out = torch.empty((n, ho, wo, cout_p), dtype=torch.float32 if out_fp32 else torch.bfloat16,
-                          device=x.device)
-    assert out.is_contiguous() and tuple(out.shape[:3]) == (n, ho, wo)
-    assert out.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+        out = torch.empty((n, ho, wo, cout_p), dtype=out_dtype or x.dtype, device=x.device)
+    assert out.is_contiguous() and tuple(out.shape[:3]) == (n, ho, wo) and out.dtype in _DT
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= cout_p
     if mask is not None:
-        assert mask.dtype == torch.bfloat16 and mask.is_contiguous() and tuple(mask.shape[:3]) == (n, ho, wo)
+        assert tuple(_h16(mask).shape[:3]) == (n, ho, wo)
     _run(lib.wcmc_conv2d, "conv2d", 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
-         x.data_ptr(), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), cout_p, _p(bias),
-                           ksize, pad, out.data_ptr(), out.shape[3], out_coff, int(out_fp32), act, _p(mask),
-                           0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream())
+         x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, _p(bias),
+         ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),
+         0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream())
     return out
 
 
@@ -230,13 +239,13 @@ def _workspace(nbytes, device):
     return ws
 
 
-def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=0, out=None, accumulate=False):
-    """dw (cout,cin,k,k) fp32 (+)= sum dy (x) x ; x (N,H,W,Cs) / dy (N,Ho,Wo,Cs') bf16 NHWC."""
+def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=0, out=None, accumulate=False,
+                 scale=None):
+    """dw (cout,cin,k,k) fp32 (+)= sum dy (x) x ; x (N,H,W,Cs) / dy (N,Ho,Wo,Cs') 16-bit NHWC."""
     lib = init(x.device)
-    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
-    n, h, w, xcs = x.shape
+    n, h, w, xcs = _h16(x).shape
     ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
-    assert tuple(dy.shape[:3]) == (n, ho, wo), (dy.shape, (n, ho, wo))
+    assert tuple(_h16(dy).shape[:3]) == (n, ho, wo), (dy.shape, (n, ho, wo))
     if out is None:
         out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
         accumulate = False
@@ -244,22 +253,21 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
     need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
     ws = _workspace(need, x.device)
     _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", 2.0 * n * ho * wo * ksize * ksize * cin * cout,
-         x.data_ptr(), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), dy.shape[3], dy_coff,
-                                 cout_p, ksize, pad, out.data_ptr(), cout, cin, int(accumulate), ws.data_ptr(),
-                                 ws.numel(), _stream())
+         x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
+         ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(), _stream())
     return out
 
 
-def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False):
+def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False, scale=None):
     lib = init(dy.device)
-    assert dy.dtype == torch.bfloat16 and dy.is_contiguous()
+    _h16(dy)
     npix = dy.shape[0] * dy.shape[1] * dy.shape[2]
     if out is None:
         out = torch.empty((cout,), dtype=torch.float32, device=dy.device)
         accumulate = False
     _run(lib.wcmc_bias_grad, "bias_grad", npix * cout * 2.0,
-         dy.data_ptr(), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate),
-                              _stream())
+         dy.data_ptr(), _dt(dy), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate), _p(scale),
+         _stream())
     return out
 
 
@@ -273,110 +281,109 @@ def kernel_apply_fwd(logits_nhwc, data, ksize, want_stats=True):
     out = torch.empty_like(data)
     stats = torch.empty((n, h, w, 2), dtype=torch.float32, device=data.device) if want_stats else None
     _run(lib.wcmc_kernel_apply_fwd, "kernel_apply_fwd", n * h * w * (ksize * ksize * 4.0 + c * 8.0),
-         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
-                                     out.data_ptr(), _p(stats), n, c, h, w, ksize, _stream())
+         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(), out.data_ptr(), _p(stats), n, c, h, w,
+         ksize, _stream())
     return out, stats
 
 
-def kernel_apply_bwd(logits_nhwc, data, out, stats, grad_out, ksize, dl_cs=None, bf16=True):
+def kernel_apply_bwd(logits_nhwc, data, out, stats, grad_out, ksize, dl_cs=None, dtype=torch.bfloat16, scale=None):
     lib = init(data.device)
     n, c, h, w = data.shape
     grad_out = grad_out.contiguous()
     assert grad_out.dtype == torch.float32
     dl_cs = dl_cs or logits_nhwc.shape[3]
-    dl = torch.empty((n, h, w, dl_cs), dtype=torch.bfloat16 if bf16 else torch.float32, device=data.device)
-    _run(lib.wcmc_kernel_apply_bwd, "kernel_apply_bwd", n * h * w * (ksize * ksize * (4.0 + (2.0 if bf16 else 4.0)) + c * 12.0 + 8.0),
-         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(),
-                                     out.data_ptr(), stats.data_ptr(), grad_out.data_ptr(), dl.data_ptr(), dl_cs,
-                                     int(bf16), n, c, h, w, ksize, _stream())
+    dl = torch.empty((n, h, w, dl_cs), dtype=dtype, device=data.device)
+    bf16 = dtype != torch.float32
+    _run(lib.wcmc_kernel_apply_bwd, "kernel_apply_bwd",
+         n * h * w * (ksize * ksize * (4.0 + (2.0 if bf16 else 4.0)) + c * 12.0 + 8.0),
+         logits_nhwc.data_ptr(), logits_nhwc.shape[3], data.data_ptr(), out.data_ptr(), stats.data_ptr(),
+         grad_out.data_ptr(), dl.data_ptr(), dl_cs, _dt(dl), n, c, h, w, ksize, _p(scale), _stream())
     return dl
 
 
-# ---- NHWC bf16 glue (PathNet / U-Net); tensors are (.., Cs) bf16 contiguous, slices by (coff, C) ----
-def _nhwc(t):
-    assert t.dtype == torch.bfloat16 and t.is_contiguous(), "expected contiguous bf16 NHWC tensor"
-    return t
-
-
+# ---- NHWC glue (PathNet / U-Net); tensors are (.., Cs) 16-bit contiguous, slices by (coff, C) --------
 def maxpool2_fwd(x, c, x_coff=0, out=None, out_coff=0):
     lib = init(x.device)
-    n, h, w, xcs = _nhwc(x).shape
+    n, h, w, xcs = _h16(x).shape
     if out is None:
-        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
-    _run(lib.wcmc_maxpool2_fwd, "maxpool2_fwd", 0.0,
-         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h, w,
-                                 c, _stream())
+        out = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype
+    _run(lib.wcmc_maxpool2_fwd, "maxpool2_fwd", 0.0, x.data_ptr(), xcs, x_coff, _h16(out).data_ptr(),
+         out.shape[3], out_coff, n, h, w, c, _dt(x), _stream())
     return out
 
 
 def maxpool2_bwd(x, dy, c, x_coff=0, dy_coff=0, add=None, add_coff=0, out=None, out_coff=0):
+    """x: forward input; dy / add / out: gradients (all one 16-bit dtype)."""
     lib = init(x.device)
-    n, h, w, xcs = _nhwc(x).shape
+    n, h, w, xcs = _h16(x).shape
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
-    _run(lib.wcmc_maxpool2_bwd, "maxpool2_bwd", 0.0,
-         x.data_ptr(), xcs, x_coff, _nhwc(dy).data_ptr(), dy.shape[3], dy_coff, _p(add),
-                                 0 if add is None else add.shape[3], add_coff, _nhwc(out).data_ptr(), out.shape[3],
-                                 out_coff, n, h, w, c, _stream())
+        out = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+    assert dy.dtype == x.dtype and out.dtype == x.dtype and (add is None or add.dtype == x.dtype)
+    _run(lib.wcmc_maxpool2_bwd, "maxpool2_bwd", 0.0, x.data_ptr(), xcs, x_coff, _h16(dy).data_ptr(), dy.shape[3],
+         dy_coff, _p(add), 0 if add is None else add.shape[3], add_coff, _h16(out).data_ptr(), out.shape[3],
+         out_coff, n, h, w, c, _dt(x), _stream())
     return out
 
 
 def upsample2_fwd(x, c, x_coff=0, out=None, out_coff=0):
     lib = init(x.device)
-    n, h, w, xcs = _nhwc(x).shape
+    n, h, w, xcs = _h16(x).shape
     if out is None:
-        out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
-    _run(lib.wcmc_upsample2_fwd, "upsample2_fwd", 0.0,
-         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h, w,
-                                  c, _stream())
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype
+    _run(lib.wcmc_upsample2_fwd, "upsample2_fwd", 0.0, x.data_ptr(), xcs, x_coff, _h16(out).data_ptr(),
+         out.shape[3], out_coff, n, h, w, c, _dt(x), _stream())
     return out
 
 
 def upsample2_bwd(dy, c, dy_coff=0, out=None, out_coff=0):
     lib = init(dy.device)
-    n, hh, ww, dcs = _nhwc(dy).shape
+    n, hh, ww, dcs = _h16(dy).shape
     h, w = hh // 2, ww // 2
     if out is None:
-        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dy.device)
-    _run(lib.wcmc_upsample2_bwd, "upsample2_bwd", 0.0,
-         dy.data_ptr(), dcs, dy_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, n, h,
-                                  w, c, _stream())
+        out = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+    assert out.dtype == dy.dtype
+    _run(lib.wcmc_upsample2_bwd, "upsample2_bwd", 0.0, dy.data_ptr(), dcs, dy_coff, _h16(out).data_ptr(),
+         out.shape[3], out_coff, n, h, w, c, _dt(dy), _stream())
     return out
 
 
 def spp_reduce(x, b, s, c, scale, x_coff=0, out=None, out_coff=0):
-    """x (B*S,H,W,Cs) -> out (B,H,W,.) = scale * sum over S."""
+    """x (B*S,H,W,Cs) -> out (B,H,W,.) = scale * sum over S (same 16-bit dtype)."""
     lib = init(x.device)
-    bs, h, w, xcs = _nhwc(x).shape
+    bs, h, w, xcs = _h16(x).shape
     assert bs == b * s
     if out is None:
-        out = torch.empty((b, h, w, c), dtype=torch.bfloat16, device=x.device)
-    _run(lib.wcmc_spp_reduce, "spp_reduce", 0.0,
-         x.data_ptr(), xcs, x_coff, _nhwc(out).data_ptr(), out.shape[3], out_coff, b, s,
-                               h * w, c, float(scale), _stream())
+        out = torch.empty((b, h, w, c), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype
+    _run(lib.wcmc_spp_reduce, "spp_reduce", 0.0, x.data_ptr(), xcs, x_coff, _h16(out).data_ptr(), out.shape[3],
+         out_coff, b, s, h * w, c, float(scale), _dt(x), _stream())
     return out
 
 
 def spp_broadcast(x, b, s, c, scale=1.0, x_coff=0, add=None, add_coff=0, out=None, out_coff=0):
-    """out (B*S,H,W,.) slice = (add or 0) + scale * x (B,H,W,.) broadcast over S."""
+    """out (B*S,H,W,.) slice = (add or 0) + scale * x (B,H,W,.) broadcast over S (same 16-bit dtype)."""
     lib = init(x.device)
-    bb, h, w, xcs = _nhwc(x).shape
+    bb, h, w, xcs = _h16(x).shape
     assert bb == b
     if out is None:
-        out = torch.empty((b * s, h, w, c), dtype=torch.bfloat16, device=x.device)
-    _run(lib.wcmc_spp_broadcast, "spp_broadcast", 0.0,
-         x.data_ptr(), xcs, x_coff, _p(add), 0 if add is None else add.shape[3], add_coff,
-                                  _nhwc(out).data_ptr(), out.shape[3], out_coff, b, s, h * w, c, float(scale),
-                                  _stream())
+        out = torch.empty((b * s, h, w, c), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype and (add is None or add.dtype == x.dtype)
+    _run(lib.wcmc_spp_broadcast, "spp_broadcast", 0.0, x.data_ptr(), xcs, x_coff, _p(add),
+         0 if add is None else add.shape[3], add_coff, _h16(out).data_ptr(), out.shape[3], out_coff, b, s, h * w, c,
+         float(scale), _dt(x), _stream())
     return out
 
 
 def act_bwd(dy, y, c, act, slope=0.01, dy_coff=0, y_coff=0, out=None, out_coff=0):
+    """dz = dy * act'(y): dy / dz gradients, y the activation output (all one 16-bit dtype)."""
     lib = init(dy.device)
+    assert dy.dtype == y.dtype
     npix = dy.shape[0] * dy.shape[1] * dy.shape[2]
     if out is None:
-        out = torch.empty(tuple(dy.shape[:3]) + (c,), dtype=torch.bfloat16, device=dy.device)
-    _run(lib.wcmc_act_bwd, "act_bwd", 0.0,
-         _nhwc(dy).data_ptr(), dy.shape[3], dy_coff, _nhwc(y).data_ptr(), y.shape[3], y_coff,
-                            _nhwc(out).data_ptr(), out.shape[3], out_coff, npix, c, act, float(slope), _stream())
+        out = torch.empty(tuple(dy.shape[:3]) + (c,), dtype=dy.dtype, device=dy.device)
+    _run(lib.wcmc_act_bwd, "act_bwd", 0.0, _h16(dy).data_ptr(), dy.shape[3], dy_coff, _h16(y).data_ptr(),
+         y.shape[3], y_coff, _h16(out).data_ptr(), out.shape[3], out_coff, npix, c, act, float(slope), _dt(dy),
+         _stream())
     return out

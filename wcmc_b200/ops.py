@@ -10,10 +10,17 @@ channel-slice write (see include/wcmc.h).  Three fused operators cover the hot p
                  (/root/reference/support/networks.py:29-42)
   AutoencoderFn  the U-Net alone (sbmc.modules.Autoencoder, A.3)
 
-Precision policy: bf16 operands, fp32 accumulation (TMEM), fp32 master weights / optimiser, fp32
-logits + softmax + kernel-apply, fp32 PathNet output; gradients travel in bf16 between layers and
-are accumulated in fp32.
+Precision policy: 16-bit tensor-core operands with fp32 accumulation in TMEM.  Activations, packed
+weights AND the gradients flowing between layers are fp16 (11-bit significand: bf16's 8 bits put the
+gradients at 1.5-3e-2 relative error through the 9-layer stack, outside north_star's 1e-2; the tensor
+cores trap on mixed f16 x bf16 operands, so one format is used throughout).  fp16's narrow exponent
+is handled by a per-call loss scale: every backward pass multiplies the incoming gradient by
+s = 256 / max|g| (computed on the device, no host sync), keeps all 16-bit gradient tensors scaled by
+s, and multiplies the fp32 results (weight / bias / input gradients) by 1/s.  fp32 master weights /
+optimiser state / biases, fp32 logits + softmax + kernel-apply, fp32 PathNet output, fp32
+weight-gradient accumulation.  WCMC_ACT_DTYPE=bf16 switches every 16-bit tensor to bf16.
 """
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -22,6 +29,18 @@ import torch
 from . import lib
 
 ACT = {"linear": 0, None: 0, "relu": 1, "leaky_relu": 2}
+ACT_DTYPE = {"f16": torch.float16, "fp16": torch.float16, "bf16": torch.bfloat16}[
+    os.environ.get("WCMC_ACT_DTYPE", "f16").lower()]
+GRAD_DTYPE = ACT_DTYPE
+GRAD_TARGET = 256.0  # max |scaled incoming gradient|
+DEBUG_TAP = None     # tests may set this to a list to capture the per-layer dz tensors
+
+
+def grad_scale(g):
+    """-> (s, 1/s) as 1-element fp32 device tensors, s = GRAD_TARGET / max|g| (no host sync)."""
+    amax = g.detach().abs().amax().float().clamp_min(1e-30)
+    s = (GRAD_TARGET / amax).reshape(1)
+    return s, (amax / GRAD_TARGET).reshape(1)
 LEAKY_SLOPE = 0.01
 
 
@@ -55,7 +74,8 @@ def pack_chain(layers: List[LayerSpec], params, need_dgrad=True):
     packed = []
     for i, l in enumerate(layers):
         w, b = params[2 * i], params[2 * i + 1]
-        packed.append(lib.pack_weights(w, b, cout_p=l.cout_p, cin_p=l.cin_p, dgrad=need_dgrad, want_bias=True))
+        packed.append(lib.pack_weights(w, b, cout_p=l.cout_p, cin_p=l.cin_p, dgrad=need_dgrad, want_bias=True,
+                                       dtype=ACT_DTYPE))
     return packed
 
 
@@ -69,27 +89,29 @@ def chain_forward(x: Slice, layers, packed, out: Optional[Slice] = None, last_fp
         assert cur.c == l.cin, "chain input has %d channels, layer %d expects %d" % (cur.c, i, l.cin)
         if last and out is not None:
             y = lib.conv2d(cur.t, wf, bp, l.ksize, l.pad, act=l.act, slope=LEAKY_SLOPE, x_coff=cur.coff, out=out.t,
-                           out_coff=out.coff, out_fp32=out.t.dtype == torch.float32, cin=l.cin, cout=l.cout)
+                           out_coff=out.coff, cin=l.cin, cout=l.cout)
             cur = Slice(y, out.coff, l.cout)
         else:
             y = lib.conv2d(cur.t, wf, bp, l.ksize, l.pad, act=l.act, slope=LEAKY_SLOPE, x_coff=cur.coff,
-                           out_fp32=last and last_fp32, cin=l.cin, cout=l.cout)
+                           out_dtype=torch.float32 if (last and last_fp32) else None, cin=l.cin, cout=l.cout)
             cur = Slice(y, 0, l.cout)
         acts.append(cur)
     return acts
 
 
-def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=True):
-    """dz = gradient w.r.t. the PRE-activation output of the last layer (bf16 NHWC slice).
-    Returns (dx Slice or None, [dw0, db0, dw1, db1, ...])."""
+def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=True, inv_scale=None):
+    """dz = (loss-scaled) gradient w.r.t. the PRE-activation output of the last layer (16-bit NHWC
+    slice).  Returns (dx Slice or None [still scaled], [dw0, db0, dw1, db1, ...] [un-scaled fp32])."""
     grads = [None] * (2 * len(layers))
     for i in range(len(layers) - 1, -1, -1):
         l = layers[i]
         xin = acts[i]
+        if DEBUG_TAP is not None:
+            DEBUG_TAP.append((i, dz.t.detach().clone(), dz.coff, l.cout, inv_scale))
         if want_param_grads:
             grads[2 * i] = lib.conv2d_wgrad(xin.t, dz.t, l.cout, l.cin, l.ksize, l.pad, l.cin_p, l.cout_p,
-                                            x_coff=xin.coff, dy_coff=dz.coff)
-            grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff)
+                                            x_coff=xin.coff, dy_coff=dz.coff, scale=inv_scale)
+            grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, scale=inv_scale)
         if i == 0 and not need_dx:
             return None, grads
         wd = packed[i][1]
@@ -105,16 +127,16 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
     return dz, grads
 
 
-def _to_nhwc(x, c_fill=None):
+def _to_nhwc(x, c_fill=None, dtype=None, scale=None):
     x = x.contiguous()
     if x.dtype != torch.float32:
         x = x.float()
-    return Slice(lib.nchw_to_nhwc(x, c_fill=c_fill), 0, x.shape[1])
+    return Slice(lib.nchw_to_nhwc(x, c_fill=c_fill, dtype=dtype or ACT_DTYPE, scale=scale), 0, x.shape[1])
 
 
-def _grad_nhwc(g, c_fill):
-    """fp32 NCHW gradient -> bf16 NHWC (channels padded with zeros)."""
-    return _to_nhwc(g, c_fill)
+def _grad_nhwc(g, c_fill, scale=None):
+    """fp32 NCHW gradient -> 16-bit NHWC, multiplied by the loss scale (channels zero padded)."""
+    return _to_nhwc(g, c_fill, GRAD_DTYPE, scale)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -123,14 +145,14 @@ def _grad_nhwc(g, c_fill):
 class ConvChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, layers, *params):
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)
         packed = pack_chain(layers, params, need_dgrad=need)
         xin = _to_nhwc(x, layers[0].cin_p)
         acts = chain_forward(xin, layers, packed)
         y = acts[-1]
         out = lib.nhwc_to_nchw(y.t, layers[-1].cout, y.coff)
         ctx.layers = layers
-        ctx.need_dx = x.requires_grad
+        ctx.need_dx = ctx.needs_input_grad[0]
         if need:
             ctx.acts = acts
             ctx.packed = packed
@@ -140,10 +162,11 @@ class ConvChainFn(torch.autograd.Function):
     def backward(ctx, g):
         layers = ctx.layers
         last = layers[-1]
-        dy = _grad_nhwc(g, last.cout_p)
+        s, inv_s = grad_scale(g)
+        dy = _grad_nhwc(g, last.cout_p, s)
         dz = _act_bwd_full(dy, ctx.acts[-1], last)
-        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx)
-        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff) if dx is not None else None
+        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx, inv_scale=inv_s)
+        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff, scale=inv_s) if dx is not None else None
         ctx.acts = ctx.packed = None
         return (gx, None) + tuple(grads)
 
@@ -163,7 +186,7 @@ def _act_bwd_full(dy: Slice, y: Slice, layer: LayerSpec):
 class KPCNBranchFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, data, ksize, layers, *params):
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)
         packed = pack_chain(layers, params, need_dgrad=need)
         xin = _to_nhwc(x, layers[0].cin_p)
         acts = chain_forward(xin, layers, packed, last_fp32=True)
@@ -171,7 +194,7 @@ class KPCNBranchFn(torch.autograd.Function):
         data = data.contiguous().float()
         assert tuple(data.shape[-2:]) == tuple(logits.shape[1:3]), "data and kernels must share spatial size"
         out, stats = lib.kernel_apply_fwd(logits, data, ksize, want_stats=need)
-        ctx.layers, ctx.ksize, ctx.need_dx = layers, ksize, x.requires_grad
+        ctx.layers, ctx.ksize, ctx.need_dx = layers, ksize, ctx.needs_input_grad[0]
         if need:
             ctx.acts, ctx.packed, ctx.aux = acts, packed, (data, stats)
             ctx.save_for_backward(out)
@@ -183,11 +206,13 @@ class KPCNBranchFn(torch.autograd.Function):
         data, stats = ctx.aux
         (out,) = ctx.saved_tensors
         logits = ctx.acts[-1].t
-        dl = lib.kernel_apply_bwd(logits, data, out, stats, g.contiguous().float(), ctx.ksize,
-                                  dl_cs=layers[-1].cout_p, bf16=True)
+        g = g.contiguous().float()
+        s, inv_s = grad_scale(g)
+        dl = lib.kernel_apply_bwd(logits, data, out, stats, g, ctx.ksize, dl_cs=layers[-1].cout_p,
+                                  dtype=GRAD_DTYPE, scale=s)
         dz = Slice(dl, 0, layers[-1].cout)
-        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx)
-        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff) if dx is not None else None
+        dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx, inv_scale=inv_s)
+        gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff, scale=inv_s) if dx is not None else None
         ctx.acts = ctx.packed = ctx.aux = None
         return (gx, None, None, None) + tuple(grads)
 
@@ -202,7 +227,7 @@ class KernelApplyFn(torch.autograd.Function):
         logits = torch.zeros((n, h, w, cs), dtype=torch.float32, device=kernels.device)
         logits[..., :k2] = kernels.permute(0, 2, 3, 1)
         data = data.contiguous().float()
-        need = torch.is_grad_enabled() and kernels.requires_grad
+        need = any(ctx.needs_input_grad)
         out, stats = lib.kernel_apply_fwd(logits, data, ksize, want_stats=need)
         ctx.k2 = k2
         ctx.ksize = ksize
@@ -213,7 +238,7 @@ class KernelApplyFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         logits, data, out, stats = ctx.saved_tensors
-        dl = lib.kernel_apply_bwd(logits, data, out, stats, g.contiguous().float(), ctx.ksize, bf16=False)
+        dl = lib.kernel_apply_bwd(logits, data, out, stats, g.contiguous().float(), ctx.ksize, dtype=torch.float32)
         return None, dl[..., :ctx.k2].permute(0, 3, 1, 2), None
 
 
@@ -247,7 +272,7 @@ def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True):
     c_left = spec.left[-1].cout
     c_up = spec.right[0].cin - c_left
     assert c_up % 8 == 0 and c_left % 8 == 0
-    cat = torch.empty((n, h, w, c_up + c_left), dtype=torch.bfloat16, device=x.t.device)
+    cat = torch.empty((n, h, w, c_up + c_left), dtype=ACT_DTYPE, device=x.t.device)
     acts_left = chain_forward(x, spec.left, p_left, out=Slice(cat, c_up, c_left))
     pooled = lib.maxpool2_fwd(cat, c_left, x_coff=c_up)
     nn_ = spec.nxt.n_params()
@@ -261,31 +286,31 @@ def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True):
     return acts_right[-1], ctx
 
 
-def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True):
-    """dy = gradient w.r.t. the (post-activation) output.  Returns (dx Slice, flat grads)."""
+def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True, inv_scale=None):
+    """dy = (loss-scaled) gradient w.r.t. the post-activation output.  Returns (dx Slice, flat grads)."""
     if spec.nxt is None:
         dz = _act_bwd_full(dy, ctx["acts_left"][-1], spec.left[-1])
-        return chain_backward(dz, ctx["acts_left"], spec.left, ctx["p_left"], need_dx)
+        return chain_backward(dz, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale)
     c_up, c_left = ctx["c_up"], ctx["c_left"]
     dz = _act_bwd_full(dy, ctx["acts_right"][-1], spec.right[-1])
-    d_cat, g_right = chain_backward(dz, ctx["acts_right"], spec.right, ctx["p_right"], True)
+    d_cat, g_right = chain_backward(dz, ctx["acts_right"], spec.right, ctx["p_right"], True, inv_scale=inv_scale)
     d_up = lib.upsample2_bwd(d_cat.t, c_up, dy_coff=d_cat.coff)
-    d_pool, g_next = unet_backward(spec.nxt, ctx["ctx_next"], Slice(d_up, 0, c_up), True)
+    d_pool, g_next = unet_backward(spec.nxt, ctx["ctx_next"], Slice(d_up, 0, c_up), True, inv_scale)
     d_left = lib.maxpool2_bwd(ctx["cat"], d_pool.t, c_left, x_coff=c_up, dy_coff=d_pool.coff, add=d_cat.t,
                               add_coff=d_cat.coff + c_up)
     left_out = ctx["acts_left"][-1]
     dzl = _act_bwd_full(Slice(d_left, 0, c_left), left_out, spec.left[-1])
-    dx, g_left = chain_backward(dzl, ctx["acts_left"], spec.left, ctx["p_left"], need_dx)
+    dx, g_left = chain_backward(dzl, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale)
     return dx, g_left + g_next + g_right
 
 
 class AutoencoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, spec, *params):
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)
         xin = _to_nhwc(x, spec.left[0].cin_p)
         y, uctx = unet_forward(spec, xin, list(params), need)
-        ctx.spec, ctx.need_dx, ctx.cin = spec, x.requires_grad, x.shape[1]
+        ctx.spec, ctx.need_dx, ctx.cin = spec, ctx.needs_input_grad[0], x.shape[1]
         ctx.uctx = uctx if need else None
         return lib.nhwc_to_nchw(y.t, y.c, y.coff)
 
@@ -293,9 +318,10 @@ class AutoencoderFn(torch.autograd.Function):
     def backward(ctx, g):
         spec = ctx.spec
         c_out = g.shape[1]
-        dy = _grad_nhwc(g, lib.pad16(c_out))
-        dx, grads = unet_backward(spec, ctx.uctx, dy, ctx.need_dx)
-        gx = lib.nhwc_to_nchw(dx.t, ctx.cin, dx.coff) if dx is not None else None
+        s, inv_s = grad_scale(g)
+        dy = _grad_nhwc(g, lib.pad16(c_out), s)
+        dx, grads = unet_backward(spec, ctx.uctx, dy, ctx.need_dx, inv_s)
+        gx = lib.nhwc_to_nchw(dx.t, ctx.cin, dx.coff, scale=inv_s) if dx is not None else None
         ctx.uctx = None
         return (gx, None) + tuple(grads)
 
@@ -314,14 +340,14 @@ class PathNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, paths, spec, *params):
         b, s, nf, h, w = paths.shape
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need = any(ctx.needs_input_grad)
         ne, nu = 2 * len(spec.embedding), spec.unet.n_params()
         p_emb = pack_chain(spec.embedding, params[:ne], need)
         p_fin = pack_chain(spec.final, params[ne + nu:], need)
         c_emb = spec.embedding[-1].cout
         c_prop = spec.final[0].cin - c_emb
         x = _to_nhwc(paths.reshape(b * s, nf, h, w), spec.embedding[0].cin_p)
-        both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=torch.bfloat16, device=paths.device)
+        both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=ACT_DTYPE, device=paths.device)
         acts_emb = chain_forward(x, spec.embedding, p_emb, out=Slice(both, 0, c_emb))
         reduced = lib.spp_reduce(both, b, s, c_emb, 1.0 / s)
         prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
@@ -350,13 +376,14 @@ class PathNetFn(torch.autograd.Function):
             g = g * (o > 0)
         elif last.act == 2:
             g = torch.where(o > 0, g, g * LEAKY_SLOPE)
-        dz = _grad_nhwc(g, last.cout_p)
-        d_both, g_fin = chain_backward(dz, acts_fin, spec.final, p_fin, True)
+        gs, inv_s = grad_scale(g)
+        dz = _grad_nhwc(g, last.cout_p, gs)
+        d_both, g_fin = chain_backward(dz, acts_fin, spec.final, p_fin, True, inv_scale=inv_s)
         d_prop = lib.spp_reduce(d_both.t, b, s, c_prop, 1.0, x_coff=d_both.coff + c_emb)
-        d_red, g_unet = unet_backward(spec.unet, uctx, Slice(d_prop, 0, c_prop), True)
+        d_red, g_unet = unet_backward(spec.unet, uctx, Slice(d_prop, 0, c_prop), True, inv_s)
         dz_emb = lib.spp_broadcast(d_red.t, b, s, c_emb, 1.0 / s, x_coff=d_red.coff, add=d_both.t,
                                    add_coff=d_both.coff)
         dze = _act_bwd_full(Slice(dz_emb, 0, c_emb), acts_emb[-1], spec.embedding[-1])
-        _, g_emb = chain_backward(dze, acts_emb, spec.embedding, p_emb, False)
+        _, g_emb = chain_backward(dze, acts_emb, spec.embedding, p_emb, False, inv_scale=inv_s)
         ctx.saved = None
         return (None, None) + tuple(g_emb) + tuple(g_unet) + tuple(g_fin)
