@@ -1,0 +1,43 @@
+"""Single-layer conv micro-benchmark (CUDA events, L2 flushed between reps) for kernel tuning.
+   python tools/conv_bench.py [fwd|dgrad|wgrad|all] [reps]"""
+import sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wcmc_b200 import lib
+lib.init()
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dt = torch.float16
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def timeit(fn, flops, name):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = sorted(ts)[len(ts) // 2]
+    print("%-34s %8.1f us  %7.1f TFLOP/s (algorithmic)" % (name, t * 1e3, flops / t / 1e9))
+g = torch.Generator(device="cuda").manual_seed(0)
+# (name, N, H, W, cin, cout, k, pad)
+cfgs = [("kpcn mid 100->100 @120", 8, 120, 120, 100, 100, 5, 0),
+        ("kpcn first 39->100 @128", 8, 128, 128, 39, 100, 5, 0),
+        ("kpcn last 100->441 @96", 8, 96, 96, 100, 441, 5, 0),
+        ("unet 64->64 3x3 @128", 8, 128, 128, 64, 64, 3, 1),
+        ("unet 384->128 3x3 @64", 8, 64, 64, 384, 128, 3, 1),
+        ("unet 256->256 3x3 @32", 8, 32, 32, 256, 256, 3, 1),
+        ("mlp 1x1 36->64 @64x128x128", 64, 128, 128, 36, 64, 1, 0),
+        ("mlp 1x1 128->128 @64x128x128", 64, 128, 128, 128, 128, 1, 0)]
+for name, n, h, w, cin, cout, k, pad in cfgs:
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    x = lib.nchw_to_nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype=dt)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.03
+    wf, wd, bp = lib.pack_weights(wt, torch.zeros(cout, device="cuda"), want_bias=True, dtype=dt)
+    dy = lib.nchw_to_nhwc(torch.randn(n, cout, ho, wo, device="cuda", generator=g), dtype=dt)
+    fl = 2.0 * n * ho * wo * k * k * cin * cout
+    if what in ("fwd", "all"):
+        timeit(lambda: lib.conv2d(x, wf, bp, k, pad, act=1), fl, "fwd   " + name)
+    if what in ("dgrad", "all"):
+        timeit(lambda: lib.conv2d(dy, wd, None, k, k - 1 - pad, act=0, mask=x), fl, "dgrad " + name)
+    if what in ("wgrad", "all"):
+        timeit(lambda: lib.conv2d_wgrad(x, dy, cout, cin, k, pad, lib.pad16(cin), lib.pad16(cout)), fl, "wgrad " + name)

@@ -27,12 +27,11 @@
 
 namespace wcmc {
 
-constexpr int kPlaneSlots = 3;
-constexpr int kBStages = 4;
-constexpr int kPlaneBytes = 51200;   // 20 x 20 halo pixels x 128 B (k = 5, mt = 2)
-constexpr int kBStageBytes = 16384;  // 128 rows x 128 B
+constexpr int kPlaneSlots = 2;       // chunk c+1 / next region's chunk 0 load while chunk c is multiplied
+constexpr int kMaxBStages = 12;
+constexpr int kBarBytes = 1024;      // mbarriers + TMEM pointer live in the first KB
 constexpr int kConvThreads = 224;
-constexpr int kConvSmem = kPlaneSlots * kPlaneBytes + kBStages * kBStageBytes + 1024 + 256;
+constexpr int kConvSmemMax = 232448 - 1024;  // opt-in limit minus the slack used to 1024-align the base
 
 struct ConvParams {
     int N, Ho, Wo;
@@ -41,6 +40,7 @@ struct ConvParams {
     int cout_p, nt, n_tiles;
     int mt, regions_x, regions_y, total_items;
     int halo_w, halo_h;
+    int plane_stride, b_stride, b_stages;  // shared-memory carve-up (bytes, bytes, count)
     void* out;
     int out_cs, out_coff, out_dtype;
     int x_dtype, w_dtype;
@@ -58,20 +58,68 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
+// One tap = MT x NK tcgen05.mma (compile-time counts: no branches between the MMAs, descriptor
+// deltas are immediates).  Executed by the single elected lane.
+template <int MT, int NK>
+__device__ __forceinline__ void issue_tap(uint32_t d_base, uint64_t ad, uint64_t bd, uint32_t idesc,
+                                          uint32_t accum) {
+#pragma unroll
+    for (int t = 0; t < MT; ++t) {
+#pragma unroll
+        for (int j = 0; j < NK; ++j)
+            umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+    }
+}
+
+// MMA-issue state that lives across chunks / regions (all in registers of the issuing thread).
+struct BRing {
+    uint64_t* full;
+    uint64_t* empty;
+    uint32_t base_lo;   // (address of stage 0) >> 4
+    uint32_t stride_lo; // stage stride >> 4
+    uint32_t cur_lo;    // (address of the current stage) >> 4
+    int stages, idx, phase;
+};
+
+// All taps of one 64-channel chunk.  MT / NK are compile-time so the tap body is branch-free:
+// one mbarrier wait, MT*NK back-to-back tcgen05.mma, one tcgen05.commit.
+template <int MT, int NK>
+__device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int row_step, uint32_t a_lo,
+                                          uint32_t a_hi, uint32_t b_hi, uint32_t lo_fixed, uint32_t d_base,
+                                          uint32_t idesc, uint32_t& accum) {
+    int kx = 0;
+    for (int tap = 0; tap < taps; ++tap) {
+        mbar_wait(&br.full[br.idx], br.phase);
+        tc_fence_after();
+        if (elect_one()) {
+            issue_tap<MT, NK>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
+                              (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | br.cur_lo), idesc, accum);
+            umma_commit(&br.empty[br.idx]);
+        }
+        __syncwarp();
+        accum = 1;
+        br.cur_lo += br.stride_lo;
+        if (++br.idx == br.stages) { br.idx = 0; br.phase ^= 1; br.cur_lo = br.base_lo; }
+        a_lo += 8;                                   // next tap: one halo pixel (128 B) to the right ...
+        if (++kx == ksize) { kx = 0; a_lo += row_step; }  // ... or down to the next halo row
+    }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                   const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    uint8_t* planes = smem;
-    uint8_t* bst = smem + kPlaneSlots * kPlaneBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bst + kBStages * kBStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* planes = smem + kBarBytes;
+    uint8_t* bst = planes + kPlaneSlots * p.plane_stride;
+    const int kBStages = p.b_stages;
     uint64_t* plane_full = bars;
     uint64_t* plane_empty = bars + kPlaneSlots;
     uint64_t* b_full = bars + 2 * kPlaneSlots;
-    uint64_t* b_empty = b_full + kBStages;
-    uint64_t* acc_full = b_empty + kBStages;
+    uint64_t* b_empty = b_full + kMaxBStages;
+    uint64_t* acc_full = b_empty + kMaxBStages;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -118,7 +166,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                 for (int c = 0; c < p.nch; ++c) {
                     mbar_wait(&plane_empty[ps], ph ^ 1);
                     mbar_expect_tx(&plane_full[ps], plane_bytes);
-                    tma_load_4d(planes + ps * kPlaneBytes, &tmx, &plane_full[ps], c * 64,
+                    tma_load_4d(planes + ps * p.plane_stride, &tmx, &plane_full[ps], c * 64,
                                 rx * region_w - p.pad, ry * 16 - p.pad, n);
                     if (++ps == kPlaneSlots) { ps = 0; ph ^= 1; }
                 }
@@ -134,7 +182,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     for (int tap = 0; tap < taps; ++tap) {
                         mbar_wait(&b_empty[bs], ph ^ 1);
                         mbar_expect_tx(&b_full[bs], b_bytes);
-                        tma_load_3d(bst + bs * kBStageBytes, &tmw, &b_full[bs], c * 64, tap, n0);
+                        tma_load_3d(bst + bs * p.b_stride, &tmw, &b_full[bs], c * 64, tap, n0);
                         if (++bs == kBStages) { bs = 0; ph ^= 1; }
                     }
                 }
@@ -142,45 +190,55 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         }
     } else if (warp == 2) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // The whole warp runs the warp-uniform control flow (so descriptors stay in uniform registers
+        // and the tcgen05.mma of a tap issue back to back); one elected lane issues them.  Descriptors
+        // are built once per plane / stage; per MMA only the 14-bit start-address field moves, by
+        // compile-time constants (issue_tap).  The (mt, nk) dispatch happens once per chunk.
+        {
             const uint32_t idesc = make_idesc_f16(128, p.nt, 0, 0, p.x_dtype, p.w_dtype);
             const uint32_t sbo = static_cast<uint32_t>(p.halo_w * 128);
-            int ps = 0, pph = 0, bs = 0, bph = 0, it = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const uint32_t a_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 16, sbo, 0) >> 32);
+            const uint32_t b_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 16, 1024, 0) >> 32);
+            const uint32_t lo_fixed = 1u << 16;  // LBO field (16 B >> 4) sits in the low word
+            const int row_step = (p.halo_w - p.ksize) * 8;
+            const int ksize = p.ksize, nch = p.nch, cin_p = p.cin_p, mt = p.mt, total = p.total_items;
+            const uint32_t plane0_lo = smem_u32(planes) >> 4;
+            const uint32_t plane_stride_lo = static_cast<uint32_t>(p.plane_stride) >> 4;
+            BRing br;
+            br.full = b_full; br.empty = b_empty;
+            br.base_lo = smem_u32(bst) >> 4; br.stride_lo = static_cast<uint32_t>(p.b_stride) >> 4;
+            br.cur_lo = br.base_lo; br.stages = p.b_stages; br.idx = 0; br.phase = 0;
+            int ps = 0, pph = 0, it = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + buf * 256;
                 uint32_t accum = 0;
-                for (int c = 0; c < p.nch; ++c) {
+                for (int c = 0; c < nch; ++c) {
                     mbar_wait(&plane_full[ps], pph);
                     tc_fence_after();
-                    const uint32_t plane_addr = smem_u32(planes + ps * kPlaneBytes);
-                    int nk = (p.cin_p - c * 64) >> 4;
+                    const uint32_t a_lo = plane0_lo + ps * plane_stride_lo;
+                    int nk = (cin_p - c * 64) >> 4;
                     if (nk > 4) nk = 4;
-                    int ky = 0, kx = 0;
-                    for (int tap = 0; tap < taps; ++tap) {
-                        mbar_wait(&b_full[bs], bph);
-                        tc_fence_after();
-                        const uint32_t b_addr = smem_u32(bst + bs * kBStageBytes);
-                        for (int t = 0; t < p.mt; ++t) {
-                            const uint32_t a_addr =
-                                plane_addr + static_cast<uint32_t>((ky * p.halo_w + kx + 8 * t) * 128);
-                            for (int j = 0; j < nk; ++j) {
-                                uint64_t ad = make_sdesc_sw128(a_addr + 32 * j, 16, sbo, 0);
-                                uint64_t bd = make_sdesc_sw128(b_addr + 32 * j, 16, 1024, 0);
-                                umma_bf16(d_base + t * 128, ad, bd, idesc, accum | (j > 0));
-                            }
-                        }
-                        accum = 1;
-                        umma_commit(&b_empty[bs]);
-                        if (++bs == kBStages) { bs = 0; bph ^= 1; }
-                        if (++kx == p.ksize) { kx = 0; ++ky; }
+#define WCMC_CHUNK(MT, NK) mma_chunk<MT, NK>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum)
+                    switch (mt * 8 + nk) {
+                        case 8 + 1: WCMC_CHUNK(1, 1); break;
+                        case 8 + 2: WCMC_CHUNK(1, 2); break;
+                        case 8 + 3: WCMC_CHUNK(1, 3); break;
+                        case 8 + 4: WCMC_CHUNK(1, 4); break;
+                        case 16 + 1: WCMC_CHUNK(2, 1); break;
+                        case 16 + 2: WCMC_CHUNK(2, 2); break;
+                        case 16 + 3: WCMC_CHUNK(2, 3); break;
+                        default: WCMC_CHUNK(2, 4); break;
                     }
-                    umma_commit(&plane_empty[ps]);
+#undef WCMC_CHUNK
+                    if (elect_one()) umma_commit(&plane_empty[ps]);
+                    __syncwarp();
                     if (++ps == kPlaneSlots) { ps = 0; pph ^= 1; }
                 }
-                umma_commit(&acc_full[buf]);
+                if (elect_one()) umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -354,14 +412,20 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
         int rc = wcmc_encode_tmap_bf16(&tmw, w_packed, 3, dims, strides, box, 1);
         if (rc) return rc;
     }
+    p.plane_stride = ((p.halo_w * p.halo_h * 128 + 1023) / 1024) * 1024;
+    p.b_stride = ((p.nt * 128 + 1023) / 1024) * 1024;
+    p.b_stages = (kConvSmemMax - kBarBytes - kPlaneSlots * p.plane_stride) / p.b_stride;
+    if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+    WCMC_REQUIRE(p.b_stages >= 2, WCMC_ESHAPE, "conv2d: shared memory carve-up failed");
+    const int smem_bytes = 1024 + kBarBytes + kPlaneSlots * p.plane_stride + p.b_stages * p.b_stride;
     static bool attr_set = false;
     if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kConvSmemMax + 1024));
         attr_set = true;
     }
     int grid = p.total_items < sms ? p.total_items : sms;
-    conv_igemm_kernel<<<grid, kConvThreads, kConvSmem, stream>>>(tmx, tmw, p);
+    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

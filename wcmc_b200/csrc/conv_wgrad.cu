@@ -106,33 +106,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(128, p.nt, 1, 1, p.dy_dtype, p.x_dtype);
-            const uint32_t b_sbo = static_cast<uint32_t>(p.halo_w * 128);
-            int s = 0, ph = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + s * kWgStageBytes);
-                const uint32_t b_base = a_base + 2 * kWgAPlane;
-                int ky = tap0 / p.ksize, kx = tap0 % p.ksize;
+        // MMA issuer: warp-uniform control flow, one elected lane issues (see conv_igemm.cu).
+        const uint32_t idesc = make_idesc_f16(128, p.nt, 1, 1, p.dy_dtype, p.x_dtype);
+        const uint32_t b_sbo = static_cast<uint32_t>(p.halo_w * 128);
+        const uint32_t a_hi = static_cast<uint32_t>(make_sdesc_sw128(0, kWgAPlane, 1024, 0) >> 32);
+        const uint32_t b_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 0, b_sbo, 0) >> 32);
+        const uint32_t a_lbo = static_cast<uint32_t>(kWgAPlane >> 4) << 16;
+        const uint32_t b_lbo = static_cast<uint32_t>(p.b_plane >> 4) << 16;
+        const uint32_t b_kstep = static_cast<uint32_t>(2 * p.halo_w * 8);  // two halo rows per K16 step
+        const int row_step = (p.halo_w - p.ksize) * 8;
+        const int ky0 = tap0 / p.ksize, kx0 = tap0 % p.ksize;
+        int s = 0, ph = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + s * kWgStageBytes);
+            const uint32_t a_lo = a_lbo | (a_base >> 4);
+            uint32_t b_lo = b_lbo | ((a_base + 2 * kWgAPlane + static_cast<uint32_t>((ky0 * p.halo_w + kx0) * 128)) >> 4);
+            int kx = kx0;
+            if (elect_one()) {
                 for (int tl = 0; tl < ntap; ++tl) {
                     const uint32_t d = tmem_base + tl * p.cstride;
-#pragma unroll 1
+#pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        uint64_t ad = make_sdesc_sw128(a_base + j * 2048, kWgAPlane, 1024, 0);
-                        uint64_t bd = make_sdesc_sw128(
-                            b_base + static_cast<uint32_t>(((2 * j + ky) * p.halo_w + kx) * 128),
-                            static_cast<uint32_t>(p.b_plane), b_sbo, 0);
+                        const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + j * 128);
+                        const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + j * b_kstep);
                         umma_bf16(d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
                     }
-                    if (++kx == p.ksize) { kx = 0; ++ky; }
+                    b_lo += 8;
+                    if (++kx == p.ksize) { kx = 0; b_lo += row_step; }
                 }
                 umma_commit(&empty[s]);
-                if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
-            umma_commit(acc_full);
+            __syncwarp();
+            if (++s == kWgStages) { s = 0; ph ^= 1; }
         }
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
     } else {
         // epilogue: TMEM lane = cout row, columns = (tap, cin)
         const int q = warp & 3;
