@@ -117,6 +117,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--perm-rng", default="device", choices=["device", "cpu"],
+                    help="pairing permutations of the path-disentangling loss: torch.randperm on the GPU "
+                         "(default) or the reference's CPU default-generator contract (13 ms of host time per "
+                         "541,696-element permutation, four per step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -148,7 +152,7 @@ def main():
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        l_manif = FeatureMSE(non_local=True)
+        l_manif = FeatureMSE(non_local=True, rng=args.perm_rng)
     loss_funcs = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
                   "l_test": RelativeMSE(), "l_manif": l_manif}
     itf = KPCNInterface(models, optims, loss_funcs, types.SimpleNamespace(model_name="bench"), use_llpm_buf=True,
@@ -229,12 +233,13 @@ def main():
     line = {
         "metric": METRIC, "value": BATCH * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH, "spp": SPP,
                    "patch": SIZE, "pnet_out_size": OUTC, "parallelism": "dp%d" % world,
                    "l2": "inputs_exceed_l2 (%.0f MB of step inputs + %.0f MB of saved activations > 126 MB L2)"
                          % (h2d_bytes / 1e6, 700.0),
-                   "precision": "bf16 operands, fp32 accumulate / master weights / losses"},
+                   "precision": "fp16 operands (loss-scaled gradients), fp32 accumulate / master weights / losses",
+                   "perm_rng": args.perm_rng},
         "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

@@ -67,6 +67,18 @@ int wcmc_pack_weights(const float* w, const float* bias, void* dst_fwd, void* ds
                       float* dst_bias, int dtype, int cout, int cin, int ksize, int cout_p, int cin_p,
                       void* stream);
 
+/* All layers of a conv chain in one launch. */
+#define WCMC_PACK_BATCH_MAX 24
+typedef struct {
+    const float* w;     /* (cout, cin, k, k) fp32 */
+    const float* bias;  /* (cout) fp32 or NULL */
+    void* dst_fwd;      /* [cout_p][k*k][cin_p] or NULL */
+    void* dst_dgrad;    /* [cin_p][k*k][cout_p] or NULL */
+    float* dst_bias;    /* [cout_p] or NULL */
+    int cout, cin, ksize, cout_p, cin_p;
+} wcmc_pack_desc;
+int wcmc_pack_weights_batch(const wcmc_pack_desc* host_descs, int n, int dtype, void* stream);
+
 /* ---- K1/K2: convolution forward / data gradient (tcgen05 implicit GEMM) -----------------------
  * Replaces nn.Conv2d(+ReLU) inside sbmc.modules.ConvChain (used at
  * /root/reference/support/networks.py:18-24 and by sbmc.KPCN, train_kpcn.py:213).

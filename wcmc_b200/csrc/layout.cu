@@ -92,28 +92,75 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     }
 }
 
-// db[c] (+)= sum_pix dy[pix][c].  grid.x CTAs each reduce a slab of pixels, then atomics.
+struct PackBatch {
+    wcmc_pack_desc d[WCMC_PACK_BATCH_MAX];
+};
+
+// blockIdx.y = layer; same element mapping as pack_weights_kernel
+__global__ void pack_weights_batch_kernel(const PackBatch pb, int dtype) {
+    const wcmc_pack_desc& L = pb.d[blockIdx.y];
+    const int taps = L.ksize * L.ksize;
+    const long total = static_cast<long>(L.cout_p) * taps * L.cin_p;
+    if (L.dst_bias != nullptr && blockIdx.x == 0)
+        for (int c = threadIdx.x; c < L.cout_p; c += blockDim.x)
+            L.dst_bias[c] = (L.bias != nullptr && c < L.cout) ? L.bias[c] : 0.f;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        if (L.dst_fwd != nullptr) {
+            int ci = static_cast<int>(i % L.cin_p);
+            int tap = static_cast<int>((i / L.cin_p) % taps);
+            int co = static_cast<int>(i / (static_cast<long>(L.cin_p) * taps));
+            float v = (co < L.cout && ci < L.cin) ? L.w[(static_cast<long>(co) * L.cin + ci) * taps + tap] : 0.f;
+            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_fwd)[i] = __float2half_rn(v);
+            else static_cast<__nv_bfloat16*>(L.dst_fwd)[i] = __float2bfloat16_rn(v);
+        }
+        if (L.dst_dgrad != nullptr) {
+            int co = static_cast<int>(i % L.cout_p);
+            int tapf = static_cast<int>((i / L.cout_p) % taps);
+            int ci = static_cast<int>(i / (static_cast<long>(L.cout_p) * taps));
+            int tap = taps - 1 - tapf;
+            float v = (co < L.cout && ci < L.cin) ? L.w[(static_cast<long>(co) * L.cin + ci) * taps + tap] : 0.f;
+            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_dgrad)[i] = __float2half_rn(v);
+            else static_cast<__nv_bfloat16*>(L.dst_dgrad)[i] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// db[c] (+)= scale * sum_pix dy[pix][coff + c].  One thread owns an 8-channel group (16-byte loads,
+// consecutive threads = consecutive groups of one pixel row: coalesced), the remaining thread
+// dimension strides over the CTA's slab of pixels; shared-memory reduce, then one atomic per channel.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long npix, int cs, int coff, int cout,
                  float* __restrict__ db, int dtype, const float* __restrict__ scale) {
-    extern __shared__ float red[];  // [8][cout]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ float red[];  // [PL][G*8]
+    const int G = (cout + 7) >> 3;
+    const int PL = 256 / G;
+    const int g = threadIdx.x % G, pl = threadIdx.x / G;
     const long per = (npix + gridDim.x - 1) / gridDim.x;
     const long b = blockIdx.x * per, e = min(npix, b + per);
-    for (int c0 = 0; c0 < cout; c0 += 32) {
-        int c = c0 + lane;
-        float s = 0.f;
-        if (c < cout)
-            for (long p = b + warp; p < e; p += 8)
-                s += dtype == WCMC_F16 ? __half2float(reinterpret_cast<const __half*>(dy)[p * cs + coff + c])
-                                       : __bfloat162float(dy[p * cs + coff + c]);
-        if (c < cout) red[warp * cout + c] = s;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (pl < PL) {
+        for (long p = b + pl; p < e; p += PL) {
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + p * cs + coff + g * 8));
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 f = unpack_h2(w[i], dtype);
+                acc[2 * i] += f.x;
+                acc[2 * i + 1] += f.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[pl * G * 8 + g * 8 + k] = acc[k];
     }
     __syncthreads();
+    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     for (int c = threadIdx.x; c < cout; c += 256) {
         float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += red[w * cout + c];
-        atomicAdd(db + c, s * (scale != nullptr ? __ldg(scale) : 1.f));
+        for (int q = 0; q < PL; ++q) s += red[q * G * 8 + c];
+        atomicAdd(db + c, s * sc);
     }
 }
 
@@ -181,6 +228,28 @@ extern "C" int wcmc_pack_weights(const float* w, const float* bias, void* dst_fw
     return WCMC_OK;
 }
 
+extern "C" int wcmc_pack_weights_batch(const wcmc_pack_desc* descs, int n, int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(descs != nullptr && n > 0, WCMC_ESHAPE, "pack_weights_batch: empty batch");
+    for (int base = 0; base < n; base += WCMC_PACK_BATCH_MAX) {
+        PackBatch pb;
+        const int m = std::min(WCMC_PACK_BATCH_MAX, n - base);
+        long max_total = 0;
+        for (int i = 0; i < m; ++i) {
+            pb.d[i] = descs[base + i];
+            const wcmc_pack_desc& L = pb.d[i];
+            WCMC_REQUIRE(L.cout > 0 && L.cin > 0 && L.cout_p >= L.cout && L.cin_p >= L.cin && L.ksize > 0 &&
+                             L.w != nullptr,
+                         WCMC_ESHAPE, "pack_weights_batch: bad layer %d", base + i);
+            max_total = std::max(max_total, static_cast<long>(L.cout_p) * L.cin_p * L.ksize * L.ksize);
+        }
+        dim3 grid(static_cast<unsigned>(std::min<long>((max_total + 255) / 256, 148)), m);
+        pack_weights_batch_kernel<<<grid, 256, 0, stream>>>(pb, dtype);
+        WCMC_LAUNCH_CHECK();
+    }
+    return WCMC_OK;
+}
+
 extern "C" int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs, int dy_coff, int cout, float* db,
                               int accumulate, const float* scale, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -190,8 +259,11 @@ extern "C" int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs,
         zero_f32_kernel<<<1, 256, 0, stream>>>(db, cout);
         WCMC_LAUNCH_CHECK();
     }
-    int blocks = std::min(296, (npix + 255) / 256);
-    bias_grad_kernel<<<blocks, 256, 8 * cout * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy),
+    WCMC_REQUIRE(dy_cs % 8 == 0 && dy_coff % 8 == 0 && dy_coff + ((cout + 7) / 8) * 8 <= dy_cs, WCMC_EALIGN,
+                 "bias_grad: channel stride/offset must be multiples of 8 and cover cout rounded up to 8");
+    int blocks = std::min(592, (npix + 63) / 64);
+    const int G = (cout + 7) / 8;
+    bias_grad_kernel<<<blocks, 256, static_cast<size_t>(256 / G) * G * 8 * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy),
                                                                         npix, dy_cs, dy_coff, cout, db, dy_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

@@ -6,6 +6,7 @@ the CPU default generator, `randperm(S*H*W)` then `randperm(B*S*H*W)` per call (
 so a seeded run pairs exactly the same samples as the reference.
 """
 import math
+import os
 
 import torch
 
@@ -32,6 +33,19 @@ def _displacement(p, r, idx, dim):
     return d_p - d_r
 
 
+def _randperm(n, device, rng):
+    """rng='cpu': the reference's contract (CPU default generator, then a host->device copy; 13 ms
+    of host time for n = 541,696).  rng='device': torch.randperm on the GPU -- the same distribution
+    from a different stream; used by the throughput benchmark."""
+    if rng == "device":
+        return torch.randperm(n, device=device)
+    return torch.randperm(n)
+
+
+def _default_rng():
+    return os.environ.get("WCMC_PERM_RNG", "cpu")
+
+
 def _check_finite(*tensors):
     ok = torch.stack([torch.isfinite(t).all() for t in tensors]).all()
     if not bool(ok):
@@ -43,12 +57,14 @@ class FeatureMSE(torch.nn.Module):
     (1/2|p_i - p_j|^2 - 1/2|t_i - t_j|^2)^2, once with pairs inside each patch and (non_local)
     once with pairs across the whole batch."""
 
-    def __init__(self, color="rgb", non_local=True):
+    def __init__(self, color="rgb", non_local=True, rng=None):
         super().__init__()
         if color != "rgb":
             raise NotImplementedError("color='hls' is never selected by the reference scripts")
         self.color = color
         self.non_local = non_local
+        self.rng = rng or _default_rng()
+        assert self.rng in ("cpu", "device")
         print("FeatureMSE locality: %s" % ("Non-local" if non_local else "Local"))
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
@@ -57,12 +73,12 @@ class FeatureMSE(torch.nn.Module):
         _check_finite(p_buffer, t)
         p, r = _rows(p_buffer, t)
         if idx_patch is None:
-            idx_patch = torch.randperm(s * h * w)
+            idx_patch = _randperm(s * h * w, p.device, self.rng)
         loss_p = 0.5 * _displacement(p, r, idx_patch, 1).pow(2).mean()
         if not self.non_local:
             return loss_p + loss_p
         if idx_batch is None:
-            idx_batch = torch.randperm(b * s * h * w)
+            idx_batch = _randperm(b * s * h * w, p.device, self.rng)
         loss_b = 0.5 * _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0).pow(2).mean()
         return loss_p + loss_b
 
@@ -70,19 +86,20 @@ class FeatureMSE(torch.nn.Module):
 class GlobalRelativeSimilarityLoss(torch.nn.Module):
     """(LSE(alpha * [d_p, d_b, -d_p, -d_b, 0]) - log(1 + 4N)) / sqrt(alpha)   (losses.py:185-211)."""
 
-    def __init__(self, alpha=2, color="rgb"):
+    def __init__(self, alpha=2, color="rgb", rng=None):
         super().__init__()
         self.color = color
         self.alpha = alpha
+        self.rng = rng or _default_rng()
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
         _check_finite(p_buffer, ref)
         b, s, c, h, w = p_buffer.shape
         p, r = _rows(p_buffer, _tonemap_gamma(ref))
         if idx_patch is None:
-            idx_patch = torch.randperm(s * h * w)
+            idx_patch = _randperm(s * h * w, p.device, self.rng)
         if idx_batch is None:
-            idx_batch = torch.randperm(b * s * h * w)
+            idx_batch = _randperm(b * s * h * w, p.device, self.rng)
         d_p = _displacement(p, r, idx_patch, 1).reshape(-1)
         d_b = _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0)
         zero = torch.zeros(1, dtype=p.dtype, device=p.device)

@@ -18,6 +18,13 @@ _inited_devices = set()
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
+class PackDesc(ctypes.Structure):
+    """wcmc_pack_desc of include/wcmc.h"""
+    _fields_ = [("w", c_void_p), ("bias", c_void_p), ("dst_fwd", c_void_p), ("dst_dgrad", c_void_p),
+                ("dst_bias", c_void_p), ("cout", c_int), ("cin", c_int), ("ksize", c_int), ("cout_p", c_int),
+                ("cin_p", c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/wcmc.h (tests check this).
 SIGNATURES = {
     "wcmc_last_error": (ctypes.c_char_p, []),
@@ -26,6 +33,7 @@ SIGNATURES = {
     "wcmc_nchw_f32_to_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
     "wcmc_nhwc_to_nchw_f32": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
     "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "wcmc_pack_weights_batch": (c_int, [ctypes.POINTER(PackDesc), c_int, c_int, c_void_p]),
     "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
                     + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
@@ -110,19 +118,36 @@ def _check(rc, what):
         raise WcmcError("%s failed (%d): %s" % (what, rc, load().wcmc_last_error().decode()))
 
 
+_ready = {"lib": None, "dev": -1}
+
+
 def init(device=None):
+    """Loads the library and checks the device once; afterwards a dictionary lookup (this sits on
+    the launch path of every kernel).  `device`: None (current), int, or torch.device."""
+    lib = _ready["lib"]
+    if lib is not None:
+        idx = device if isinstance(device, int) else (None if device is None else device.index)
+        if idx is None or idx == _ready["dev"]:
+            return lib
     lib = load()
     if not torch.cuda.is_available():
         raise WcmcError("wcmc_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
-    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if isinstance(device, int):
+        dev = device
+    elif device is None or torch.device(device).index is None:
+        dev = torch.cuda.current_device()
+    else:
+        dev = torch.device(device).index
     if dev not in _inited_devices:
         _check(lib.wcmc_init(dev), "wcmc_init")
         _inited_devices.add(dev)
+    _ready["lib"], _ready["dev"] = lib, dev
     return lib
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~15 us per call)
+    return torch._C._cuda_getCurrentRawStream(_ready["dev"])
 
 
 def _p(t):
@@ -202,6 +227,32 @@ def pack_weights(w, bias=None, cout_p=None, cin_p=None, fwd=True, dgrad=True, wa
     if want_bias:
         return f, d, bp
     return f, d
+
+
+def pack_weights_batch(specs, dtype=torch.bfloat16, dgrad=True):
+    """specs: [(w, bias, cout_p, cin_p)] -> [(fwd, dgrad or None, bias_p)], one kernel launch."""
+    lib = init(specs[0][0].device)
+    n = len(specs)
+    descs = (PackDesc * n)()
+    out, keep = [], []
+    for i, (w, bias, cout_p, cin_p) in enumerate(specs):
+        w = w.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        cout, cin, k, _ = w.shape
+        f = torch.empty((cout_p, k * k, cin_p), dtype=dtype, device=w.device)
+        d = torch.empty((cin_p, k * k, cout_p), dtype=dtype, device=w.device) if dgrad else None
+        bp = torch.empty((cout_p,), dtype=torch.float32, device=w.device)
+        if bias is not None:
+            bias = bias.detach()
+            if bias.dtype != torch.float32 or not bias.is_contiguous():
+                bias = bias.float().contiguous()
+        keep.append((w, bias))
+        descs[i] = PackDesc(w.data_ptr(), _p(bias), f.data_ptr(), _p(d), bp.data_ptr(), cout, cin, k, cout_p, cin_p)
+        out.append((f, d, bp))
+    _run(lib.wcmc_pack_weights_batch, "pack_weights", sum(s[0].numel() for s in specs) * 8.0, descs, n,
+         _DT[dtype], _stream())
+    return out
 
 
 def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype=None, x_coff=0, mask=None,

@@ -71,12 +71,8 @@ class Slice:
 
 def pack_chain(layers: List[LayerSpec], params, need_dgrad=True):
     """params = [w0, b0, w1, b1, ...] (torch layout fp32) -> [(w_fwd, w_dgrad, bias_p)]."""
-    packed = []
-    for i, l in enumerate(layers):
-        w, b = params[2 * i], params[2 * i + 1]
-        packed.append(lib.pack_weights(w, b, cout_p=l.cout_p, cin_p=l.cin_p, dgrad=need_dgrad, want_bias=True,
-                                       dtype=ACT_DTYPE))
-    return packed
+    specs = [(params[2 * i], params[2 * i + 1], l.cout_p, l.cin_p) for i, l in enumerate(layers)]
+    return lib.pack_weights_batch(specs, dtype=ACT_DTYPE, dgrad=need_dgrad)
 
 
 def chain_forward(x: Slice, layers, packed, out: Optional[Slice] = None, last_fp32=False):
