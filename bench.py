@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python (no CUDA graph)")
     ap.add_argument("--perm-rng", default="device", choices=["device", "cpu"],
                     help="pairing permutations of the path-disentangling loss: torch.randperm on the GPU "
                          "(default) or the reference's CPU default-generator contract (13 ms of host time per "
@@ -165,9 +166,17 @@ def main():
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     itf.to_train_mode()
 
+    use_graph = not args.no_graph and args.perm_rng == "device"
+    if use_graph:
+        from wcmc_b200.engine import GraphedTrainStep
+        graphed = GraphedTrainStep(itf, dev)
+
     def step(batch):
-        itf.preprocess(batch)
-        itf.train_batch(batch)
+        if use_graph:
+            graphed(batch)
+        else:
+            itf.preprocess(batch)
+            itf.train_batch(batch)
 
     def barrier():
         if world > 1:
@@ -192,23 +201,32 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    n0 = lib.LAUNCHES["count"]
     ms_step = timed(lambda: step(dev), args.steps)
-    launches = (lib.LAUNCHES["count"] - n0) // args.steps
     clk = clocks.stop() if rank == 0 else None
 
-    # live per-kernel device time (CUDA events on the launching stream) over a second timed pass
+    # live per-kernel device time (CUDA events on the launching stream) over a second timed pass.  The
+    # kernels are the same ones the graph replays; this pass launches them eagerly so that each launch
+    # can be bracketed by events.
+    def eager_step():
+        itf.preprocess(dev)
+        itf.train_batch(dev)
+    eager_step()
+    n0 = lib.LAUNCHES["count"]
     lib.profile_start()
-    timed(lambda: step(dev), args.steps)
+    timed(eager_step, args.steps)
     prof = lib.profile_stop()
+    launches = (lib.LAUNCHES["count"] - n0) // args.steps
 
     # end to end: pinned host batch -> device every step, loss read back every step
     dev2 = {k: torch.empty_like(v, device="cuda") for k, v in host.items()}
 
     def e2e_step():
-        for k in host:
-            dev2[k].copy_(host[k], non_blocking=True)
-        step(dev2)
+        if use_graph:
+            step(host)   # GraphedTrainStep copies the pinned host batch straight into its input buffers
+        else:
+            for k in host:
+                dev2[k].copy_(host[k], non_blocking=True)
+            step(dev2)
         return float(itf.m_losses["m_l_total"])  # device -> host read of the step's loss
 
     e2e_step()
@@ -239,7 +257,7 @@ def main():
                    "l2": "inputs_exceed_l2 (%.0f MB of step inputs + %.0f MB of saved activations > 126 MB L2)"
                          % (h2d_bytes / 1e6, 700.0),
                    "precision": "fp16 operands (loss-scaled gradients), fp32 accumulate / master weights / losses",
-                   "perm_rng": args.perm_rng},
+                   "perm_rng": args.perm_rng, "cuda_graph": bool(use_graph)},
         "e2e": {"value": BATCH * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

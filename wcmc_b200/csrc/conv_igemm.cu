@@ -27,10 +27,10 @@
 
 namespace wcmc {
 
-constexpr int kPlaneSlots = 2;       // chunk c+1 / next region's chunk 0 load while chunk c is multiplied
+constexpr int kMaxPlaneSlots = 4;
 constexpr int kMaxBStages = 12;
 constexpr int kBarBytes = 1024;      // mbarriers + TMEM pointer live in the first KB
-constexpr int kConvThreads = 224;
+constexpr int kConvThreads = 96 + 256;  // 3 single-role warps + 8 epilogue warps
 constexpr int kConvSmemMax = 232448 - 1024;  // opt-in limit minus the slack used to 1024-align the base
 
 struct ConvParams {
@@ -40,7 +40,7 @@ struct ConvParams {
     int cout_p, nt, n_tiles;
     int mt, regions_x, regions_y, total_items;
     int halo_w, halo_h;
-    int plane_stride, b_stride, b_stages;  // shared-memory carve-up (bytes, bytes, count)
+    int plane_stride, b_stride, b_stages, plane_slots;  // shared-memory carve-up
     void* out;
     int out_cs, out_coff, out_dtype;
     int x_dtype, w_dtype;
@@ -113,11 +113,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                                                ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint8_t* planes = smem + kBarBytes;
+    const int kPlaneSlots = p.plane_slots;
     uint8_t* bst = planes + kPlaneSlots * p.plane_stride;
     const int kBStages = p.b_stages;
     uint64_t* plane_full = bars;
-    uint64_t* plane_empty = bars + kPlaneSlots;
-    uint64_t* b_full = bars + 2 * kPlaneSlots;
+    uint64_t* plane_empty = bars + kMaxPlaneSlots;
+    uint64_t* b_full = bars + 2 * kMaxPlaneSlots;
     uint64_t* b_empty = b_full + kMaxBStages;
     uint64_t* acc_full = b_empty + kMaxBStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -139,7 +140,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
+            mbar_init(&acc_empty[i], 256);
         }
         fence_barrier_init();
     }
@@ -242,10 +243,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             }
         }
     } else {
-        // ---------------- epilogue ----------------
+        // ---------------- epilogue (8 warps) ----------------
+        // warp w: TMEM lane quarter q = w & 3 (hardware rule), half h = (w - 3) >> 2.  With two M tiles
+        // each half owns one tile; with one tile the halves interleave 16-column chunks.  TMEM loads are
+        // software pipelined (the load of chunk i+1 is in flight while chunk i is processed).
         const int q = warp & 3;
+        const int half = (warp - 3) >> 2;
         const int m = q * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
+        const int cc0 = (p.mt == 2) ? 0 : half;
+        const int ccs = (p.mt == 2) ? 1 : 2;
+        const int t = (p.mt == 2) ? half : 0;
         int it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -258,63 +266,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            for (int t = 0; t < p.mt; ++t) {
-                const int oy = ry * 16 + ty;
-                const int ox = rx * region_w + 8 * t + tx;
-                const bool valid = (oy < p.Ho) && (ox < p.Wo);
-                const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
-                const uint32_t taddr =
-                    tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
-                for (int cc = 0; cc < ncc; ++cc) {
-                    uint32_t v[16];
+            const int oy = ry * 16 + ty;
+            const int ox = rx * region_w + 8 * t + tx;
+            const bool valid = (oy < p.Ho) && (ox < p.Wo);
+            const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
+
+            auto process = [&](const uint32_t (&v)[16], int cc) {
+                if (!valid) return;
+                const int ch = n0 + cc * 16;
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                if (p.bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 b = __ldg(b4 + i);
+                        f[4 * i + 0] += b.x;
+                        f[4 * i + 1] += b.y;
+                        f[4 * i + 2] += b.z;
+                        f[4 * i + 3] += b.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
+                if (p.mask != nullptr) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cs + p.mask_coff + ch);
+                    uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                    uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        f[2 * i] *= h16_pos(mw[i] & 0xFFFFu) ? 1.f : p.slope;
+                        f[2 * i + 1] *= h16_pos(mw[i] >> 16) ? 1.f : p.slope;
+                    }
+                }
+                if (p.out_dtype == WCMC_F32) {
+                    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                } else {
+                    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs +
+                                                         p.out_coff + ch);
+                    const int dt = p.out_dtype;
+                    op[0] = make_uint4(pack_h2(f[0], f[1], dt), pack_h2(f[2], f[3], dt), pack_h2(f[4], f[5], dt),
+                                       pack_h2(f[6], f[7], dt));
+                    op[1] = make_uint4(pack_h2(f[8], f[9], dt), pack_h2(f[10], f[11], dt),
+                                       pack_h2(f[12], f[13], dt), pack_h2(f[14], f[15], dt));
+                }
+            };
+
+            uint32_t va[16], vb[16];
+            __syncwarp();
+            if (cc0 < ncc) tmem_ld16(taddr + cc0 * 16, va);
+            for (int cc = cc0; cc < ncc; cc += 2 * ccs) {
+                tmem_ld_wait16(va);
+                const int c1 = cc + ccs;
+                __syncwarp();
+                if (c1 < ncc) tmem_ld16(taddr + c1 * 16, vb);
+                process(va, cc);
+                if (c1 < ncc) {
+                    tmem_ld_wait16(vb);
+                    const int c2 = c1 + ccs;
                     __syncwarp();
-                    tmem_ld16(taddr + cc * 16, v);
-                    tmem_ld_wait();
-                    if (valid) {
-                    const int ch = n0 + cc * 16;
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    if (p.bias != nullptr) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float4 b = __ldg(b4 + i);
-                            f[4 * i + 0] += b.x;
-                            f[4 * i + 1] += b.y;
-                            f[4 * i + 2] += b.z;
-                            f[4 * i + 3] += b.w;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
-                    if (p.mask != nullptr) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(
-                            p.mask + pix * p.mask_cs + p.mask_coff + ch);
-                        uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-                        uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            f[2 * i] *= h16_pos(mw[i] & 0xFFFFu) ? 1.f : p.slope;
-                            f[2 * i + 1] *= h16_pos(mw[i] >> 16) ? 1.f : p.slope;
-                        }
-                    }
-                    if (p.out_dtype == WCMC_F32) {
-                        float4* op = reinterpret_cast<float4*>(
-                            static_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            op[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(
-                            static_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + p.out_coff + ch);
-                        const int dt = p.out_dtype;
-                        op[0] = make_uint4(pack_h2(f[0], f[1], dt), pack_h2(f[2], f[3], dt),
-                                           pack_h2(f[4], f[5], dt), pack_h2(f[6], f[7], dt));
-                        op[1] = make_uint4(pack_h2(f[8], f[9], dt), pack_h2(f[10], f[11], dt),
-                                           pack_h2(f[12], f[13], dt), pack_h2(f[14], f[15], dt));
-                    }
-                    }  // valid
+                    if (c2 < ncc) tmem_ld16(taddr + c2 * 16, va);
+                    process(vb, c1);
                 }
             }
             tc_fence_before();
@@ -414,10 +431,14 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     }
     p.plane_stride = ((p.halo_w * p.halo_h * 128 + 1023) / 1024) * 1024;
     p.b_stride = ((p.nt * 128 + 1023) / 1024) * 1024;
-    p.b_stages = (kConvSmemMax - kBarBytes - kPlaneSlots * p.plane_stride) / p.b_stride;
+    // Two halo slots are enough when a chunk carries k*k taps of MMAs (the next plane loads during a whole
+    // chunk); 1x1 convolutions have one tap per region and are HBM-bound: give them a deeper plane ring.
+    p.plane_slots = (ksize == 1) ? kMaxPlaneSlots : 2;
+    p.b_stages = (kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride) / p.b_stride;
     if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
+    if (ksize == 1 && p.b_stages > 4) p.b_stages = 4;
     WCMC_REQUIRE(p.b_stages >= 2, WCMC_ESHAPE, "conv2d: shared memory carve-up failed");
-    const int smem_bytes = 1024 + kBarBytes + kPlaneSlots * p.plane_stride + p.b_stages * p.b_stride;
+    const int smem_bytes = 1024 + kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
     static bool attr_set = false;
     if (!attr_set) {
         WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

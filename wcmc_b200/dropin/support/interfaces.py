@@ -216,13 +216,17 @@ class KPCNInterface(BaseInterface):
         order = ["l_diffuse", "l_specular", "l_manif_diffuse", "l_manif_specular", "l_total", "rmse"]
         return {k: losses[k] for k in order if k in losses}
 
-    def _logging(self, loss_dict):
+    def _assert_finite(self, loss_dict):
         keys = list(loss_dict)
         vals = torch.stack([loss_dict[k].reshape(()) for k in keys])
         finite = torch.isfinite(vals)
         if not bool(finite.all()):  # the single host sync of the step
             bad = keys[int((~finite).nonzero()[0])]
             raise RuntimeError("%s: Non-finite loss at train time." % bad)
+
+    def _logging(self, loss_dict):
+        keys = list(loss_dict)
+        self._assert_finite(loss_dict)
         if self.grad_sync is not None:
             self.grad_sync(self.models)
         for model in self.models.values():

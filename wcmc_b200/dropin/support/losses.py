@@ -46,8 +46,17 @@ def _default_rng():
     return os.environ.get("WCMC_PERM_RNG", "cpu")
 
 
+# When True the finite flag of the last call is left on the device in `FINITE_FLAGS` instead of being
+# checked with a host sync: wcmc_b200.engine.GraphedTrainStep (CUDA-graph capture) reads it once per step.
+DEFER_FINITE_CHECK = False
+FINITE_FLAGS = []
+
+
 def _check_finite(*tensors):
     ok = torch.stack([torch.isfinite(t).all() for t in tensors]).all()
+    if DEFER_FINITE_CHECK:
+        FINITE_FLAGS.append(ok)
+        return
     if not bool(ok):
         raise RuntimeError("Infinite loss at train time.")
 
