@@ -217,16 +217,20 @@ def main():
     prof = lib.profile_stop()
     launches = (lib.LAUNCHES["count"] - n0) // args.steps
 
-    # end to end: pinned host batch -> device every step, loss read back every step
-    dev2 = {k: torch.empty_like(v, device="cuda") for k, v in host.items()}
+    # end to end: every step's batch comes from pinned host memory (double-buffered copy stream, so the
+    # PCIe transfer of step i+1 overlaps the compute of step i) and the step's loss is read back
+    from wcmc_b200.engine import DevicePrefetcher
+
+    def host_batches():
+        while True:
+            yield host
+
+    pf = DevicePrefetcher(host_batches())
 
     def e2e_step():
-        if use_graph:
-            step(host)   # GraphedTrainStep copies the pinned host batch straight into its input buffers
-        else:
-            for k in host:
-                dev2[k].copy_(host[k], non_blocking=True)
-            step(dev2)
+        batch = next(pf)
+        step(batch)
+        pf.release()
         return float(itf.m_losses["m_l_total"])  # device -> host read of the step's loss
 
     e2e_step()

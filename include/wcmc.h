@@ -88,12 +88,16 @@ int wcmc_pack_weights_batch(const wcmc_pack_desc* host_descs, int n, int dtype, 
  * bias: fp32[cout_p] or NULL; y: NHWC (N,Ho,Wo,y_cs) in y_dtype (bf16 / f16 / f32), channels
  * [y_coff, y_coff+cout_p), Ho = H + 2*pad - ksize + 1.  mask (optional, NHWC bf16 with the
  * spatial size of y) fuses the activation derivative of the previous layer into a dgrad.
+ * colsum (optional, fp32[cout_p], caller zero-initialises): colsum[c] += *colsum_scale * sum over all
+ * output pixels of y[.., c] -- a data-gradient launch thereby also produces the bias gradient of
+ * the layer below it.
  * flags: 0 for production (test knobs: bits 4-5 force m tiles per region, bits 8-15 force the
  * n tile).                                                                                    */
 int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                 const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
                 void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask, int mask_cs,
-                int mask_coff, float slope, int flags, void* stream);
+                int mask_coff, float slope, float* colsum, const float* colsum_scale, int flags,
+                void* stream);
 
 /* ---- K3: convolution weight gradient (tcgen05, MN-major operands, split-K) --------------------
  * Autograd of nn.Conv2d w.r.t. its weight (reference: `L_diffuse.backward()`,

@@ -50,6 +50,8 @@ struct ConvParams {
     int mask_cs, mask_coff;
     float slope;
     int flags;
+    float* colsum;             // optional: colsum[ch] += colsum_scale * sum over valid pixels of the output
+    const float* colsum_scale;  // device scalar or null
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -273,7 +275,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
 
             auto process = [&](const uint32_t (&v)[16], int cc) {
-                if (!valid) return;
+                if (!valid && p.colsum == nullptr) return;
                 const int ch = n0 + cc * 16;
                 float f[16];
 #pragma unroll
@@ -291,7 +293,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], p.act, p.slope);
-                if (p.mask != nullptr) {
+                if (p.mask != nullptr && valid) {
                     const uint4* mp = reinterpret_cast<const uint4*>(p.mask + pix * p.mask_cs + p.mask_coff + ch);
                     uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
                     uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
@@ -300,6 +302,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                         f[2 * i] *= h16_pos(mw[i] & 0xFFFFu) ? 1.f : p.slope;
                         f[2 * i + 1] *= h16_pos(mw[i] >> 16) ? 1.f : p.slope;
                     }
+                }
+                if (p.colsum != nullptr) {
+                    // per-channel sum over the 32 pixels of this warp: butterfly that halves the number of
+                    // live values at every step (16 shuffles instead of 80), then one atomic per channel
+                    float w8[8], w4[4], w2[2];
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float keep = valid ? (h16 ? f[i + 8] : f[i]) : 0.f;
+                        float send = valid ? (h16 ? f[i] : f[i + 8]) : 0.f;
+                        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        w4[i] = (h8 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[i] : w8[i + 4], 8);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        w2[i] = (h4 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? w4[i] : w4[i + 2], 4);
+                    float w1 = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
+                    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                    if ((lane & 1) == 0) {
+                        const int c = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+                        const float sc = p.colsum_scale != nullptr ? __ldg(p.colsum_scale) : 1.f;
+                        atomicAdd(p.colsum + ch + c, w1 * sc);
+                    }
+                    if (!valid) return;
                 }
                 if (p.out_dtype == WCMC_F32) {
                     float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * p.out_cs + p.out_coff + ch);
@@ -358,7 +386,8 @@ static int pick_nt(int cout_p) {
 extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                            const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
                            void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
-                           int mask_cs, int mask_coff, float slope, int flags, void* stream_) {
+                           int mask_cs, int mask_coff, float slope, float* colsum, const float* colsum_scale,
+                           int flags, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "conv2d: ksize %d not in {1,3,5}", ksize);
     WCMC_REQUIRE((x_dtype == WCMC_BF16 || x_dtype == WCMC_F16) && (w_dtype == WCMC_BF16 || w_dtype == WCMC_F16) &&
@@ -408,6 +437,7 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.bias = bias; p.act = act;
     p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
     p.slope = slope; p.flags = flags;
+    p.colsum = colsum; p.colsum_scale = colsum_scale;
 
     CUtensorMap tmx, tmw;
     {

@@ -81,3 +81,60 @@ class GraphedTrainStep:
         itf._logging(self.loss)       # finite check of the losses, grad sync, clip, m_losses
         itf._optimization()
         return self.loss
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging of training batches on a copy stream, so the PCIe
+    transfer of batch i+1 overlaps the compute of batch i (the reference's loop does a blocking
+    `.cuda()` per tensor before every step, /root/reference/train_kpcn.py:47-50).
+
+        pf = DevicePrefetcher(host_batches)      # iterable of dicts of (pinned) CPU tensors
+        for dev_batch in pf: step(dev_batch)
+    """
+
+    def __init__(self, batches, device=None):
+        self.it = iter(batches)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]
+        self.i = 0
+        self._issue(0)
+
+    def _issue(self, slot):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.bufs[slot] = None
+            return
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[slot] is not None:
+                self.copy_stream.wait_event(self.free[slot])   # the consumer of this slot has finished
+            if self.bufs[slot] is None or any(self.bufs[slot][k].shape != v.shape for k, v in host.items()):
+                self.bufs[slot] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            for k, v in host.items():
+                self.bufs[slot][k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        slot = self.i & 1
+        if self.bufs[slot] is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[slot])
+        batch = self.bufs[slot]
+        self.i += 1
+        self._issue(self.i & 1)    # start the next transfer while this batch is being consumed
+        return batch
+
+    def release(self, batch_slot_index=None):
+        """Call after the step that consumed the batch returned by the previous __next__ has been
+        enqueued: marks that slot reusable once the current stream reaches this point."""
+        slot = (self.i - 1) & 1
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[slot] = ev

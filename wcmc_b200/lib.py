@@ -35,7 +35,7 @@ SIGNATURES = {
     "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "wcmc_pack_weights_batch": (c_int, [ctypes.POINTER(PackDesc), c_int, c_int, c_void_p]),
     "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
-                    + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_int, c_void_p]),
+                    + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
     "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 6 + [c_void_p]
                           + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -256,7 +256,7 @@ def pack_weights_batch(specs, dtype=torch.bfloat16, dgrad=True):
 
 
 def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype=None, x_coff=0, mask=None,
-           mask_coff=0, slope=0.0, flags=0, cin=None, cout=None):
+           mask_coff=0, slope=0.0, flags=0, cin=None, cout=None, colsum=None, colsum_scale=None):
     """x (N,H,W,Cs) 16-bit NHWC; w_packed (cout_p, k*k, cin_p) 16-bit; returns the NHWC output
     (dtype `out_dtype`, default = x's dtype; torch.float32 for the logits layer)."""
     lib = init(x.device)
@@ -274,7 +274,8 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype
     _run(lib.wcmc_conv2d, "conv2d", 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, _p(bias),
          ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),
-         0 if mask is None else mask.shape[3], mask_coff, float(slope), flags, _stream())
+         0 if mask is None else mask.shape[3], mask_coff, float(slope), _p(colsum), _p(colsum_scale), flags,
+         _stream())
     return out
 
 

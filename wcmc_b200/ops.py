@@ -99,6 +99,14 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
     """dz = (loss-scaled) gradient w.r.t. the PRE-activation output of the last layer (16-bit NHWC
     slice).  Returns (dx Slice or None [still scaled], [dw0, db0, dw1, db1, ...] [un-scaled fp32])."""
     grads = [None] * (2 * len(layers))
+    # bias gradients of layers 0..L-2 come for free from the epilogue of the data-gradient launch that
+    # produces their dz (column sums); one zero-filled buffer serves the whole chain
+    db_all = None
+    if want_param_grads and len(layers) > 1:
+        offs = [0]
+        for l in layers[:-1]:
+            offs.append(offs[-1] + l.cout_p)
+        db_all = torch.zeros(offs[-1], dtype=torch.float32, device=dz.t.device)
     for i in range(len(layers) - 1, -1, -1):
         l = layers[i]
         xin = acts[i]
@@ -107,7 +115,10 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
         if want_param_grads:
             grads[2 * i] = lib.conv2d_wgrad(xin.t, dz.t, l.cout, l.cin, l.ksize, l.pad, l.cin_p, l.cout_p,
                                             x_coff=xin.coff, dy_coff=dz.coff, scale=inv_scale)
-            grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, scale=inv_scale)
+            if i == len(layers) - 1:
+                grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, scale=inv_scale)
+            else:
+                grads[2 * i + 1] = db_all[offs[i]:offs[i] + l.cout]
         if i == 0 and not need_dx:
             return None, grads
         wd = packed[i][1]
@@ -118,7 +129,9 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
             slope = LEAKY_SLOPE if layers[i - 1].act == 2 else 0.0
         d = lib.conv2d(dz.t, wd, None, l.ksize, l.ksize - 1 - l.pad, act=0, x_coff=dz.coff,
                        mask=None if mask is None else mask.t, mask_coff=0 if mask is None else mask.coff,
-                       slope=slope, cin=l.cout, cout=l.cin)
+                       slope=slope, cin=l.cout, cout=l.cin,
+                       colsum=db_all[offs[i - 1]:] if (db_all is not None and i > 0) else None,
+                       colsum_scale=inv_scale)
         dz = Slice(d, 0, l.cin)
     return dz, grads
 
