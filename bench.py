@@ -110,6 +110,58 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def bench_720p(args, KPCN, make_batch):
+    """BASELINE.json configs[3]: full-frame 1280x720 KPCN denoise (n_in = 34, no PathNet), ms/frame.
+    `ms_per_frame`: padded inputs resident in HBM; `e2e_ms_per_frame`: un-padded fp32 frame buffers in
+    pinned host memory -> device, replicate pad, both branches, radiance copied back to the host."""
+    import torch
+    from wcmc_b200 import inference, lib
+    torch.manual_seed(0)
+    net = KPCN(34).cuda().eval()
+    host = {k: v.pin_memory() for k, v in make_batch(batch=1, size=0, height=720, width=1280, seed=7, paths=False,
+                                                     llpm_channel=False).items() if k.startswith("kpcn")}
+    dev = inference.pad_frame({k: v.cuda() for k, v in host.items()})
+    out_host = torch.empty((1, 3, 720, 1280), dtype=torch.float32).pin_memory()
+
+    def resident():
+        return inference.denoise_frame(net, dev, padded=True)["radiance"]
+
+    def e2e():
+        b = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+        out_host.copy_(inference.denoise_frame(net, b)["radiance"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(3):
+        resident()
+    n = max(3, min(args.steps, 10))
+    lib.profile_start()
+    ms = timed(resident, n)
+    prof = lib.profile_stop()
+    ms_plain = timed(resident, n)          # without the per-launch events
+    e2e()
+    ms_e2e = timed(e2e, n)
+    n_c, ms_c, fl_c = prof.get("conv2d", (0, 1.0, 0.0))
+    n_k, ms_k, by_k = prof.get("kernel_apply_fwd", (0, 1.0, 0.0))
+    flops = fl_c / n
+    return {"ms_per_frame": round(ms_plain, 3), "e2e_ms_per_frame": round(ms_e2e, 3),
+            "h2d_bytes_per_frame": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_frame": out_host.numel() * 4,
+            "conv_tflop_per_frame": round(flops / 1e12, 3), "conv_tflops": round(fl_c / (ms_c * 1e-3) / 1e12, 1),
+            "conv_ms": round(ms_c / n, 3), "kernel_apply_ms": round(ms_k / n, 3),
+            "kernel_apply_gbs": round(by_k / (ms_k * 1e-3) / 1e9, 1), "frames": n,
+            "workload": "configs[3]: 1280x720, n_in 34, replicate pad 18, both branches + 21x21 kernel-apply, "
+                        "whole frame in one pass (no tiling)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -117,6 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-720p", action="store_true", help="skip the 1280x720 full-frame denoise measurement")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python (no CUDA graph)")
     ap.add_argument("--perm-rng", default="device", choices=["device", "cpu"],
                     help="pairing permutations of the path-disentangling loss: torch.randperm on the GPU "
@@ -241,6 +294,7 @@ def main():
             dist.destroy_process_group()
         return
     pk, pk_src = peaks()
+    frame = bench_720p(args, KPCN, make_batch) if (world == 1 and not args.no_720p) else None
     total_ms = sum(v[1] for v in prof.values()) or 1.0
     n_c, ms_c, fl_c = prof.get("conv2d", (0, 1.0, 0.0))
     n_w, ms_w, fl_w = prof.get("conv2d_wgrad", (0, 1.0, 0.0))
@@ -273,6 +327,8 @@ def main():
                      "share_of_step_kernel_time": round(ms_c / total_ms, 4)},
         "kernels": kernels,
     }
+    if frame is not None:
+        line["denoise_720p"] = frame
     if world == 1 and not args.no_cpu_baseline:
         val, threads, dt = cpu_reference_steps(2, 1, 2)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

@@ -92,7 +92,8 @@ int wcmc_pack_weights_batch(const wcmc_pack_desc* host_descs, int n, int dtype, 
  * output pixels of y[.., c] -- a data-gradient launch thereby also produces the bias gradient of
  * the layer below it.
  * flags: 0 for production (test knobs: bits 4-5 force m tiles per region, bits 8-15 force the
- * n tile).                                                                                    */
+ * n tile; tuning knobs that give WRONG results, used by tools/conv_bench.py to find the bound:
+ * bit 16 weights loaded once, bit 17 halos loaded once, bit 18 epilogue skipped).                                                                                  */
 int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                 const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
                 void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask, int mask_cs,
@@ -158,6 +159,34 @@ int wcmc_spp_broadcast(const void* x, int x_cs, int x_coff, const void* add, int
 /* dz = dy * act'(y), y = activation output (act = WCMC_ACT_RELU / WCMC_ACT_LEAKY) */
 int wcmc_act_bwd(const void* dy, int dy_cs, int dy_coff, const void* y, int y_cs, int y_coff, void* dz,
                  int dz_cs, int dz_coff, long npix, int C, int act, float slope, int dtype, void* stream);
+
+/* ---- K10: path-disentangling loss, permutation-paired form (FeatureMSE,
+ * /root/reference/support/losses.py:33-61 intra_patch_dist / intra_batch_dist, :82-113 forward;
+ * the displacement vectors also feed GlobalRelativeSimilarityLoss, :185-211) -----------------
+ * p  : strided fp32 view (B,S,C,H,W) of the p-buffer (element strides p_sb,p_ss,p_sc,p_sh; x stride 1)
+ * ref: strided fp32 view (B,3,H,W) of the target radiance (strides r_sb,r_sc,r_sh); it is
+ *      tone-mapped inside: t = (max(ref,0)/(1+max(ref,0)))^0.454545 (losses.py:63-65)
+ * idx_patch: int64[S*H*W] permutation shared by every batch item (losses.py:35);
+ * idx_batch: int64[B*S*H*W] permutation of all rows (losses.py:50), NULL for non_local=False.
+ * Row order is (s,y,x) inside a batch item, (b,s,y,x) globally (losses.py:88-93).
+ *   e_patch[b*n+i] = 1/2|P_i-P_j|^2 - 1/2|t_i-t_j|^2, j = idx_patch[i] (same b);  e_batch likewise
+ *   loss[0] = 1/2 mean(e_patch^2), loss[1] = 1/2 mean(e_batch^2)   (fp32[2])
+ *   inv_patch int32[n], inv_batch int32[B*n] = inverse permutations (consumed by the backward)
+ *   *nonfinite |= 1 when any P or t value is not finite (losses.py:99-102); caller zero-initialises.
+ * The indices must be permutations (the reference always draws torch.randperm).              */
+size_t wcmc_fmse_perm_workspace(int B, int S, int H, int W);
+int wcmc_fmse_perm_fwd(const float* p, long p_sb, long p_ss, long p_sc, long p_sh, const float* ref,
+                       long r_sb, long r_sc, long r_sh, const int64_t* idx_patch, const int64_t* idx_batch,
+                       int B, int S, int C, int H, int W, float* e_patch, float* e_batch, int32_t* inv_patch,
+                       int32_t* inv_batch, float* loss, int* nonfinite, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* dp (B,S,C,H,W) contiguous fp32 = sum over modes of
+ *   g*coef*( w[i] (P_i - P_idx(i)) + w[inv(i)] (P_i - P_inv(i)) ),  g = *scale (device float) or 1.
+ * FeatureMSE: w = e, coef = 1/(B*n), scale = upstream gradient.  GRS: w = dL/de, coef = 1.     */
+int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_sc, long p_sh, const int64_t* idx_patch,
+                       const int64_t* idx_batch, const int32_t* inv_patch, const int32_t* inv_batch,
+                       const float* w_patch, const float* w_batch, const float* scale, float coef_patch,
+                       float coef_batch, int B, int S, int C, int H, int W, float* dp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,27 +89,16 @@ def test_state_dict_keys_match_oracle(oracle):
         assert k1 == k2 and torch.equal(v1, v2)
 
 
-def test_losses_match_reference_golden_on_cpu(golden):
-    """The drop-in losses are plain torch on the host side: pin them on CPU against vectors the
-    reference's own support/losses.py produced (tests/golden/make_golden.py)."""
-    from wcmc_b200 import dropin
+def test_losses_refuse_cpu_tensors(golden):
+    """The path-disentangling loss is a CUDA kernel pair; on a CPU tensor it raises (no fallback).
+    RelativeMSE is a one-line torch expression and is pinned here against the reference's vector."""
+    from wcmc_b200 import dropin, lib
     dropin.install()
     from support.losses import FeatureMSE, GlobalRelativeSimilarityLoss, RelativeMSE
-    for tag in ("a", "b"):
-        for nl in (True, False):
-            g = golden["fmse_%s_nl%d" % (tag, nl)]
-            p = g["p"].clone().requires_grad_(True)
-            torch.manual_seed(g["seed"])
-            loss = FeatureMSE(non_local=nl)(p, g["ref"])
-            loss.backward()
-            torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-7)
-            torch.testing.assert_close(p.grad, g["grad"], rtol=1e-4, atol=1e-8)
-        g = golden["grs_%s" % tag]
-        p = g["p"].clone().requires_grad_(True)
-        torch.manual_seed(g["seed"])
-        loss = GlobalRelativeSimilarityLoss()(p, g["ref"])
-        loss.backward()
-        torch.testing.assert_close(loss, g["loss"], rtol=1e-5, atol=1e-7)
-        torch.testing.assert_close(p.grad, g["grad"], rtol=1e-4, atol=1e-8)
+    g = golden["fmse_a_nl1"]
+    with pytest.raises(lib.WcmcError):
+        FeatureMSE(non_local=True)(g["p"], g["ref"])
+    with pytest.raises(lib.WcmcError):
+        GlobalRelativeSimilarityLoss()(g["p"], g["ref"])
     g = golden["relmse"]
     torch.testing.assert_close(RelativeMSE()(g["im"], g["ref"]), g["loss"], rtol=1e-5, atol=1e-7)

@@ -410,3 +410,34 @@ def test_graphed_step_matches_eager(backend, oracle):
                 pe = torch.cat([p.detach().flatten() for p in models_e[name].parameters()])
                 pg = torch.cat([p.detach().flatten() for p in models_g[name].parameters()])
                 assert rel(pg, pe) < 5e-3
+
+
+def test_full_frame_denoise_vs_oracle_and_tiling(backend, oracle):
+    """wcmc_b200.inference.denoise_frame (configs[3] at a small frame): equals the oracle KPCN on the
+    replicate-padded frame, and -- the property that justifies not tiling -- an interior 92x92 block
+    equals what the reference's 128x128 tile protocol computes for that tile."""
+    from wcmc_b200 import inference
+    torch.manual_seed(0)
+    ref = oracle.KPCN(34)
+    net = backend.KPCN(34)
+    net.load_state_dict(ref.state_dict())
+    net.cuda().eval()
+    ref.cuda().eval()
+    h, w = 150, 212
+    batch = to_cuda({k: v for k, v in make_batch(batch=1, size=0, height=h, width=w, seed=9, paths=False,
+                                                 llpm_channel=False).items() if k.startswith("kpcn")})
+    out = inference.denoise_frame(net, batch)
+    assert tuple(out["radiance"].shape) == (1, 3, h, w)
+    with torch.no_grad():
+        want = ref(inference.pad_frame(batch))
+    for k in ("radiance", "diffuse", "specular"):
+        assert rel(out[k], want[k]) < TOL_IMG, k
+    # tile protocol: a 128x128 crop whose 92x92 centre is at least 10 px (the 21x21 gather radius) away from
+    # the crop's valid border sees zero padding where the full frame has data, so compare the part of
+    # the centre the tile computes from in-tile data only: the inner 72x72.
+    y0, x0 = 11, 40
+    tile = {k: v[..., y0:y0 + 128, x0:x0 + 128].contiguous() for k, v in batch.items()}
+    with torch.no_grad():
+        t = net(tile)["radiance"]                        # (1,3,92,92) = frame rows y0+18 .. y0+110
+    full = out["radiance"][..., y0 + 18:y0 + 110, x0 + 18:x0 + 110]
+    assert rel(t[..., 10:-10, 10:-10], full[..., 10:-10, 10:-10]) < TOL_IMG

@@ -1,36 +1,20 @@
 """B200 drop-in for the hot-path losses of /root/reference/support/losses.py.
 
 FeatureMSE (path disentangling loss, losses.py:9-113), GlobalRelativeSimilarityLoss (:116-211) and
-RelativeMSE (:245-264).  RNG contract kept from the reference: the pairing permutations come from
+RelativeMSE (:245-264).  The displacement / loss arithmetic runs in two CUDA launches
+(wcmc_fmse_perm_fwd / _bwd, wcmc_b200/csrc/fmse.cu) on the cropped p-buffer view as it is -- no
+permute / reshape copies.  RNG contract kept from the reference: the pairing permutations come from
 the CPU default generator, `randperm(S*H*W)` then `randperm(B*S*H*W)` per call (losses.py:35, :50),
-so a seeded run pairs exactly the same samples as the reference.
+so a seeded run pairs exactly the same samples as the reference.  CUDA tensors only.
 """
 import math
 import os
 
 import torch
 
+from wcmc_b200 import lib
+
 __all__ = ["GlobalRelativeSimilarityLoss", "FeatureMSE", "RelativeMSE"]
-
-
-def _tonemap_gamma(img):
-    img = torch.clamp(img, min=0)
-    return (img / (1 + img)) ** 0.454545
-
-
-def _rows(p_buffer, t):
-    """(B,S,C,H,W), tone-mapped ref (B,3,H,W) -> rows (B, S*H*W, C) and (B, S*H*W, 3), (s,h,w) order."""
-    b, s, c, h, w = p_buffer.shape
-    r = t.permute(0, 2, 3, 1).unsqueeze(1).expand(b, s, h, w, 3).reshape(b, s * h * w, 3)
-    p = p_buffer.permute(0, 1, 3, 4, 2).reshape(b, s * h * w, c)
-    return p, r
-
-
-def _displacement(p, r, idx, dim):
-    idx = idx.to(p.device, non_blocking=True)
-    d_p = 0.5 * (p - p.index_select(dim, idx)).pow(2).sum(-1)
-    d_r = 0.5 * (r - r.index_select(dim, idx)).pow(2).sum(-1)
-    return d_p - d_r
 
 
 def _randperm(n, device, rng):
@@ -39,7 +23,7 @@ def _randperm(n, device, rng):
     from a different stream; used by the throughput benchmark."""
     if rng == "device":
         return torch.randperm(n, device=device)
-    return torch.randperm(n)
+    return torch.randperm(n).to(device, non_blocking=True)
 
 
 def _default_rng():
@@ -52,8 +36,8 @@ DEFER_FINITE_CHECK = False
 FINITE_FLAGS = []
 
 
-def _check_finite(*tensors):
-    ok = torch.stack([torch.isfinite(t).all() for t in tensors]).all()
+def _check_flag(nonfinite):
+    ok = nonfinite[0] == 0
     if DEFER_FINITE_CHECK:
         FINITE_FLAGS.append(ok)
         return
@@ -61,10 +45,76 @@ def _check_finite(*tensors):
         raise RuntimeError("Infinite loss at train time.")
 
 
+def _views(p_buffer, ref):
+    """The kernels read strided (cropped) fp32 views directly; anything else is normalised here."""
+    if not p_buffer.is_cuda:
+        raise lib.WcmcError("the path-disentangling loss runs on the B200 only (got a %s tensor); there is no CPU "
+                            "fallback" % p_buffer.device)
+    if p_buffer.dtype != torch.float32:
+        p_buffer = p_buffer.float()
+    if p_buffer.stride(4) != 1:
+        p_buffer = p_buffer.contiguous()
+    ref = ref.to(p_buffer.device, torch.float32)
+    if ref.stride(3) != 1:
+        ref = ref.contiguous()
+    return p_buffer, ref
+
+
+def _perms(p, rng, non_local, idx_patch, idx_batch):
+    b, s, c, h, w = p.shape
+    if idx_patch is None:
+        idx_patch = _randperm(s * h * w, p.device, rng)
+    if non_local and idx_batch is None:
+        idx_batch = _randperm(b * s * h * w, p.device, rng)
+    fix = lambda i: None if i is None else i.to(p.device, torch.int64).contiguous()  # noqa: E731
+    return fix(idx_patch), fix(idx_batch) if non_local else None
+
+
+class _FmseFn(torch.autograd.Function):
+    """loss = 1/2 mean e_patch^2 + 1/2 mean e_batch^2 (local only: the patch term twice), one fused
+    forward launch (wcmc_fmse_perm_fwd) and one gather-only backward launch (wcmc_fmse_perm_bwd)."""
+
+    @staticmethod
+    def forward(ctx, p, ref, idx_patch, idx_batch):
+        r = lib.fmse_perm_fwd(p, ref, idx_patch, idx_batch)
+        _check_flag(r["nonfinite"])
+        ctx.save_for_backward(p, idx_patch, idx_batch, r["inv_patch"], r["inv_batch"], r["e_patch"], r["e_batch"])
+        loss = r["loss"]
+        return loss[0] + (loss[1] if idx_batch is not None else loss[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        p, idx_patch, idx_batch, inv_patch, inv_batch, e_patch, e_batch = ctx.saved_tensors
+        rows = e_patch.numel()
+        coef_p = (1.0 if idx_batch is not None else 2.0) / rows
+        dp = lib.fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, e_patch, e_batch,
+                               g.reshape(1).float().contiguous(), coef_p, 1.0 / rows)
+        return dp, None, None, None
+
+
+class _PairDisplacementFn(torch.autograd.Function):
+    """-> (e_patch, e_batch) displacement vectors with a gradient to p (used by GRS)."""
+
+    @staticmethod
+    def forward(ctx, p, ref, idx_patch, idx_batch):
+        r = lib.fmse_perm_fwd(p, ref, idx_patch, idx_batch)
+        _check_flag(r["nonfinite"])
+        ctx.save_for_backward(p, idx_patch, idx_batch, r["inv_patch"], r["inv_batch"])
+        return r["e_patch"], r["e_batch"]
+
+    @staticmethod
+    def backward(ctx, g_p, g_b):
+        p, idx_patch, idx_batch, inv_patch, inv_batch = ctx.saved_tensors
+        dp = lib.fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, g_p.contiguous(), g_b.contiguous(),
+                               None, 1.0, 1.0)
+        return dp, None, None, None
+
+
 class FeatureMSE(torch.nn.Module):
     """Path disentangling loss: for random sample pairs (i, pi(i)) penalise
     (1/2|p_i - p_j|^2 - 1/2|t_i - t_j|^2)^2, once with pairs inside each patch and (non_local)
-    once with pairs across the whole batch."""
+    once with pairs across the whole batch.  `idx_patch` / `idx_batch` (optional, extension) pin the
+    pairing permutations; by default they are drawn exactly as the reference draws them."""
 
     def __init__(self, color="rgb", non_local=True, rng=None):
         super().__init__()
@@ -77,19 +127,9 @@ class FeatureMSE(torch.nn.Module):
         print("FeatureMSE locality: %s" % ("Non-local" if non_local else "Local"))
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
-        b, s, c, h, w = p_buffer.shape
-        t = _tonemap_gamma(ref)
-        _check_finite(p_buffer, t)
-        p, r = _rows(p_buffer, t)
-        if idx_patch is None:
-            idx_patch = _randperm(s * h * w, p.device, self.rng)
-        loss_p = 0.5 * _displacement(p, r, idx_patch, 1).pow(2).mean()
-        if not self.non_local:
-            return loss_p + loss_p
-        if idx_batch is None:
-            idx_batch = _randperm(b * s * h * w, p.device, self.rng)
-        loss_b = 0.5 * _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0).pow(2).mean()
-        return loss_p + loss_b
+        p, r = _views(p_buffer, ref)
+        idx_patch, idx_batch = _perms(p, self.rng, self.non_local, idx_patch, idx_batch)
+        return _FmseFn.apply(p, r, idx_patch, idx_batch)
 
 
 class GlobalRelativeSimilarityLoss(torch.nn.Module):
@@ -102,15 +142,10 @@ class GlobalRelativeSimilarityLoss(torch.nn.Module):
         self.rng = rng or _default_rng()
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
-        _check_finite(p_buffer, ref)
-        b, s, c, h, w = p_buffer.shape
-        p, r = _rows(p_buffer, _tonemap_gamma(ref))
-        if idx_patch is None:
-            idx_patch = _randperm(s * h * w, p.device, self.rng)
-        if idx_batch is None:
-            idx_batch = _randperm(b * s * h * w, p.device, self.rng)
-        d_p = _displacement(p, r, idx_patch, 1).reshape(-1)
-        d_b = _displacement(p.reshape(-1, c), r.reshape(-1, 3), idx_batch, 0)
+        p, r = _views(p_buffer, ref)
+        b, s, c, h, w = p.shape
+        idx_patch, idx_batch = _perms(p, self.rng, True, idx_patch, idx_batch)
+        d_p, d_b = _PairDisplacementFn.apply(p, r, idx_patch, idx_batch)
         zero = torch.zeros(1, dtype=p.dtype, device=p.device)
         ex = self.alpha * torch.cat([d_p, d_b, -d_p, -d_b, zero], 0)
         return (torch.logsumexp(ex, 0) - math.log(1 + 4 * b * s * h * w)) / math.sqrt(self.alpha)

@@ -17,6 +17,7 @@ _lock = threading.Lock()
 _inited_devices = set()
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+c_long = ctypes.c_long
 
 class PackDesc(ctypes.Structure):
     """wcmc_pack_desc of include/wcmc.h"""
@@ -48,6 +49,11 @@ SIGNATURES = {
     "wcmc_upsample2_bwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 5 + [c_void_p]),
     "wcmc_spp_reduce": (c_int, [c_void_p, c_int, c_int] * 2 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "wcmc_spp_broadcast": (c_int, [c_void_p, c_int, c_int] * 3 + [c_int] * 4 + [c_float, c_int, c_void_p]),
+    "wcmc_fmse_perm_workspace": (c_size_t, [c_int] * 4),
+    "wcmc_fmse_perm_fwd": (c_int, [c_void_p] + [c_long] * 4 + [c_void_p] + [c_long] * 3 + [c_void_p, c_void_p]
+                           + [c_int] * 5 + [c_void_p] * 7 + [c_size_t, c_void_p]),
+    "wcmc_fmse_perm_bwd": (c_int, [c_void_p] + [c_long] * 4 + [c_void_p] * 7 + [c_float, c_float] + [c_int] * 5
+                           + [c_void_p, c_void_p]),
     "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_int, c_void_p]),
 }
 
@@ -59,7 +65,7 @@ class WcmcError(RuntimeError):
 # ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
-_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2}
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2}
 
 
 def profile_start():
@@ -439,3 +445,55 @@ def act_bwd(dy, y, c, act, slope=0.01, dy_coff=0, y_coff=0, out=None, out_coff=0
          y.shape[3], y_coff, _h16(out).data_ptr(), out.shape[3], out_coff, npix, c, act, float(slope), _dt(dy),
          _stream())
     return out
+
+
+# ---- K10: path-disentangling loss (permutation-paired) ------------------------------------------
+def _pview(p):
+    """(B,S,C,H,W) fp32 view with unit x stride -> (ptr, sb, ss, sc, sh)."""
+    assert p.dtype == torch.float32 and p.dim() == 5 and p.stride(4) == 1, "p-buffer view must be fp32 with unit W stride"
+    return (p.data_ptr(),) + tuple(p.stride()[:4])
+
+
+def fmse_perm_fwd(p, ref, idx_patch, idx_batch=None):
+    """p (B,S,C,H,W) / ref (B,3,H,W): fp32 (possibly cropped, strided) views; idx_*: int64 device
+    permutations.  -> dict(loss (2,), e_patch, e_batch, inv_patch, inv_batch, nonfinite (int32 flag))."""
+    lib = init(p.device)
+    b, s, c, h, w = p.shape
+    assert ref.dtype == torch.float32 and tuple(ref.shape) == (b, 3, h, w) and ref.stride(3) == 1
+    n = s * h * w
+    dev = p.device
+    assert idx_patch.dtype == torch.int64 and idx_patch.numel() == n and idx_patch.is_contiguous()
+    assert idx_patch.device == dev
+    if idx_batch is not None:
+        assert idx_batch.dtype == torch.int64 and idx_batch.numel() == b * n and idx_batch.is_contiguous()
+        assert idx_batch.device == dev
+    r = dict(loss=torch.empty(2, dtype=torch.float32, device=dev),
+             e_patch=torch.empty(b * n, dtype=torch.float32, device=dev),
+             e_batch=torch.empty(b * n, dtype=torch.float32, device=dev) if idx_batch is not None else None,
+             inv_patch=torch.empty(n, dtype=torch.int32, device=dev),
+             inv_batch=torch.empty(b * n, dtype=torch.int32, device=dev) if idx_batch is not None else None,
+             nonfinite=torch.zeros(1, dtype=torch.int32, device=dev))
+    need = lib.wcmc_fmse_perm_workspace(b, s, h, w)
+    ws = _workspace(need, dev)
+    modes = 2 if idx_batch is not None else 1
+    work = b * n * ((c + 3) * 4.0 * (1 + modes) + modes * 16.0)   # row + partner rows, idx + e + inv per mode
+    _run(lib.wcmc_fmse_perm_fwd, "fmse_perm_fwd", work, *_pview(p), ref.data_ptr(), ref.stride(0), ref.stride(1),
+         ref.stride(2), idx_patch.data_ptr(), _p(idx_batch), b, s, c, h, w, r["e_patch"].data_ptr(),
+         _p(r["e_batch"]), r["inv_patch"].data_ptr(), _p(r["inv_batch"]), r["loss"].data_ptr(),
+         r["nonfinite"].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    return r
+
+
+def fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch):
+    """-> dp (B,S,C,H,W) contiguous fp32 (see include/wcmc.h)."""
+    lib = init(p.device)
+    b, s, c, h, w = p.shape
+    dp = torch.empty((b, s, c, h, w), dtype=torch.float32, device=p.device)
+    for t in (w_patch, w_batch):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == b * s * h * w)
+    modes = 2 if idx_batch is not None else 1
+    work = b * s * h * w * (c * 4.0 * (2 + 2 * modes) + modes * 20.0)
+    _run(lib.wcmc_fmse_perm_bwd, "fmse_perm_bwd", work, *_pview(p), idx_patch.data_ptr(), _p(idx_batch),
+         inv_patch.data_ptr(), _p(inv_batch), w_patch.data_ptr(), _p(w_batch), _p(scale), float(coef_patch),
+         float(coef_batch), b, s, c, h, w, dp.data_ptr(), _stream())
+    return dp
