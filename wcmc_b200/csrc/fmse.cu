@@ -49,8 +49,11 @@ fmse_perm_fwd_kernel(PView pv, RView rv, const int64_t* __restrict__ idx_patch,
         const int s = i / hw, r = i - s * hw, y = r / W, x = r - y * W;
         const float* pi = pv.p + b * pv.sb + s * pv.ss + y * pv.sh + x;
         const float* ri = rv.p + b * rv.sb + y * rv.sh + x;
-        const float t0 = tonemap(ri[0]), t1 = tonemap(ri[rv.sc]), t2 = tonemap(ri[2 * rv.sc]);
-        bool bad = !(isfinite(t0) && isfinite(t1) && isfinite(t2));
+        const float r0 = ri[0], r1 = ri[rv.sc], r2 = ri[2 * rv.sc];
+        const float t0 = tonemap(r0), t1 = tonemap(r1), t2 = tonemap(r2);
+        // torch.clamp propagates NaN and inf/(1+inf) is NaN, fmaxf does not: test the raw values
+        // (-inf clamps to 0 and is fine, as in the reference)
+        bool bad = isnan(r0) || isnan(r1) || isnan(r2) || r0 == INFINITY || r1 == INFINITY || r2 == INFINITY;
         // partner inside the patch (same b)
         const int j = static_cast<int>(idx_patch[i]);
         const int js = j / hw, jr = j - js * hw, jy = jr / W, jx = jr - jy * W;

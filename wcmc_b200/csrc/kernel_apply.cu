@@ -10,12 +10,15 @@
 // (32+k-1) halo of the radiance buffer is staged once per CTA in shared memory with a row pitch
 // == k (mod 32), which makes tap k hit bank (k mod 32): conflict free for consecutive taps.
 // The logits are read exactly once (softmax is fused; probabilities never reach HBM); the
-// backward recomputes them from the saved (max, 1/sum) pair.
+// backward recomputes them from the saved (max, 1/sum) pair.  Each warp keeps the NEXT pixel's
+// 14 coalesced 128-byte logit loads in flight while it reduces the current one (two register
+// sets), and 3 CTAs are resident per SM: ~24 warps x 3.5 KB of loads in flight per SM, which is what
+// Little's law asks for at HBM3e latency.  Logits use streaming loads (read once, never reused).
 #include "common.cuh"
 
 namespace wcmc {
 
-constexpr int kKaTileW = 32;
+constexpr int kKaTileW = 16;     // 16 x 8 pixel tiles: 576 CTAs at 8 x 92 x 92 (~4 resident per SM)
 constexpr int kKaTileH = 8;
 constexpr int kKaThreads = 256;  // 8 warps; warp w owns tile row w
 constexpr int kKaMaxSlots = 14;  // ceil(441 / 32)
@@ -45,7 +48,7 @@ __device__ __forceinline__ void ka_load_halo(float* sm, const float* __restrict_
 }
 
 template <int C>
-__global__ void __launch_bounds__(kKaThreads)
+__global__ void __launch_bounds__(kKaThreads, 3)
 kernel_apply_fwd_kernel(const float* __restrict__ logits, int l_cs, const float* __restrict__ data,
                         float* __restrict__ out, float* __restrict__ stats, int N, int H, int W, int ks) {
     extern __shared__ float sm[];
@@ -68,14 +71,16 @@ kernel_apply_fwd_kernel(const float* __restrict__ logits, int l_cs, const float*
     }
     const float kLog2e = 1.4426950408889634f;
     const int xe = min(kKaTileW, W - x0);
-    for (int tx = 0; tx < xe; ++tx) {
-        const float* lp = logits + ((static_cast<size_t>(n) * H + y) * W + (x0 + tx)) * l_cs;
-        float z[kKaMaxSlots];
+    const float* row = logits + ((static_cast<size_t>(n) * H + y) * W + x0) * l_cs;
+    auto load = [&](float (&z)[kKaMaxSlots], int tx) {
+        const float* lp = row + static_cast<size_t>(tx) * l_cs;
 #pragma unroll
         for (int j = 0; j < kKaMaxSlots; ++j) {
             int k = lane + 32 * j;
-            z[j] = (k < taps) ? __ldg(lp + k) : -INFINITY;
+            z[j] = (k < taps) ? __ldcs(lp + k) : -INFINITY;
         }
+    };
+    auto compute = [&](const float (&z)[kKaMaxSlots], int tx) {
         float mx = z[0];
 #pragma unroll
         for (int j = 1; j < kKaMaxSlots; ++j) mx = fmaxf(mx, z[j]);
@@ -105,11 +110,19 @@ kernel_apply_fwd_kernel(const float* __restrict__ logits, int l_cs, const float*
             float2* sp = reinterpret_cast<float2*>(stats) + (static_cast<size_t>(n) * H + y) * W + x0 + tx;
             *sp = make_float2(mx, inv);
         }
+    };
+    float za[kKaMaxSlots], zb[kKaMaxSlots];
+    load(za, 0);
+    for (int tx = 0; tx < xe; tx += 2) {
+        if (tx + 1 < xe) load(zb, tx + 1);
+        compute(za, tx);
+        if (tx + 2 < xe) load(za, tx + 2);
+        if (tx + 1 < xe) compute(zb, tx + 1);
     }
 }
 
 template <int C, int DT>
-__global__ void __launch_bounds__(kKaThreads)
+__global__ void __launch_bounds__(kKaThreads, 2)
 kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float* __restrict__ data,
                         const float* __restrict__ out, const float* __restrict__ stats,
                         const float* __restrict__ gout, void* __restrict__ dlogits, int dl_cs, int N, int H,
@@ -141,23 +154,25 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
     const float kLog2e = 1.4426950408889634f;
     const int xe = min(kKaTileW, W - x0);
     const int nslots = (dl_cs + 31) / 32;
-    for (int tx = 0; tx < xe; ++tx) {
-        const size_t pix = (static_cast<size_t>(n) * H + y) * W + (x0 + tx);
-        const float* lp = logits + pix * l_cs;
-        float z[kKaMaxSlots];
+    const size_t pix0 = (static_cast<size_t>(n) * H + y) * W + x0;
+    // per pixel: logits z, (max, 1/sum), upstream gradient g and its dot product with the output
+    auto load = [&](float (&z)[kKaMaxSlots], float2& st, float (&g)[C], float& go, int tx) {
+        const float* lp = logits + (pix0 + tx) * l_cs;
 #pragma unroll
         for (int j = 0; j < kKaMaxSlots; ++j) {
             int k = lane + 32 * j;
-            z[j] = (k < taps) ? __ldg(lp + k) : -INFINITY;
+            z[j] = (k < taps) ? __ldcs(lp + k) : -INFINITY;
         }
-        const float2 st = __ldg(reinterpret_cast<const float2*>(stats) + pix);
-        float g[C], go = 0.f;
+        st = __ldg(reinterpret_cast<const float2*>(stats) + pix0 + tx);
+        go = 0.f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             size_t o = ((static_cast<size_t>(n) * C + c) * H + y) * W + x0 + tx;
             g[c] = __ldg(gout + o);
             go = fmaf(g[c], __ldg(out + o), go);
         }
+    };
+    auto compute = [&](const float (&z)[kKaMaxSlots], const float2 st, const float (&g)[C], const float go, int tx) {
         const float mxs = st.x * kLog2e;
 #pragma unroll
         for (int j = 0; j < kKaMaxSlots; ++j) {
@@ -182,11 +197,20 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
         {
             const int nvec = stage_elems / 4;  // uint4 per pixel row
             uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(dlogits) +
-                                                  pix * static_cast<size_t>(dl_cs) * (H16 ? 2 : 4));
+                                                  (pix0 + tx) * static_cast<size_t>(dl_cs) * (H16 ? 2 : 4));
             const uint4* src = reinterpret_cast<const uint4*>(stage);
-            for (int i = lane; i < nvec; i += 32) dst[i] = src[i];
+            for (int i = lane; i < nvec; i += 32) __stcs(dst + i, src[i]);
         }
         __syncwarp();
+    };
+    float za[kKaMaxSlots], zb[kKaMaxSlots], ga[C], gb[C], goa, gob;
+    float2 sta, stb;
+    load(za, sta, ga, goa, 0);
+    for (int tx = 0; tx < xe; tx += 2) {
+        if (tx + 1 < xe) load(zb, stb, gb, gob, tx + 1);
+        compute(za, sta, ga, goa, tx);
+        if (tx + 2 < xe) load(za, sta, ga, goa, tx + 2);
+        if (tx + 1 < xe) compute(zb, stb, gb, gob, tx + 1);
     }
 }
 
