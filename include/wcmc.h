@@ -47,6 +47,8 @@ const char* wcmc_last_error(void);
 const char* wcmc_version(void);
 /* Checks that `device` is a compute-capability-10.x GPU and prepares per-process state. */
 int wcmc_init(int device);
+/* Tuning knobs for the micro-benchmarks under tools/ ("ka_tile_w" = 16 | 32: kernel-apply tile width). */
+int wcmc_tuning_set(const char* name, int value);
 
 /* ---- layout conversion (boundary between torch NCHW fp32 tensors and the NHWC bf16 pipeline) --
  * dst[n,h,w,dst_coff+c] = half(src[n,c,h,w]) for c < C; channels C..c_fill-1 are written as 0.
@@ -187,6 +189,30 @@ int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_sc, long p_s
                        const int64_t* idx_batch, const int32_t* inv_patch, const int32_t* inv_batch,
                        const float* w_patch, const float* w_batch, const float* scale, float coef_patch,
                        float coef_batch, int B, int S, int C, int H, int W, float* dp, void* stream);
+
+/* ---- K6/K7: the per-sample 1x1 MLPs of the path-embedding network, one kernel each
+ * (PathNet.embedding / PathNet.final, /root/reference/support/networks.py:18-19, :23-24, :29-42) ----
+ * K6: paths (B,S,Cin,HW) fp32 (the dataset's layout) -> act1(W1 x + b1) -> act2(W2 . + b2) ->
+ *     act3(W3 . + b3), all 64 wide.  w*: 16-bit packed [64][cin_p] / [64][64] (wcmc_pack_weights,
+ *     fwd form); b*: fp32[64].  Outputs, all 16-bit NHWC over B*S*HW pixels (optional ones may be NULL):
+ *       emb  (.., emb_cs) channels [emb_coff, emb_coff+64)   layer-3 output
+ *       mean (B*HW, mean_cs) channels [mean_coff, +64)       mean of emb over the S samples (networks.py:36)
+ *       x16, h1, h2 (.., 64)                                 input (zero padded to 64 channels) / hidden
+ *                                                            activations for the backward pass
+ *     Requires H*W % 4 == 0 (TMA row stride).  16-bit outputs leave by TMA store.                 */
+int wcmc_pathnet_embed_fwd(const float* paths, int B, int S, int Cin, int HW, const void* w1, const float* b1,
+                           const void* w2, const float* b2, const void* w3, const float* b3, int cin_p,
+                           int dtype, int act1, int act2, int act3, float slope, void* x16, void* h1, void* h2,
+                           void* emb, int emb_cs, int emb_coff, void* mean, int mean_cs, int mean_coff,
+                           void* stream);
+/* K7: out (B,S,outc,HW) fp32 = act2(W2 act1(W1 [emb_s | prop] + b1) + b2): emb (B*S*HW px, 64 ch) per
+ *     sample, prop (B*HW px, 64 ch) per pixel (the reference repeats it S times and concatenates,
+ *     networks.py:39-40).  w1: [128][128], w2: [outc_p][128] packed 16-bit; outc_p <= 32.
+ *     h (optional): (B*S*HW, 128) 16-bit hidden activation for the backward pass.               */
+int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff, const void* prop, int prop_cs,
+                           int prop_coff, const void* w1, const float* b1, const void* w2, const float* b2,
+                           int outc, int outc_p, int dtype, int act1, int act2, float slope, void* h,
+                           float* out, int B, int S, int HW, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,11 @@ int wcmc_num_sms() { return g_sms > 0 ? g_sms : 148; }
 
 int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                           const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+    return wcmc_encode_tmap(map, WCMC_BF16, base, rank, dims, strides_bytes, box, swizzle128);
+}
+
+int wcmc_encode_tmap(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
     WCMC_REQUIRE(g_encode != nullptr, WCMC_ECUDA, "wcmc_init() has not been called");
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5];
@@ -58,7 +63,8 @@ int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
         estr[i] = 1;
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+    CUresult r = g_encode(map, dtype == WCMC_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                          static_cast<cuuint32_t>(rank),
                           const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -73,4 +79,12 @@ int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
         return WCMC_ECUDA;
     }
     return WCMC_OK;
+}
+
+// Tuning hooks for the micro-benchmarks under tools/ (never used by the product path).
+int wcmc_ka_set_tile(int w);   // kernel_apply.cu
+extern "C" int wcmc_tuning_set(const char* name, int value) {
+    if (name != nullptr && strcmp(name, "ka_tile_w") == 0 && wcmc_ka_set_tile(value) == 0) return WCMC_OK;
+    wcmc_set_error("wcmc_tuning_set: unknown knob or bad value (%s = %d)", name ? name : "(null)", value);
+    return WCMC_ESHAPE;
 }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "wcmc_last_error": (ctypes.c_char_p, []),
     "wcmc_version": (ctypes.c_char_p, []),
     "wcmc_init": (c_int, [c_int]),
+    "wcmc_tuning_set": (c_int, [ctypes.c_char_p, c_int]),
     "wcmc_nchw_f32_to_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
     "wcmc_nhwc_to_nchw_f32": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]),
     "wcmc_pack_weights": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
@@ -54,6 +55,11 @@ SIGNATURES = {
                            + [c_int] * 5 + [c_void_p] * 7 + [c_size_t, c_void_p]),
     "wcmc_fmse_perm_bwd": (c_int, [c_void_p] + [c_long] * 4 + [c_void_p] * 7 + [c_float, c_float] + [c_int] * 5
                            + [c_void_p, c_void_p]),
+    "wcmc_pathnet_embed_fwd": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p] * 6 + [c_int] * 5 + [c_float]
+                               + [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                  c_void_p]),
+    "wcmc_pathnet_final_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_void_p] * 4 + [c_int] * 5 + [c_float]
+                               + [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_int, c_void_p]),
 }
 
@@ -497,3 +503,45 @@ def fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batc
          inv_patch.data_ptr(), _p(inv_batch), w_patch.data_ptr(), _p(w_batch), _p(scale), float(coef_patch),
          float(coef_batch), b, s, c, h, w, dp.data_ptr(), _stream())
     return dp
+
+
+# ---- K6/K7: fused PathNet MLPs ----------------------------------------------------------------------
+def pathnet_embed_fwd(paths, packed, acts, slope, emb, emb_coff, mean, x16=None, h1=None, h2=None):
+    """paths (B,S,Cin,H,W) fp32; packed = [(w_fwd, _, bias_p)] x 3 from pack_weights_batch; acts = 3
+    activation codes.  Writes emb[..., emb_coff:emb_coff+64] (B*S,H,W,cs), mean (B,H,W,64) and, when
+    given, the 16-bit input copy x16 (B*S,H,W,cin_p) and the hidden activations h1, h2 (B*S,H,W,64)."""
+    lib = init(paths.device)
+    b, s, cin, h, w = paths.shape
+    assert paths.dtype == torch.float32 and paths.is_contiguous()
+    (w1, _, b1), (w2, _, b2), (w3, _, b3) = packed
+    cin_p = w1.shape[2]
+    assert tuple(w1.shape) == (64, 1, cin_p) and tuple(w2.shape) == (64, 1, 64) and tuple(w3.shape) == (64, 1, 64)
+    for t in (emb, mean, x16, h1, h2):
+        assert t is None or (t.dtype == w1.dtype and t.is_contiguous())
+    for t in (x16, h1, h2):
+        assert t is None or t.shape[-1] == 64
+    hw = h * w
+    work = b * s * hw * (cin * 4.0 + 64 * 2.0 * (1 + (h1 is not None) + (h2 is not None)) +
+                         (0 if x16 is None else x16.shape[-1] * 2.0)) + b * hw * 128.0
+    _run(lib.wcmc_pathnet_embed_fwd, "pathnet_embed_fwd", work, paths.data_ptr(), b, s, cin, hw, w1.data_ptr(),
+         b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), w3.data_ptr(), b3.data_ptr(), cin_p, _dt(w1), acts[0], acts[1],
+         acts[2], float(slope), _p(x16), _p(h1), _p(h2), emb.data_ptr(),
+         emb.shape[-1], emb_coff, _p(mean), 0 if mean is None else mean.shape[-1], 0, _stream())
+
+
+def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc, b, s, hfin=None):
+    """emb (B*S,H,W,cs) / prop (B,H,W,cs') 16-bit NHWC -> out (B,S,outc,H,W) fp32 [+ hfin (B*S,H,W,128)]."""
+    lib = init(emb.device)
+    bs, h, w, ecs = _h16(emb).shape
+    assert bs == b * s and tuple(_h16(prop).shape[:3]) == (b, h, w) and prop.dtype == emb.dtype
+    (w1, _, b1), (w2, _, b2) = packed
+    outc_p = w2.shape[0]
+    assert tuple(w1.shape) == (128, 1, 128) and tuple(w2.shape) == (outc_p, 1, 128) and w1.dtype == emb.dtype
+    assert hfin is None or (hfin.dtype == emb.dtype and hfin.is_contiguous() and hfin.shape[-1] == 128)
+    out = torch.empty((b, s, outc, h, w), dtype=torch.float32, device=emb.device)
+    hw = h * w
+    work = bs * hw * (128.0 + outc * 4.0 + (0.0 if hfin is None else 256.0)) + b * hw * 128.0
+    _run(lib.wcmc_pathnet_final_fwd, "pathnet_final_fwd", work, emb.data_ptr(), ecs, emb_coff, prop.data_ptr(),
+         prop.shape[-1], prop_coff, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), outc, outc_p,
+         _dt(emb), acts[0], acts[1], float(slope), _p(hfin), out.data_ptr(), b, s, hw, _stream())
+    return out

@@ -345,6 +345,17 @@ class PathNetSpec:
     final: List[LayerSpec]
 
 
+def fused_mlp_ok(spec):
+    """The fused K6 / K7 kernels cover the shapes PathNet is built with (intermc = 64, networks.py:11-24)."""
+    e, f = spec.embedding, spec.final
+    return (len(e) == 3 and all(l.ksize == 1 and l.pad == 0 and l.cout == 64 for l in e) and e[0].cin <= 64
+            and e[1].cin == 64 and e[2].cin == 64 and len(f) == 2 and all(l.ksize == 1 and l.pad == 0 for l in f)
+            and f[0].cin == 128 and f[0].cout == 128 and f[1].cin == 128 and f[1].cout <= 32)
+
+
+FUSED_MLP = os.environ.get("WCMC_FUSED_MLP", "1") != "0"
+
+
 class PathNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, paths, spec, *params):
@@ -355,17 +366,41 @@ class PathNetFn(torch.autograd.Function):
         p_fin = pack_chain(spec.final, params[ne + nu:], need)
         c_emb = spec.embedding[-1].cout
         c_prop = spec.final[0].cin - c_emb
-        x = _to_nhwc(paths.reshape(b * s, nf, h, w), spec.embedding[0].cin_p)
-        both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=ACT_DTYPE, device=paths.device)
-        acts_emb = chain_forward(x, spec.embedding, p_emb, out=Slice(both, 0, c_emb))
-        reduced = lib.spp_reduce(both, b, s, c_emb, 1.0 / s)
-        prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
-        assert prop.c == c_prop
-        lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
-        acts_fin = chain_forward(Slice(both, 0, c_emb + c_prop), spec.final, p_fin, last_fp32=True)
         outc = spec.final[-1].cout
-        y = acts_fin[-1].t  # (B*S,H,W,outc_p) fp32
-        out = y[..., :outc].permute(0, 3, 1, 2).reshape(b, s, outc, h, w).contiguous()
+        dev = paths.device
+        if FUSED_MLP and fused_mlp_ok(spec):
+            # K6: fp32 NCHW paths -> 3-layer MLP -> emb (+ spp mean) in one kernel; K7: [emb | prop] -> out
+            px = paths.contiguous().float()
+            both = torch.empty((b * s, h, w, c_emb + c_prop if need else c_emb), dtype=ACT_DTYPE, device=dev)
+            reduced = torch.empty((b, h, w, c_emb), dtype=ACT_DTYPE, device=dev)
+            x16 = h1 = h2 = hfin = None
+            if need:
+                x16 = torch.empty((b * s, h, w, 64), dtype=ACT_DTYPE, device=dev)   # zero padded to 64 channels
+                h1 = torch.empty((b * s, h, w, c_emb), dtype=ACT_DTYPE, device=dev)
+                h2 = torch.empty((b * s, h, w, c_emb), dtype=ACT_DTYPE, device=dev)
+                hfin = torch.empty((b * s, h, w, spec.final[0].cout), dtype=ACT_DTYPE, device=dev)
+            lib.pathnet_embed_fwd(px, p_emb, [l.act for l in spec.embedding], LEAKY_SLOPE, both, 0, reduced,
+                                  x16=x16, h1=h1, h2=h2)
+            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
+            assert prop.c == c_prop
+            out = lib.pathnet_final_fwd(both, 0, prop.t, prop.coff, p_fin, [l.act for l in spec.final], LEAKY_SLOPE,
+                                        outc, b, s, hfin=hfin)
+            if need:
+                # the backward pass (generic wgrad / dgrad kernels) reads [emb | prop] as one 128-channel tensor
+                lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
+                acts_emb = [Slice(x16, 0, nf), Slice(h1, 0, c_emb), Slice(h2, 0, c_emb), Slice(both, 0, c_emb)]
+                acts_fin = [Slice(both, 0, c_emb + c_prop), Slice(hfin, 0, spec.final[0].cout), None]
+        else:
+            x = _to_nhwc(paths.reshape(b * s, nf, h, w), spec.embedding[0].cin_p)
+            both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=ACT_DTYPE, device=dev)
+            acts_emb = chain_forward(x, spec.embedding, p_emb, out=Slice(both, 0, c_emb))
+            reduced = lib.spp_reduce(both, b, s, c_emb, 1.0 / s)
+            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
+            assert prop.c == c_prop
+            lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
+            acts_fin = chain_forward(Slice(both, 0, c_emb + c_prop), spec.final, p_fin, last_fp32=True)
+            y = acts_fin[-1].t  # (B*S,H,W,outc_p) fp32
+            out = y[..., :outc].permute(0, 3, 1, 2).reshape(b, s, outc, h, w).contiguous()
         ctx.spec, ctx.dims = spec, (b, s, h, w, c_emb, c_prop, outc)
         if need:
             ctx.saved = (acts_emb, p_emb, uctx, acts_fin, p_fin)
