@@ -82,6 +82,9 @@ def cpu_reference_steps(sample_batch, warmup, steps):
     all host cores.  Returns (patches/s, threads, seconds per step)."""
     import torch
     from wcmc_b200.synth import make_batch
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm is meant to use every host core it can
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, ncpu))
     o, models, optims = build_oracle_models()
     batch = make_batch(batch=sample_batch, spp=SPP, size=SIZE, seed=1234)
     for _ in range(warmup):

@@ -114,6 +114,23 @@ int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs,
                       const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize, int pad,
                       float* dw, int cout, int cin, int accumulate, const float* scale, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* The same in two steps, so that one launch finalises many layers: `_partial` runs the tensor-core
+ * kernel only (split-K partial sums stay in `workspace`, which must stay alive and un-aliased until
+ * the reduction) and fills *desc_out; wcmc_wgrad_reduce_batch sums the splits of n layers, transposes
+ * to torch's (cout,cin,k,k) layout with full-sector stores and applies accumulate / scale.        */
+typedef struct {
+    const float* ws;     /* [nsplit][taps][cout_p][cin_p] partial sums */
+    float* dw;           /* (cout, cin, k, k) fp32 */
+    const float* scale;  /* device float or NULL */
+    int nsplit, cout, cin, taps, cout_p, cin_p, accumulate;
+} wcmc_wgrad_reduce_desc;
+#define WCMC_WGRAD_BATCH_MAX 32
+int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                              const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize,
+                              int pad, float* dw, int cout, int cin, int accumulate, const float* scale,
+                              void* workspace, size_t workspace_bytes, wcmc_wgrad_reduce_desc* desc_out,
+                              void* stream);
+int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs, int n, void* stream);
 /* db[co] (+)= scale * sum over all pixels of dy[pix][dy_coff+co]   (scale: device float or NULL) */
 int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs, int dy_coff, int cout, float* db,
                    int accumulate, const float* scale, void* stream);
@@ -213,6 +230,27 @@ int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff, const void
                            int prop_coff, const void* w1, const float* b1, const void* w2, const float* b2,
                            int outc, int outc_p, int dtype, int act1, int act2, float slope, void* h,
                            float* out, int B, int S, int HW, void* stream);
+
+/* ---- K12: clip_grad_value_ + Adam for all parameter tensors in one launch
+ * (/root/reference/support/interfaces.py:261 clip, :269-271 three optimiser steps; Adam with torch's
+ * defaults as constructed at /root/reference/train_kpcn.py:277) -----------------------------------
+ * dev_tensors: DEVICE array of descriptors; dev_blocks: DEVICE array of nblocks (tensor index,
+ * chunk index) pairs, one per CTA, chunk = wcmc_adam_chunk() elements; *dev_step = number of steps
+ * taken so far (the kernel uses t = *dev_step + 1 for the bias corrections and the call increments
+ * it); dev_ok_flag (optional): when it points at 0 nothing is modified (non-finite loss: the host
+ * raises after its one sync of the step).  clip <= 0 disables clipping; otherwise the clipped
+ * gradient is written back, as clip_grad_value_ does.                                            */
+typedef struct {
+    float* p;   /* parameter */
+    float* g;   /* gradient */
+    float* m;   /* exp_avg */
+    float* v;   /* exp_avg_sq */
+    long n;
+    float lr, beta1, beta2, eps;
+} wcmc_adam_tensor;
+int wcmc_adam_chunk(void);
+int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const int* dev_blocks, int nblocks, int* dev_step,
+                        const int* dev_ok_flag, float clip, void* stream);
 
 #ifdef __cplusplus
 }

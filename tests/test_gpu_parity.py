@@ -441,3 +441,48 @@ def test_full_frame_denoise_vs_oracle_and_tiling(backend, oracle):
         t = net(tile)["radiance"]                        # (1,3,92,92) = frame rows y0+18 .. y0+110
     full = out["radiance"][..., y0 + 18:y0 + 110, x0 + 18:x0 + 110]
     assert rel(t[..., 10:-10, 10:-10], full[..., 10:-10, 10:-10]) < TOL_IMG
+
+
+def test_fused_clip_adam_matches_torch(backend):
+    """wcmc_adam_clip_step on torch.optim.Adam's own state == clip_grad_value_ + Adam.step() of torch,
+    over several steps, tensors of awkward sizes, two optimisers with different learning rates; the
+    optimiser state stays loadable by torch (state_dict round trip); ok_flag = 0 leaves everything alone."""
+    from wcmc_b200 import optim as wopt
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(100, 39, 5, 5), (100,), (441, 100, 5, 5), (7,), (64, 36, 1, 1), (4097,), (1,)]
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)))
+              for i, s in enumerate(shapes)]
+        return ps, [torch.optim.Adam(ps[:4], lr=1e-4), torch.optim.Adam(ps[4:], lr=1e-6)]
+
+    pa, oa = make()
+    pb, ob = make()
+    fused = wopt.FusedClipAdam(ob)
+    assert all(wopt.supported(o) for o in ob)
+    for step in range(5):
+        grads = [torch.randn(s, device="cuda", generator=g) * (3.0 if step % 2 else 0.3) for s in shapes]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        torch.nn.utils.clip_grad_value_(pa, 1.0)
+        for o in oa:
+            o.step()
+        fused.step(clip=1.0)
+        for p, q in zip(pa, pb):
+            assert torch.equal(p.grad, q.grad)                       # clipped gradient written back
+            torch.testing.assert_close(q.detach(), p.detach(), rtol=1e-6, atol=1e-9)
+    for o1, o2 in zip(oa, ob):
+        s1, s2 = o1.state_dict(), o2.state_dict()
+        for k in s1["state"]:
+            assert float(s1["state"][k]["step"]) == float(s2["state"][k]["step"]) == 5.0
+            # same operations, but fused multiply-adds round once where torch's separate kernels round twice
+            torch.testing.assert_close(s2["state"][k]["exp_avg"], s1["state"][k]["exp_avg"], rtol=1e-5, atol=2e-7)
+            torch.testing.assert_close(s2["state"][k]["exp_avg_sq"], s1["state"][k]["exp_avg_sq"], rtol=1e-5, atol=2e-7)
+    before = [q.detach().clone() for q in pb]
+    for q in pb:
+        q.grad = torch.ones_like(q)
+    fused.step(clip=1.0, ok_flag=torch.zeros(1, dtype=torch.int32, device="cuda"), count=False)
+    for q, b in zip(pb, before):
+        assert torch.equal(q.detach(), b)
+    assert int(fused.t_dev) == 5

@@ -200,6 +200,36 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     }
 }
 
+struct ReduceBatch {
+    wcmc_wgrad_reduce_desc d[WCMC_WGRAD_BATCH_MAX];
+};
+
+// Finalisation of many layers in one launch: blockIdx.y = layer, a CTA owns output channels co =
+// blockIdx.x, blockIdx.x + gridDim.x, ...  For one co it sums the split-K slabs with coalesced reads
+// (ci fastest, as the workspace is laid out), transposes (tap, ci) -> (ci, tap) through shared memory and
+// writes torch's dw[co][ci][tap] block as one contiguous run (full-sector stores).
+__global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceBatch rb) {
+    extern __shared__ float tile[];
+    const wcmc_wgrad_reduce_desc& L = rb.d[blockIdx.y];
+    const float sc = L.scale != nullptr ? __ldg(L.scale) : 1.f;
+    const long slab = static_cast<long>(L.taps) * L.cout_p * L.cin_p;
+    const int per_co = L.cin * L.taps;
+    for (int co = blockIdx.x; co < L.cout; co += gridDim.x) {
+        for (int idx = threadIdx.x; idx < per_co; idx += blockDim.x) {
+            const int tap = idx / L.cin, ci = idx - tap * L.cin;
+            const float* src = L.ws + (static_cast<long>(tap) * L.cout_p + co) * L.cin_p + ci;
+            float s = 0.f;
+            for (int k = 0; k < L.nsplit; ++k) s += src[k * slab];
+            tile[ci * L.taps + tap] = s * sc;
+        }
+        __syncthreads();
+        float* dst = L.dw + static_cast<long>(co) * per_co;
+        for (int idx = threadIdx.x; idx < per_co; idx += blockDim.x)
+            dst[idx] = L.accumulate ? dst[idx] + tile[idx] : tile[idx];
+        __syncthreads();
+    }
+}
+
 }  // namespace wcmc
 
 using namespace wcmc;
@@ -242,12 +272,13 @@ extern "C" size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, in
     return static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
 }
 
-extern "C" int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                                 const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize,
-                                 int pad,
-                                 float* dw, int cout, int cin, int accumulate, const float* scale, void* workspace,
-                                 size_t workspace_bytes, void* stream_) {
+extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff,
+                                         int cin_p, const void* dy, int dy_dtype, int dy_cs, int dy_coff,
+                                         int cout_p, int ksize, int pad, float* dw, int cout, int cin,
+                                         int accumulate, const float* scale, void* workspace,
+                                         size_t workspace_bytes, wcmc_wgrad_reduce_desc* desc_out, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(desc_out != nullptr && dw != nullptr, WCMC_ESHAPE, "wgrad_partial: null desc_out / dw");
     WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "wgrad: ksize %d not in {1,3,5}", ksize);
     WCMC_REQUIRE(pad >= 0 && pad < ksize, WCMC_ESHAPE, "wgrad: bad pad %d", pad);
     WCMC_REQUIRE((x_dtype == WCMC_BF16 || x_dtype == WCMC_F16) && (dy_dtype == WCMC_BF16 || dy_dtype == WCMC_F16),
@@ -300,10 +331,52 @@ extern "C" int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W
     const int grid = p.m_tiles * p.ci_tiles * p.tap_groups * p.nsplit;
     conv_wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(tmdy, tmx, p);
     WCMC_LAUNCH_CHECK();
-    long total = static_cast<long>(cout) * cin * p.taps;
-    int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, dw, p.nsplit, cout, cin, p.taps, cout_p, cin_p,
-                                                    accumulate, scale);
-    WCMC_LAUNCH_CHECK();
+    desc_out->ws = p.ws;
+    desc_out->dw = dw;
+    desc_out->scale = scale;
+    desc_out->nsplit = p.nsplit;
+    desc_out->cout = cout;
+    desc_out->cin = cin;
+    desc_out->taps = p.taps;
+    desc_out->cout_p = cout_p;
+    desc_out->cin_p = cin_p;
+    desc_out->accumulate = accumulate;
     return WCMC_OK;
+}
+
+extern "C" int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs, int n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(host_descs != nullptr && n >= 0, WCMC_ESHAPE, "wgrad_reduce_batch: bad arguments");
+    for (int base = 0; base < n; base += WCMC_WGRAD_BATCH_MAX) {
+        const int m = std::min(WCMC_WGRAD_BATCH_MAX, n - base);
+        ReduceBatch rb;
+        int max_co = 1, max_tile = 1;
+        for (int i = 0; i < m; ++i) {
+            rb.d[i] = host_descs[base + i];
+            const wcmc_wgrad_reduce_desc& d = rb.d[i];
+            WCMC_REQUIRE(d.ws && d.dw && d.nsplit > 0 && d.cout > 0 && d.cin > 0 && d.taps > 0 &&
+                             d.cout <= d.cout_p && d.cin <= d.cin_p,
+                         WCMC_ESHAPE, "wgrad_reduce_batch: bad descriptor %d", base + i);
+            max_co = std::max(max_co, d.cout);
+            max_tile = std::max(max_tile, d.cin * d.taps);
+        }
+        WCMC_REQUIRE(max_tile * sizeof(float) <= 48 * 1024, WCMC_ESHAPE,
+                     "wgrad_reduce_batch: cin * k * k = %d too large", max_tile);
+        dim3 grid(std::min(max_co, 128), m);
+        wgrad_reduce_batch_kernel<<<grid, 256, max_tile * sizeof(float), stream>>>(rb);
+        WCMC_LAUNCH_CHECK();
+    }
+    return WCMC_OK;
+}
+
+extern "C" int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                                 const void* dy, int dy_dtype, int dy_cs, int dy_coff, int cout_p, int ksize,
+                                 int pad, float* dw, int cout, int cin, int accumulate, const float* scale,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+    wcmc_wgrad_reduce_desc d;
+    int rc = wcmc_conv2d_wgrad_partial(x, x_dtype, N, H, W, x_cs, x_coff, cin_p, dy, dy_dtype, dy_cs, dy_coff, cout_p,
+                                       ksize, pad, dw, cout, cin, accumulate, scale, workspace, workspace_bytes, &d,
+                                       stream_);
+    if (rc) return rc;
+    return wcmc_wgrad_reduce_batch(&d, 1, stream_);
 }

@@ -112,6 +112,10 @@ class KPCNInterface(BaseInterface):
         self.train_branches = train_branches
         self.disentanglement_option = disentanglement_option
         self.grad_sync = None  # optional callable(models): data-parallel gradient all-reduce
+        # clip_grad_value_ + the Adam steps as one kernel when every optimiser is a default torch Adam
+        # (WCMC_FUSED_ADAM=0 or `itf.fused_optim = False` keeps torch's own step)
+        self.fused_optim = os.environ.get("WCMC_FUSED_ADAM", "1") != "0"
+        self._fused_adam = None
 
     def __str__(self):
         return "KPCNInterface"
@@ -224,19 +228,36 @@ class KPCNInterface(BaseInterface):
             bad = keys[int((~finite).nonzero()[0])]
             raise RuntimeError("%s: Non-finite loss at train time." % bad)
 
-    def _logging(self, loss_dict):
-        keys = list(loss_dict)
-        self._assert_finite(loss_dict)
-        if self.grad_sync is not None:
-            self.grad_sync(self.models)
-        for model in self.models.values():
-            nn.utils.clip_grad_value_(model.parameters(), clip_value=1.0)
-        for k in keys:
+    def _fused(self):
+        """FusedClipAdam over this interface's optimisers, or None when they are not plain Adam."""
+        if not self.fused_optim:
+            return None
+        if self._fused_adam is None:
+            from wcmc_b200 import optim as wopt
+            opts = [self.optims["optim_" + name] for name in self.models]
+            self._fused_adam = wopt.FusedClipAdam(opts) if all(wopt.supported(o) for o in opts) else False
+        return self._fused_adam or None
+
+    def _accumulate(self, loss_dict):
+        for k in loss_dict:
             if "m_" + k not in self.m_losses:
                 self.m_losses["m_" + k] = torch.tensor(0.0, device=loss_dict[k].device)
             self.m_losses["m_" + k] += loss_dict[k]
 
+    def _logging(self, loss_dict):
+        self._assert_finite(loss_dict)
+        if self.grad_sync is not None:
+            self.grad_sync(self.models)
+        if self._fused() is None:   # otherwise the clip is part of the fused optimiser kernel
+            for model in self.models.values():
+                nn.utils.clip_grad_value_(model.parameters(), clip_value=1.0)
+        self._accumulate(loss_dict)
+
     def _optimization(self):
+        fused = self._fused()
+        if fused is not None:
+            fused.step(clip=1.0)
+            return
         for name in self.models:
             self.optims["optim_" + name].step()
 

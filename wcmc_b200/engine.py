@@ -63,11 +63,23 @@ class GraphedTrainStep:
         return loss, flags
 
     def _capture(self):
+        itf = self.itf
+        # single process: clip + Adam (one kernel, predicated on the finite flag) join the graph; with a
+        # gradient all-reduce between backward and update the optimiser stays outside
+        self.fused = itf._fused() if itf.grad_sync is None else None
+        if self.fused is not None:
+            self.fused.prepare()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             loss, flags = self._fwd_bwd()
             self.loss = loss
-            self.flags = torch.stack(flags).all() if flags else None
+            ok = torch.isfinite(torch.stack([v.reshape(()) for v in loss.values()])).all()
+            if flags:
+                ok = ok & torch.stack(flags).all()
+            self.flags = ok
+            if self.fused is not None:
+                self.ok_i32 = ok.to(torch.int32).reshape(1)
+                self.fused.step(clip=1.0, ok_flag=self.ok_i32, count=False)
 
     def __call__(self, batch):
         itf = self.itf
@@ -76,7 +88,13 @@ class GraphedTrainStep:
             if k in self.static:
                 self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()
-        if self.flags is not None and not bool(self.flags):
+        if self.fused is not None:
+            if not bool(self.flags):     # the single host sync of the step; the update was skipped on the device
+                raise RuntimeError("Infinite loss at train time.")
+            itf._accumulate(self.loss)
+            self.fused.note_step()
+            return self.loss
+        if not bool(self.flags):
             raise RuntimeError("Infinite loss at train time.")
         itf._logging(self.loss)       # finite check of the losses, grad sync, clip, m_losses
         itf._optimization()

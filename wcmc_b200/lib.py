@@ -26,6 +26,18 @@ class PackDesc(ctypes.Structure):
                 ("cin_p", c_int)]
 
 
+class WgradReduceDesc(ctypes.Structure):
+    """wcmc_wgrad_reduce_desc of include/wcmc.h"""
+    _fields_ = [("ws", c_void_p), ("dw", c_void_p), ("scale", c_void_p), ("nsplit", c_int), ("cout", c_int),
+                ("cin", c_int), ("taps", c_int), ("cout_p", c_int), ("cin_p", c_int), ("accumulate", c_int)]
+
+
+class AdamTensor(ctypes.Structure):
+    """wcmc_adam_tensor of include/wcmc.h"""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", ctypes.c_long),
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/wcmc.h (tests check this).
 SIGNATURES = {
     "wcmc_last_error": (ctypes.c_char_p, []),
@@ -41,6 +53,10 @@ SIGNATURES = {
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
     "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 6 + [c_void_p]
                           + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wcmc_conv2d_wgrad_partial": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 6 + [c_void_p]
+                                  + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, ctypes.POINTER(WgradReduceDesc),
+                                                   c_void_p]),
+    "wcmc_wgrad_reduce_batch": (c_int, [ctypes.POINTER(WgradReduceDesc), c_int, c_void_p]),
     "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_int, c_void_p, c_void_p]),
     "wcmc_kernel_apply_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
@@ -60,6 +76,8 @@ SIGNATURES = {
                                   c_void_p]),
     "wcmc_pathnet_final_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_void_p] * 4 + [c_int] * 5 + [c_float]
                                + [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "wcmc_adam_chunk": (c_int, []),
+    "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_int, c_void_p]),
 }
 
@@ -71,7 +89,8 @@ class WcmcError(RuntimeError):
 # ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
-_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2}
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2}
+_pending_wgrad = []  # (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
 
 
 def profile_start():
@@ -304,8 +323,10 @@ def _workspace(nbytes, device):
 
 
 def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=0, out=None, accumulate=False,
-                 scale=None):
-    """dw (cout,cin,k,k) fp32 (+)= sum dy (x) x ; x (N,H,W,Cs) / dy (N,Ho,Wo,Cs') 16-bit NHWC."""
+                 scale=None, defer=False):
+    """dw (cout,cin,k,k) fp32 (+)= sum dy (x) x ; x (N,H,W,Cs) / dy (N,Ho,Wo,Cs') 16-bit NHWC.
+    defer=True: only the tensor-core kernel runs now; the split-K reduction of every deferred layer
+    happens in ONE launch at the next wgrad_flush() (dw is not valid before that)."""
     lib = init(x.device)
     n, h, w, xcs = _h16(x).shape
     ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
@@ -315,11 +336,36 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
         accumulate = False
     assert out.is_contiguous() and out.dtype == torch.float32
     need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
+    work = 2.0 * n * ho * wo * ksize * ksize * cin * cout
+    if defer:
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        desc = WgradReduceDesc()
+        LAUNCHES["count"] -= 1   # _run counts 2 kernels per conv2d_wgrad call; the reduce comes at the flush
+        _run(lib.wcmc_conv2d_wgrad_partial, "conv2d_wgrad", work,
+             x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
+             ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(),
+             ctypes.byref(desc), _stream())
+        _pending_wgrad.append((desc, (ws, out, scale)))
+        return out
     ws = _workspace(need, x.device)
-    _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", 2.0 * n * ho * wo * ksize * ksize * cin * cout,
+    _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", work,
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
          ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(), _stream())
     return out
+
+
+def wgrad_flush():
+    """Finalises every deferred weight gradient (one launch per 32 layers)."""
+    if not _pending_wgrad:
+        return
+    lib = init()
+    n = len(_pending_wgrad)
+    descs = (WgradReduceDesc * n)(*[d for d, _ in _pending_wgrad])
+    byts = float(sum(d.nsplit * d.taps * d.cout_p * d.cin_p * 4 for d, _ in _pending_wgrad))
+    try:
+        _run(lib.wcmc_wgrad_reduce_batch, "wgrad_reduce", byts, descs, n, _stream())
+    finally:
+        _pending_wgrad.clear()
 
 
 def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False, scale=None):
@@ -545,3 +591,11 @@ def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc,
          prop.shape[-1], prop_coff, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), outc, outc_p,
          _dt(emb), acts[0], acts[1], float(slope), _p(hfin), out.data_ptr(), b, s, hw, _stream())
     return out
+
+
+# ---- K12: fused clip + Adam ------------------------------------------------------------------------
+def adam_clip_step(dev_tensors, dev_blocks, nblocks, dev_step, ok_flag, clip, nbytes=0.0):
+    """dev_tensors: uint8 device tensor holding AdamTensor structs; dev_blocks: int32 (nblocks, 2)."""
+    lib = init(dev_step.device)
+    _run(lib.wcmc_adam_clip_step, "adam_clip_step", nbytes, dev_tensors.data_ptr(), dev_blocks.data_ptr(), nblocks,
+         dev_step.data_ptr(), _p(ok_flag), float(clip), _stream())

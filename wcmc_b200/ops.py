@@ -114,7 +114,7 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
             DEBUG_TAP.append((i, dz.t.detach().clone(), dz.coff, l.cout, inv_scale))
         if want_param_grads:
             grads[2 * i] = lib.conv2d_wgrad(xin.t, dz.t, l.cout, l.cin, l.ksize, l.pad, l.cin_p, l.cout_p,
-                                            x_coff=xin.coff, dy_coff=dz.coff, scale=inv_scale)
+                                            x_coff=xin.coff, dy_coff=dz.coff, scale=inv_scale, defer=True)
             if i == len(layers) - 1:
                 grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, scale=inv_scale)
             else:
@@ -176,6 +176,7 @@ class ConvChainFn(torch.autograd.Function):
         dz = _act_bwd_full(dy, ctx.acts[-1], last)
         dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx, inv_scale=inv_s)
         gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff, scale=inv_s) if dx is not None else None
+        lib.wgrad_flush()
         ctx.acts = ctx.packed = None
         return (gx, None) + tuple(grads)
 
@@ -222,6 +223,7 @@ class KPCNBranchFn(torch.autograd.Function):
         dz = Slice(dl, 0, layers[-1].cout)
         dx, grads = chain_backward(dz, ctx.acts, layers, ctx.packed, ctx.need_dx, inv_scale=inv_s)
         gx = lib.nhwc_to_nchw(dx.t, layers[0].cin, dx.coff, scale=inv_s) if dx is not None else None
+        lib.wgrad_flush()
         ctx.acts = ctx.packed = ctx.aux = None
         return (gx, None, None, None) + tuple(grads)
 
@@ -331,6 +333,7 @@ class AutoencoderFn(torch.autograd.Function):
         dy = _grad_nhwc(g, lib.pad16(c_out), s)
         dx, grads = unet_backward(spec, ctx.uctx, dy, ctx.need_dx, inv_s)
         gx = lib.nhwc_to_nchw(dx.t, ctx.cin, dx.coff, scale=inv_s) if dx is not None else None
+        lib.wgrad_flush()
         ctx.uctx = None
         return (gx, None) + tuple(grads)
 
@@ -429,5 +432,6 @@ class PathNetFn(torch.autograd.Function):
                                    add_coff=d_both.coff)
         dze = _act_bwd_full(Slice(dz_emb, 0, c_emb), acts_emb[-1], spec.embedding[-1])
         _, g_emb = chain_backward(dze, acts_emb, spec.embedding, p_emb, False, inv_scale=inv_s)
+        lib.wgrad_flush()
         ctx.saved = None
         return (None, None) + tuple(g_emb) + tuple(g_unet) + tuple(g_fin)
