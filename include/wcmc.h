@@ -252,6 +252,19 @@ int wcmc_adam_chunk(void);
 int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const int* dev_blocks, int nblocks, int* dev_step,
                         const int* dev_ok_flag, float clip, void* stream);
 
+/* ---- K11: all-pairs form of the path-disentangling loss on the tensor cores (EXTENSION: the reference
+ * pairs each row with one random partner, /root/reference/support/losses.py:33-61; this is the quantity
+ * that estimator samples, BASELINE.json north_star (4) / configs[4]; oracle/allpairs_ref.py) ---------
+ * p_rows (N,D) fp32 row-major embeddings, ref_rows (N,3) fp32 reference radiance (tone-mapped inside).
+ *   e_ij = 1/2|P_i-P_j|^2 - 1/2|t_i-t_j|^2 over all i != j [with 1/2|t_i-t_j|^2 < tau when tau > 0]
+ *   mode 0: out[0] = sum 1/2 e^2 / N^2          mode 1: out[0] = (logsumexp(alpha [e,-e,0]) - log(1+2 kept)) / sqrt(alpha)
+ *   out[1] = number of kept ordered pairs.  *nonfinite |= 1 on non-finite input (caller zero-initialises).
+ * D <= 37.  workspace: wcmc_fmse_allpairs_workspace(N, D) bytes, 256-byte aligned.                 */
+size_t wcmc_fmse_allpairs_workspace(int N, int D);
+int wcmc_fmse_allpairs_fwd(const float* p_rows, const float* ref_rows, int N, int D, int mode, float alpha,
+                           float tau, float* out, int* nonfinite, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ SIGNATURES = {
                                + [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
+    "wcmc_fmse_allpairs_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
     "wcmc_act_bwd": (c_int, [c_void_p, c_int, c_int] * 3 + [ctypes.c_long, c_int, c_int, c_float, c_int, c_void_p]),
 }
 
@@ -89,7 +92,8 @@ class WcmcError(RuntimeError):
 # ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
-_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2}
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
+                     "fmse_allpairs_fwd": 3}
 _pending_wgrad = []  # (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
 
 
@@ -599,3 +603,21 @@ def adam_clip_step(dev_tensors, dev_blocks, nblocks, dev_step, ok_flag, clip, nb
     lib = init(dev_step.device)
     _run(lib.wcmc_adam_clip_step, "adam_clip_step", nbytes, dev_tensors.data_ptr(), dev_blocks.data_ptr(), nblocks,
          dev_step.data_ptr(), _p(ok_flag), float(clip), _stream())
+
+
+# ---- K11: all-pairs loss (extension) --------------------------------------------------------------------
+def fmse_allpairs_fwd(p_rows, ref_rows, mode=0, alpha=2.0, tau=0.0):
+    """p_rows (N,D), ref_rows (N,3) fp32 contiguous -> (out (2,) = [loss, kept ordered pairs], nonfinite flag)."""
+    lib = init(p_rows.device)
+    n, d = p_rows.shape
+    assert p_rows.dtype == torch.float32 and p_rows.is_contiguous()
+    assert ref_rows.dtype == torch.float32 and ref_rows.is_contiguous() and tuple(ref_rows.shape) == (n, 3)
+    out = torch.empty(2, dtype=torch.float32, device=p_rows.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=p_rows.device)
+    need = lib.wcmc_fmse_allpairs_workspace(n, d)
+    ws = _workspace(need + 256, p_rows.device)
+    off = (-ws.data_ptr()) % 256
+    _run(lib.wcmc_fmse_allpairs_fwd, "fmse_allpairs_fwd", 2.0 * n * n * (d + 3) / 2, p_rows.data_ptr(),
+         ref_rows.data_ptr(), n, d, int(mode), float(alpha), float(tau or 0.0), out.data_ptr(), flag.data_ptr(),
+         ws.data_ptr() + off, need, _stream())
+    return out, flag
