@@ -119,10 +119,12 @@ int wcmc_conv2d_wgrad(const void* x, int x_dtype, int N, int H, int W, int x_cs,
  * the reduction) and fills *desc_out; wcmc_wgrad_reduce_batch sums the splits of n layers, transposes
  * to torch's (cout,cin,k,k) layout with full-sector stores and applies accumulate / scale.        */
 typedef struct {
-    const float* ws;     /* [nsplit][taps][cout_p][cin_p] partial sums */
+    const float* ws;     /* partial sums: [nsplit][taps_a][cout_p][cin_p] for taps < taps_a, followed by
+                            [nsplit_b][taps - taps_a][cout_p][cin_p] for the last (short) tap group */
     float* dw;           /* (cout, cin, k, k) fp32 */
     const float* scale;  /* device float or NULL */
     int nsplit, cout, cin, taps, cout_p, cin_p, accumulate;
+    int nsplit_b, taps_a;
 } wcmc_wgrad_reduce_desc;
 #define WCMC_WGRAD_BATCH_MAX 32
 int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,

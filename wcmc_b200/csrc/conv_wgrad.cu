@@ -34,7 +34,7 @@ struct WgradParams {
     int cin_p, cout_p;
     int nt, ci_tiles, m_tiles;
     int cstride, tpg, tap_groups;
-    int nsplit;
+    int nsplit_a, nsplit_b, taps_a;   // K splits of the full tap groups / of the last (short) group; taps in full groups
     int tiles_x, tiles_y, total_tiles;
     int halo_w, halo_h, b_plane;  // b_plane: bytes between the two 64-channel halo planes
     int a_planes, b_planes;
@@ -57,15 +57,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // decode the work item
+    // CTAs are handed out in proportion to the taps a group carries: the last group of a 3x3 layer has 1 tap
+    // against 8 (5x5: 1 against 4), so it gets 1/8 (1/4) of the K splits of a full group.
+    const int per_mc = (p.tap_groups - 1) * p.nsplit_a + p.nsplit_b;
     int item = blockIdx.x;
-    const int split = item % p.nsplit; item /= p.nsplit;
-    const int tg = item % p.tap_groups; item /= p.tap_groups;
+    const int rr = item % per_mc; item /= per_mc;
     const int cit = item % p.ci_tiles; item /= p.ci_tiles;
     const int mtile = item;
+    const bool last_group = rr >= (p.tap_groups - 1) * p.nsplit_a;
+    const int tg = last_group ? p.tap_groups - 1 : rr / p.nsplit_a;
+    const int split = last_group ? rr - (p.tap_groups - 1) * p.nsplit_a : rr % p.nsplit_a;
+    const int nsplit = last_group ? p.nsplit_b : p.nsplit_a;
     const int tap0 = tg * p.tpg;
     const int ntap = min(p.tpg, p.taps - tap0);
     const int ci0 = cit * p.nt, co0 = mtile * 128;
-    const int my_tiles = (p.total_tiles - split + p.nsplit - 1) / p.nsplit;
+    const int my_tiles = (p.total_tiles - split + nsplit - 1) / nsplit;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmdy);
@@ -90,7 +96,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
         if (lane == 0) {
             int s = 0, ph = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const int tile = split + i * p.nsplit;
+                const int tile = split + i * nsplit;
                 const int tx = tile % p.tiles_x;
                 const int ty = (tile / p.tiles_x) % p.tiles_y;
                 const int n = tile / (p.tiles_x * p.tiles_y);
@@ -153,7 +159,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
         if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
         for (int tl = 0; tl < ntap; ++tl) {
             const int tap = tap0 + tl;
-            float* dst = p.ws + ((static_cast<size_t>(split) * p.taps + tap) * p.cout_p + co) * p.cin_p + ci0;
+            const size_t slab = static_cast<size_t>(p.cout_p) * p.cin_p;
+            float* dst = last_group
+                             ? p.ws + (static_cast<size_t>(p.nsplit_a) * p.taps_a +
+                                       static_cast<size_t>(split) * (p.taps - p.taps_a) + (tap - p.taps_a)) * slab
+                             : p.ws + (static_cast<size_t>(split) * p.taps_a + tap) * slab;
+            dst += static_cast<size_t>(co) * p.cin_p + ci0;
             for (int cc = 0; cc < ncc; ++cc) {
                 uint32_t v[16];
                 if (my_tiles > 0) {
@@ -178,28 +189,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// out[co][ci][tap] (+)= sum_split ws[split][tap][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int nsplit, int cout,
-                                    int cin, int taps, int cout_p, int cin_p, int accumulate,
-                                    const float* __restrict__ scale) {
-    const float sc = scale != nullptr ? __ldg(scale) : 1.f;
-    const long total = static_cast<long>(cout) * cin * taps;
-    const long slab = static_cast<long>(taps) * cout_p * cin_p;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        // iterate in workspace order (ci fastest) for coalesced reads
-        int ci = static_cast<int>(i % cin);
-        int co = static_cast<int>((i / cin) % cout);
-        int tap = static_cast<int>(i / (static_cast<long>(cin) * cout));
-        const float* src = ws + (static_cast<long>(tap) * cout_p + co) * cin_p + ci;
-        float s = 0.f;
-        for (int k = 0; k < nsplit; ++k) s += src[k * slab];
-        s *= sc;
-        float* d = dw + (static_cast<long>(co) * cin + ci) * taps + tap;
-        *d = accumulate ? (*d + s) : s;
-    }
-}
-
 struct ReduceBatch {
     wcmc_wgrad_reduce_desc d[WCMC_WGRAD_BATCH_MAX];
 };
@@ -212,15 +201,25 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceBat
     extern __shared__ float tile[];
     const wcmc_wgrad_reduce_desc& L = rb.d[blockIdx.y];
     const float sc = L.scale != nullptr ? __ldg(L.scale) : 1.f;
-    const long slab = static_cast<long>(L.taps) * L.cout_p * L.cin_p;
+    const long mat = static_cast<long>(L.cout_p) * L.cin_p;
+    const int taps_b = L.taps - L.taps_a;
+    const float* ws_b = L.ws + static_cast<long>(L.nsplit) * L.taps_a * mat;
     const int per_co = L.cin * L.taps;
     for (int co = blockIdx.x; co < L.cout; co += gridDim.x) {
         for (int idx = threadIdx.x; idx < per_co; idx += blockDim.x) {
             const int tap = idx / L.cin, ci = idx - tap * L.cin;
-            const float* src = L.ws + (static_cast<long>(tap) * L.cout_p + co) * L.cin_p + ci;
-            float s = 0.f;
-            for (int k = 0; k < L.nsplit; ++k) s += src[k * slab];
-            tile[ci * L.taps + tap] = s * sc;
+            const bool a = tap < L.taps_a;
+            const float* src = (a ? L.ws + tap * mat : ws_b + (tap - L.taps_a) * mat) + static_cast<long>(co) * L.cin_p + ci;
+            const long slab = (a ? L.taps_a : taps_b) * mat;
+            const int ns = a ? L.nsplit : L.nsplit_b;
+            float s0 = 0.f, s1 = 0.f;
+            int k = 0;
+            for (; k + 1 < ns; k += 2) {
+                s0 += src[k * slab];
+                s1 += src[(k + 1) * slab];
+            }
+            if (k < ns) s0 += src[k * slab];
+            tile[ci * L.taps + tap] = (s0 + s1) * sc;
         }
         __syncthreads();
         float* dst = L.dw + static_cast<long>(co) * per_co;
@@ -253,10 +252,23 @@ static int wgrad_plan(int N, int Ho, int Wo, int cin_p, int cout_p, int ksize, W
     p->tiles_x = (Wo + 7) / 8;
     p->tiles_y = (Ho + 15) / 16;
     p->total_tiles = N * p->tiles_x * p->tiles_y;
-    int base_items = p->m_tiles * p->ci_tiles * p->tap_groups;
-    int nsplit = wcmc_num_sms() / base_items;
-    nsplit = std::max(1, std::min(nsplit, p->total_tiles));
-    p->nsplit = nsplit;
+    {
+        const int budget = std::max(1, wcmc_num_sms() / (p->m_tiles * p->ci_tiles));   // CTAs per (cout, cin) tile
+        const int G = p->tap_groups;
+        const int rem = p->taps - (G - 1) * p->tpg;
+        p->taps_a = (G - 1) * p->tpg;
+        int nb, na;
+        if (G == 1) {
+            nb = na = budget;
+        } else if (rem == p->tpg) {
+            nb = na = std::max(1, budget / G);
+        } else {
+            nb = std::max(1, (budget * rem + p->taps / 2) / p->taps);
+            na = std::max(1, (budget - nb) / (G - 1));
+        }
+        p->nsplit_a = std::max(1, std::min(na, p->total_tiles));
+        p->nsplit_b = std::max(1, std::min(nb, p->total_tiles));
+    }
     p->halo_w = 8 + ksize - 1;
     p->halo_h = 16 + ksize - 1;
     p->b_plane = ((p->halo_w * p->halo_h * 128 + 1023) / 1024) * 1024;
@@ -269,7 +281,8 @@ extern "C" size_t wcmc_conv2d_wgrad_workspace(int N, int H, int W, int cin_p, in
     WgradParams p;
     const int Ho = H + 2 * pad - ksize + 1, Wo = W + 2 * pad - ksize + 1;
     wgrad_plan(N, Ho, Wo, cin_p, cout_p, ksize, &p);
-    return static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
+    return (static_cast<size_t>(p.nsplit_a) * p.taps_a + static_cast<size_t>(p.nsplit_b) * (p.taps - p.taps_a)) *
+           cout_p * cin_p * sizeof(float);
 }
 
 extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff,
@@ -295,7 +308,8 @@ extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int 
     WgradParams p;
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.ksize = ksize; p.pad = pad;
     wgrad_plan(N, Ho, Wo, cin_p, cout_p, ksize, &p);
-    size_t need = static_cast<size_t>(p.nsplit) * p.taps * cout_p * cin_p * sizeof(float);
+    size_t need = (static_cast<size_t>(p.nsplit_a) * p.taps_a + static_cast<size_t>(p.nsplit_b) * (p.taps - p.taps_a)) *
+                  cout_p * cin_p * sizeof(float);
     WCMC_REQUIRE(workspace != nullptr && workspace_bytes >= need, WCMC_EWORKSPACE,
                  "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
     p.ws = static_cast<float*>(workspace);
@@ -328,13 +342,15 @@ extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int 
             cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
         attr_set = true;
     }
-    const int grid = p.m_tiles * p.ci_tiles * p.tap_groups * p.nsplit;
+    const int grid = p.m_tiles * p.ci_tiles * ((p.tap_groups - 1) * p.nsplit_a + p.nsplit_b);
     conv_wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(tmdy, tmx, p);
     WCMC_LAUNCH_CHECK();
     desc_out->ws = p.ws;
     desc_out->dw = dw;
     desc_out->scale = scale;
-    desc_out->nsplit = p.nsplit;
+    desc_out->nsplit = p.nsplit_a;
+    desc_out->nsplit_b = p.nsplit_b;
+    desc_out->taps_a = p.taps_a;
     desc_out->cout = cout;
     desc_out->cin = cin;
     desc_out->taps = p.taps;
@@ -354,8 +370,8 @@ extern "C" int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs,
         for (int i = 0; i < m; ++i) {
             rb.d[i] = host_descs[base + i];
             const wcmc_wgrad_reduce_desc& d = rb.d[i];
-            WCMC_REQUIRE(d.ws && d.dw && d.nsplit > 0 && d.cout > 0 && d.cin > 0 && d.taps > 0 &&
-                             d.cout <= d.cout_p && d.cin <= d.cin_p,
+            WCMC_REQUIRE(d.ws && d.dw && d.nsplit > 0 && d.nsplit_b > 0 && d.cout > 0 && d.cin > 0 && d.taps > 0 &&
+                             d.taps_a >= 0 && d.taps_a < d.taps && d.cout <= d.cout_p && d.cin <= d.cin_p,
                          WCMC_ESHAPE, "wgrad_reduce_batch: bad descriptor %d", base + i);
             max_co = std::max(max_co, d.cout);
             max_tile = std::max(max_tile, d.cin * d.taps);

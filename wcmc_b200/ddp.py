@@ -35,6 +35,15 @@ class GradAllReduce:
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
 
 
+    def all_ranks(self, ok):
+        """Logical AND of a 0-d bool tensor over the ranks (a non-finite loss on one rank must stop them all)."""
+        if self.world == 1:
+            return ok
+        t = ok.to(torch.int32).reshape(1)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t[0] > 0
+
+
 def broadcast_parameters(models, src=0, group=None):
     """Replicas start from rank `src`'s weights."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

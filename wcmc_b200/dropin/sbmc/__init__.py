@@ -36,8 +36,12 @@ class KPCN(nn.Module):
         return ops.KPCNBranchFn.apply(x, crop_like(buf, tgt), self.ksize, layers, *params)
 
     def forward(self, data):
-        r_d = self._branch(self.diffuse, data["kpcn_diffuse_in"], data["kpcn_diffuse_buffer"])
-        r_s = self._branch(self.specular, data["kpcn_specular_in"], data["kpcn_specular_buffer"])
+        from wcmc_b200 import streams
+        with streams.fork("diffuse"):     # independent branches on two streams (see wcmc_b200/streams.py)
+            r_d = self._branch(self.diffuse, data["kpcn_diffuse_in"], data["kpcn_diffuse_buffer"])
+        with streams.fork("specular"):
+            r_s = self._branch(self.specular, data["kpcn_specular_in"], data["kpcn_specular_buffer"])
+        streams.join()
         albedo = crop_like(data["kpcn_albedo"], r_d)
         radiance = albedo * r_d + torch.exp(r_s) - 1.0
         return dict(radiance=radiance, diffuse=r_d, specular=r_s)

@@ -141,8 +141,16 @@ class KPCNInterface(BaseInterface):
 
     # ---- forward pieces ------------------------------------------------------------------------
     def _manifold_forward(self, batch):
-        return {"diffuse": self.models["backbone_diffuse"](batch),
-                "specular": self.models["backbone_specular"](batch)}
+        # The two path-embedding networks are independent: on two CUDA streams the tail of one network's
+        # kernels (partial last wave on 148 SMs, small U-Net levels) overlaps the other's.  Autograd runs each
+        # backward node on its forward stream, so the backward passes overlap the same way.
+        from wcmc_b200 import streams
+        with streams.fork("diffuse"):
+            d = self.models["backbone_diffuse"](batch)
+        with streams.fork("specular"):
+            s = self.models["backbone_specular"](batch)
+        streams.join()
+        return {"diffuse": d, "specular": s}
 
     def _regress_forward(self, batch):
         return self.models["dncnn"](batch)
@@ -206,8 +214,10 @@ class KPCNInterface(BaseInterface):
                     loss = loss + l_manif * self.w_manif
                 losses["l_" + name] = loss.detach()
                 branch_loss[name] = loss
-            branch_loss["diffuse"].backward()
-            branch_loss["specular"].backward()
+            # the reference calls L_diffuse.backward(); L_specular.backward() (:237-238): the two graphs share no
+            # parameter, so one traversal with both roots gives the same gradients and lets the branches' backward
+            # kernels (recorded on different streams) overlap
+            torch.autograd.backward([branch_loss["diffuse"], branch_loss["specular"]])
             with torch.no_grad():
                 losses["l_total"] = self.loss_funcs["l_recon"](total, tgt_total).detach()
         else:

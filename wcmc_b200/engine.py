@@ -12,6 +12,8 @@ with two restrictions: the path-disentangling loss must draw its pairing permuta
 (`FeatureMSE(rng="device")`: a CPU `randperm` would be frozen into the graph), and the every-1000-
 iterations PNG dump of the p-buffers is skipped.
 """
+import os
+
 import torch
 
 from support import losses as _losses
@@ -64,9 +66,11 @@ class GraphedTrainStep:
 
     def _capture(self):
         itf = self.itf
-        # single process: clip + Adam (one kernel, predicated on the finite flag) join the graph; with a
-        # gradient all-reduce between backward and update the optimiser stays outside
-        self.fused = itf._fused() if itf.grad_sync is None else None
+        # clip + Adam (one kernel, predicated on the finite flag) join the graph.  With data parallelism the
+        # NCCL gradient all-reduce sits between backward and update (support/interfaces.py:237-238 -> :261 ->
+        # :271) and is captured too (WCMC_GRAPH_ALLREDUCE=0 keeps all-reduce + optimiser outside the graph).
+        self.sync_in_graph = itf.grad_sync is not None and os.environ.get("WCMC_GRAPH_ALLREDUCE", "1") != "0"
+        self.fused = itf._fused() if (itf.grad_sync is None or self.sync_in_graph) else None
         if self.fused is not None:
             self.fused.prepare()
         self.graph = torch.cuda.CUDAGraph()
@@ -78,6 +82,10 @@ class GraphedTrainStep:
                 ok = ok & torch.stack(flags).all()
             self.flags = ok
             if self.fused is not None:
+                if self.sync_in_graph:
+                    itf.grad_sync(itf.models)
+                    ok = itf.grad_sync.all_ranks(ok)      # every rank takes or skips the update together
+                    self.flags = ok
                 self.ok_i32 = ok.to(torch.int32).reshape(1)
                 self.fused.step(clip=1.0, ok_flag=self.ok_i32, count=False)
 

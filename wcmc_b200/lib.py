@@ -29,7 +29,8 @@ class PackDesc(ctypes.Structure):
 class WgradReduceDesc(ctypes.Structure):
     """wcmc_wgrad_reduce_desc of include/wcmc.h"""
     _fields_ = [("ws", c_void_p), ("dw", c_void_p), ("scale", c_void_p), ("nsplit", c_int), ("cout", c_int),
-                ("cin", c_int), ("taps", c_int), ("cout_p", c_int), ("cin_p", c_int), ("accumulate", c_int)]
+                ("cin", c_int), ("taps", c_int), ("cout_p", c_int), ("cin_p", c_int), ("accumulate", c_int),
+                ("nsplit_b", c_int), ("taps_a", c_int)]
 
 
 class AdamTensor(ctypes.Structure):
@@ -92,7 +93,7 @@ class WcmcError(RuntimeError):
 # ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
-_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "conv2d_wgrad_k1": 2, "conv2d_wgrad_k3": 2, "conv2d_wgrad_k5": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
                      "fmse_allpairs_fwd": 3}
 _pending_wgrad = []  # (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
 
@@ -306,7 +307,7 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype
         assert bias.dtype == torch.float32 and bias.numel() >= cout_p
     if mask is not None:
         assert tuple(_h16(mask).shape[:3]) == (n, ho, wo)
-    _run(lib.wcmc_conv2d, "conv2d", 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
+    _run(lib.wcmc_conv2d, "conv2d_k%d" % ksize, 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, _p(bias),
          ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),
          0 if mask is None else mask.shape[3], mask_coff, float(slope), _p(colsum), _p(colsum_scale), flags,
@@ -345,7 +346,7 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
         ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         desc = WgradReduceDesc()
         LAUNCHES["count"] -= 1   # _run counts 2 kernels per conv2d_wgrad call; the reduce comes at the flush
-        _run(lib.wcmc_conv2d_wgrad_partial, "conv2d_wgrad", work,
+        _run(lib.wcmc_conv2d_wgrad_partial, "conv2d_wgrad_k%d" % ksize, work,
              x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
              ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(),
              ctypes.byref(desc), _stream())
@@ -365,7 +366,8 @@ def wgrad_flush():
     lib = init()
     n = len(_pending_wgrad)
     descs = (WgradReduceDesc * n)(*[d for d, _ in _pending_wgrad])
-    byts = float(sum(d.nsplit * d.taps * d.cout_p * d.cin_p * 4 for d, _ in _pending_wgrad))
+    byts = float(sum((d.nsplit * d.taps_a + d.nsplit_b * (d.taps - d.taps_a)) * d.cout_p * d.cin_p * 4
+                     for d, _ in _pending_wgrad))
     try:
         _run(lib.wcmc_wgrad_reduce_batch, "wgrad_reduce", byts, descs, n, _stream())
     finally:

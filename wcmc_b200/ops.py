@@ -271,10 +271,21 @@ class UNetSpec:
         return n
 
 
-def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True):
-    """Returns (output Slice, ctx).  params is the flat [w,b,...] list in spec order."""
+def unet_layers(spec: UNetSpec):
+    """Flat list of the LayerSpecs in parameter order (left, next level..., right)."""
+    out = list(spec.left)
+    if spec.nxt is not None:
+        out += unet_layers(spec.nxt) + list(spec.right)
+    return out
+
+
+def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True, packed=None):
+    """Returns (output Slice, ctx).  params is the flat [w,b,...] list in spec order; packed (optional) the
+    already packed weights of every layer in the same order (one pack launch for the whole network)."""
     nl = 2 * len(spec.left)
-    p_left = pack_chain(spec.left, params[:nl], need_dgrad)
+    if packed is None:
+        packed = pack_chain(unet_layers(spec), params, need_dgrad)
+    p_left = packed[:nl // 2]
     if spec.nxt is None:
         acts = chain_forward(x, spec.left, p_left)
         return acts[-1], dict(acts_left=acts, p_left=p_left)
@@ -287,10 +298,11 @@ def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True):
     acts_left = chain_forward(x, spec.left, p_left, out=Slice(cat, c_up, c_left))
     pooled = lib.maxpool2_fwd(cat, c_left, x_coff=c_up)
     nn_ = spec.nxt.n_params()
-    y_next, ctx_next = unet_forward(spec.nxt, Slice(pooled, 0, c_left), params[nl:nl + nn_], need_dgrad)
+    y_next, ctx_next = unet_forward(spec.nxt, Slice(pooled, 0, c_left), params[nl:nl + nn_], need_dgrad,
+                                    packed[nl // 2:(nl + nn_) // 2])
     assert y_next.c == c_up
     lib.upsample2_fwd(y_next.t, c_up, x_coff=y_next.coff, out=cat, out_coff=0)
-    p_right = pack_chain(spec.right, params[nl + nn_:], need_dgrad)
+    p_right = packed[(nl + nn_) // 2:]
     acts_right = chain_forward(Slice(cat, 0, c_up + c_left), spec.right, p_right)
     ctx = dict(acts_left=acts_left, p_left=p_left, cat=cat, pooled=pooled, ctx_next=ctx_next, y_next=y_next,
                acts_right=acts_right, p_right=p_right, c_up=c_up, c_left=c_left)
@@ -365,8 +377,9 @@ class PathNetFn(torch.autograd.Function):
         b, s, nf, h, w = paths.shape
         need = any(ctx.needs_input_grad)
         ne, nu = 2 * len(spec.embedding), spec.unet.n_params()
-        p_emb = pack_chain(spec.embedding, params[:ne], need)
-        p_fin = pack_chain(spec.final, params[ne + nu:], need)
+        # one launch packs the weights of all 20 layers (embedding, U-Net, final)
+        p_all = pack_chain(list(spec.embedding) + unet_layers(spec.unet) + list(spec.final), params, need)
+        p_emb, p_unet, p_fin = p_all[:ne // 2], p_all[ne // 2:(ne + nu) // 2], p_all[(ne + nu) // 2:]
         c_emb = spec.embedding[-1].cout
         c_prop = spec.final[0].cin - c_emb
         outc = spec.final[-1].cout
@@ -384,7 +397,7 @@ class PathNetFn(torch.autograd.Function):
                 hfin = torch.empty((b * s, h, w, spec.final[0].cout), dtype=ACT_DTYPE, device=dev)
             lib.pathnet_embed_fwd(px, p_emb, [l.act for l in spec.embedding], LEAKY_SLOPE, both, 0, reduced,
                                   x16=x16, h1=h1, h2=h2)
-            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
+            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need, p_unet)
             assert prop.c == c_prop
             out = lib.pathnet_final_fwd(both, 0, prop.t, prop.coff, p_fin, [l.act for l in spec.final], LEAKY_SLOPE,
                                         outc, b, s, hfin=hfin)
@@ -398,7 +411,7 @@ class PathNetFn(torch.autograd.Function):
             both = torch.empty((b * s, h, w, c_emb + c_prop), dtype=ACT_DTYPE, device=dev)
             acts_emb = chain_forward(x, spec.embedding, p_emb, out=Slice(both, 0, c_emb))
             reduced = lib.spp_reduce(both, b, s, c_emb, 1.0 / s)
-            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need)
+            prop, uctx = unet_forward(spec.unet, Slice(reduced, 0, c_emb), list(params[ne:ne + nu]), need, p_unet)
             assert prop.c == c_prop
             lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
             acts_fin = chain_forward(Slice(both, 0, c_emb + c_prop), spec.final, p_fin, last_fp32=True)
