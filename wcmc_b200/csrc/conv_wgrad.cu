@@ -57,8 +57,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // decode the work item
-    // CTAs are handed out in proportion to the taps a group carries: the last group of a 3x3 layer has 1 tap
-    // against 8 (5x5: 1 against 4), so it gets 1/8 (1/4) of the K splits of a full group.
+    // tap groups 0 .. G-2 carry tpg taps and nsplit_a K splits each, the last group the remaining taps and nsplit_b
     const int per_mc = (p.tap_groups - 1) * p.nsplit_a + p.nsplit_b;
     int item = blockIdx.x;
     const int rr = item % per_mc; item /= per_mc;
@@ -193,37 +192,43 @@ struct ReduceBatch {
     wcmc_wgrad_reduce_desc d[WCMC_WGRAD_BATCH_MAX];
 };
 
-// Finalisation of many layers in one launch: blockIdx.y = layer, a CTA owns output channels co =
-// blockIdx.x, blockIdx.x + gridDim.x, ...  For one co it sums the split-K slabs with coalesced reads
-// (ci fastest, as the workspace is laid out), transposes (tap, ci) -> (ci, tap) through shared memory and
-// writes torch's dw[co][ci][tap] block as one contiguous run (full-sector stores).
+// Finalisation of many layers in one launch: blockIdx.y = layer, blockIdx.x walks (output channel co, block of
+// kRedCi input channels).  For its block a CTA sums the split-K slabs with coalesced reads (ci fastest, as the
+// workspace is laid out; 8 independent loads in flight per thread), transposes (tap, ci) -> (ci, tap) through
+// shared memory and writes torch's dw[co][ci0 .. ci0+kRedCi)[tap] as one contiguous run (full-sector stores).
+constexpr int kRedCi = 32;
+
 __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceBatch rb) {
-    extern __shared__ float tile[];
+    __shared__ float tile[kRedCi * 25 + 8];
     const wcmc_wgrad_reduce_desc& L = rb.d[blockIdx.y];
     const float sc = L.scale != nullptr ? __ldg(L.scale) : 1.f;
     const long mat = static_cast<long>(L.cout_p) * L.cin_p;
     const int taps_b = L.taps - L.taps_a;
     const float* ws_b = L.ws + static_cast<long>(L.nsplit) * L.taps_a * mat;
-    const int per_co = L.cin * L.taps;
-    for (int co = blockIdx.x; co < L.cout; co += gridDim.x) {
-        for (int idx = threadIdx.x; idx < per_co; idx += blockDim.x) {
-            const int tap = idx / L.cin, ci = idx - tap * L.cin;
+    const int nblk = (L.cin + kRedCi - 1) / kRedCi;
+    for (int item = blockIdx.x; item < L.cout * nblk; item += gridDim.x) {
+        const int co = item / nblk, ci0 = (item - co * nblk) * kRedCi;
+        const int nci = min(kRedCi, L.cin - ci0);
+        const int per = nci * L.taps;
+        for (int idx = threadIdx.x; idx < per; idx += blockDim.x) {
+            const int tap = idx / nci, ci = idx - tap * nci;
             const bool a = tap < L.taps_a;
-            const float* src = (a ? L.ws + tap * mat : ws_b + (tap - L.taps_a) * mat) + static_cast<long>(co) * L.cin_p + ci;
+            const float* src = (a ? L.ws + tap * mat : ws_b + (tap - L.taps_a) * mat) + static_cast<long>(co) * L.cin_p +
+                               ci0 + ci;
             const long slab = (a ? L.taps_a : taps_b) * mat;
             const int ns = a ? L.nsplit : L.nsplit_b;
-            float s0 = 0.f, s1 = 0.f;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             int k = 0;
-            for (; k + 1 < ns; k += 2) {
-                s0 += src[k * slab];
-                s1 += src[(k + 1) * slab];
+            for (; k + 8 <= ns; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += __ldcs(src + (k + u) * slab);
             }
-            if (k < ns) s0 += src[k * slab];
-            tile[ci * L.taps + tap] = (s0 + s1) * sc;
+            for (; k < ns; ++k) acc[0] += __ldcs(src + k * slab);
+            tile[ci * L.taps + tap] = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]))) * sc;
         }
         __syncthreads();
-        float* dst = L.dw + static_cast<long>(co) * per_co;
-        for (int idx = threadIdx.x; idx < per_co; idx += blockDim.x)
+        float* dst = L.dw + (static_cast<long>(co) * L.cin + ci0) * L.taps;
+        for (int idx = threadIdx.x; idx < per; idx += blockDim.x)
             dst[idx] = L.accumulate ? dst[idx] + tile[idx] : tile[idx];
         __syncthreads();
     }
@@ -232,6 +237,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceBat
 }  // namespace wcmc
 
 using namespace wcmc;
+
+// Same K splits for every tap group by default: the kernel is bound by the L2 -> SM stream of the pixel tiles
+// (94 KB per tile for <= 4 taps of MMAs), not by the MMAs, so a group with fewer taps is NOT cheaper per tile, and
+// equal split counts keep the groups' CTAs walking the same tiles at the same time (measured: splits
+// proportional to the taps made the 5x5 layers 1.9x slower; wcmc_tuning_set("wgrad_uniform", 0) selects that).
+static int g_wgrad_uniform = 1;
+int wcmc_wgrad_set_uniform(int v) { g_wgrad_uniform = v; return 0; }
 
 static int wgrad_plan(int N, int Ho, int Wo, int cin_p, int cout_p, int ksize, WgradParams* p) {
     p->taps = ksize * ksize;
@@ -260,7 +272,7 @@ static int wgrad_plan(int N, int Ho, int Wo, int cin_p, int cout_p, int ksize, W
         int nb, na;
         if (G == 1) {
             nb = na = budget;
-        } else if (rem == p->tpg) {
+        } else if (rem == p->tpg || g_wgrad_uniform) {
             nb = na = std::max(1, budget / G);
         } else {
             nb = std::max(1, (budget * rem + p->taps / 2) / p->taps);
@@ -366,20 +378,18 @@ extern "C" int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs,
     for (int base = 0; base < n; base += WCMC_WGRAD_BATCH_MAX) {
         const int m = std::min(WCMC_WGRAD_BATCH_MAX, n - base);
         ReduceBatch rb;
-        int max_co = 1, max_tile = 1;
+        int max_items = 1;
         for (int i = 0; i < m; ++i) {
             rb.d[i] = host_descs[base + i];
             const wcmc_wgrad_reduce_desc& d = rb.d[i];
             WCMC_REQUIRE(d.ws && d.dw && d.nsplit > 0 && d.nsplit_b > 0 && d.cout > 0 && d.cin > 0 && d.taps > 0 &&
                              d.taps_a >= 0 && d.taps_a < d.taps && d.cout <= d.cout_p && d.cin <= d.cin_p,
                          WCMC_ESHAPE, "wgrad_reduce_batch: bad descriptor %d", base + i);
-            max_co = std::max(max_co, d.cout);
-            max_tile = std::max(max_tile, d.cin * d.taps);
+            WCMC_REQUIRE(d.taps <= 25, WCMC_ESHAPE, "wgrad_reduce_batch: more than 25 taps");
+            max_items = std::max(max_items, d.cout * ((d.cin + kRedCi - 1) / kRedCi));
         }
-        WCMC_REQUIRE(max_tile * sizeof(float) <= 48 * 1024, WCMC_ESHAPE,
-                     "wgrad_reduce_batch: cin * k * k = %d too large", max_tile);
-        dim3 grid(std::min(max_co, 128), m);
-        wgrad_reduce_batch_kernel<<<grid, 256, max_tile * sizeof(float), stream>>>(rb);
+        dim3 grid(std::min(max_items, 148 * 4), m);
+        wgrad_reduce_batch_kernel<<<grid, 256, 0, stream>>>(rb);
         WCMC_LAUNCH_CHECK();
     }
     return WCMC_OK;
