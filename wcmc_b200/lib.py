@@ -381,6 +381,8 @@ def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False, scale=None):
     if out is None:
         out = torch.empty((cout,), dtype=torch.float32, device=dy.device)
         accumulate = False
+    if accumulate:
+        LAUNCHES["count"] -= 1   # no zero kernel
     _run(lib.wcmc_bias_grad, "bias_grad", npix * cout * 2.0,
          dy.data_ptr(), _dt(dy), npix, dy.shape[3], dy_coff, cout, out.data_ptr(), int(accumulate), _p(scale),
          _stream())

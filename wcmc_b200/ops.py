@@ -100,11 +100,12 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
     slice).  Returns (dx Slice or None [still scaled], [dw0, db0, dw1, db1, ...] [un-scaled fp32])."""
     grads = [None] * (2 * len(layers))
     # bias gradients of layers 0..L-2 come for free from the epilogue of the data-gradient launch that
-    # produces their dz (column sums); one zero-filled buffer serves the whole chain
+    # produces their dz (column sums); the last layer's is a column-sum kernel accumulating into the same
+    # zero-filled buffer (one memset per chain instead of a zero kernel per bias)
     db_all = None
-    if want_param_grads and len(layers) > 1:
+    if want_param_grads:
         offs = [0]
-        for l in layers[:-1]:
+        for l in layers:
             offs.append(offs[-1] + l.cout_p)
         db_all = torch.zeros(offs[-1], dtype=torch.float32, device=dz.t.device)
     for i in range(len(layers) - 1, -1, -1):
@@ -115,10 +116,9 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
         if want_param_grads:
             grads[2 * i] = lib.conv2d_wgrad(xin.t, dz.t, l.cout, l.cin, l.ksize, l.pad, l.cin_p, l.cout_p,
                                             x_coff=xin.coff, dy_coff=dz.coff, scale=inv_scale, defer=True)
+            grads[2 * i + 1] = db_all[offs[i]:offs[i] + l.cout]
             if i == len(layers) - 1:
-                grads[2 * i + 1] = lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, scale=inv_scale)
-            else:
-                grads[2 * i + 1] = db_all[offs[i]:offs[i] + l.cout]
+                lib.bias_grad(dz.t, l.cout, dy_coff=dz.coff, out=grads[2 * i + 1], accumulate=True, scale=inv_scale)
         if i == 0 and not need_dx:
             return None, grads
         wd = packed[i][1]
