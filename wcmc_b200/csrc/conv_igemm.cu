@@ -62,14 +62,25 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 
 // One tap = MT x NK tcgen05.mma (compile-time counts: no branches between the MMAs, descriptor
 // deltas are immediates).  Executed by the single elected lane.
-template <int MT, int NK>
+// IL = true alternates the M tiles inside a tap (t is the inner loop), so two consecutive MMAs never
+// accumulate into the same TMEM tile (tuning bit 19 of `flags`; measured with tools/conv_bench.py knobs).
+template <int MT, int NK, bool IL>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint64_t ad, uint64_t bd, uint32_t idesc,
                                           uint32_t accum) {
+    if (IL) {
 #pragma unroll
-    for (int t = 0; t < MT; ++t) {
+        for (int j = 0; j < NK; ++j) {
 #pragma unroll
-        for (int j = 0; j < NK; ++j)
-            umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+            for (int t = 0; t < MT; ++t)
+                umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+#pragma unroll
+            for (int j = 0; j < NK; ++j)
+                umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+        }
     }
 }
 
@@ -85,7 +96,7 @@ struct BRing {
 
 // All taps of one 64-channel chunk.  MT / NK are compile-time so the tap body is branch-free:
 // one mbarrier wait, MT*NK back-to-back tcgen05.mma, one tcgen05.commit.
-template <int MT, int NK>
+template <int MT, int NK, bool IL>
 __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int row_step, uint32_t a_lo,
                                           uint32_t a_hi, uint32_t b_hi, uint32_t lo_fixed, uint32_t d_base,
                                           uint32_t idesc, uint32_t& accum) {
@@ -94,7 +105,7 @@ __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int ro
         mbar_wait(&br.full[br.idx], br.phase);
         tc_fence_after();
         if (elect_one()) {
-            issue_tap<MT, NK>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
+            issue_tap<MT, NK, IL>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
                               (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | br.cur_lo), idesc, accum);
             umma_commit(&br.empty[br.idx]);
         }
@@ -217,6 +228,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const uint32_t lo_fixed = 1u << 16;  // LBO field (16 B >> 4) sits in the low word
             const int row_step = (p.halo_w - p.ksize) * 8;
             const int ksize = p.ksize, nch = p.nch, cin_p = p.cin_p, mt = p.mt, total = p.total_items;
+            const bool interleave = (p.flags & (1 << 19)) != 0;
             const uint32_t plane0_lo = smem_u32(planes) >> 4;
             const uint32_t plane_stride_lo = static_cast<uint32_t>(p.plane_stride) >> 4;
             BRing br;
@@ -236,7 +248,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     const uint32_t a_lo = plane0_lo + ps * plane_stride_lo;
                     int nk = (cin_p - c * 64) >> 4;
                     if (nk > 4) nk = 4;
-#define WCMC_CHUNK(MT, NK) mma_chunk<MT, NK>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum)
+#define WCMC_CHUNK(MT, NK)                                                                                      \
+    do {                                                                                                        \
+        if (MT > 1 && interleave)                                                                               \
+            mma_chunk<MT, NK, true>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum);  \
+        else                                                                                                    \
+            mma_chunk<MT, NK, false>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum); \
+    } while (0)
                     switch (mt * 8 + nk) {
                         case 8 + 1: WCMC_CHUNK(1, 1); break;
                         case 8 + 2: WCMC_CHUNK(1, 2); break;
@@ -396,6 +414,11 @@ static int pick_nt(int cout_p) {
     return 128;
 }
 
+// tuning hook: wcmc_tuning_set("conv_interleave", 0 | 1) ORs bit 19 (alternate the M tiles inside a tap) into
+// the flags of every launch
+static int g_conv_interleave = 0;
+int wcmc_conv_set_interleave(int v) { g_conv_interleave = v ? 1 : 0; return 0; }
+
 extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                            const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
                            void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
@@ -449,7 +472,7 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.x_dtype = x_dtype; p.w_dtype = w_dtype;
     p.bias = bias; p.act = act;
     p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
-    p.slope = slope; p.flags = flags;
+    p.slope = slope; p.flags = flags | (g_conv_interleave ? (1 << 19) : 0);
     p.colsum = colsum; p.colsum_scale = colsum_scale;
 
     CUtensorMap tmx, tmw;

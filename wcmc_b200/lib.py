@@ -177,6 +177,10 @@ def init(device=None):
     if dev not in _inited_devices:
         _check(lib.wcmc_init(dev), "wcmc_init")
         _inited_devices.add(dev)
+        # measurement aid: WCMC_TUNE="knob=value,..." forwards to wcmc_tuning_set (tools/, bench A/B runs)
+        for item in filter(None, os.environ.get("WCMC_TUNE", "").split(",")):
+            name, _, val = item.partition("=")
+            _check(lib.wcmc_tuning_set(name.strip().encode(), int(val)), "wcmc_tuning_set")
     _ready["lib"], _ready["dev"] = lib, dev
     return lib
 
