@@ -39,6 +39,7 @@ struct ConvParams {
     int cin_p, nch;
     int cout_p, nt, n_tiles;
     int mt, regions_x, regions_y, total_items;
+    int total_regions, pair_items;   // CTA-pair mode: regions over the batch; (region pair, n tile) work items
     int halo_w, halo_h;
     int plane_stride, b_stride, b_stages, plane_slots;  // shared-memory carve-up
     void* out;
@@ -64,7 +65,13 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // deltas are immediates).  Executed by the single elected lane.
 // IL = true alternates the M tiles inside a tap (t is the inner loop), so two consecutive MMAs never
 // accumulate into the same TMEM tile (tuning bit 19 of `flags`; measured with tools/conv_bench.py knobs).
-template <int MT, int NK, bool IL>
+// PAIR = true issues tcgen05.mma.cta_group::2 (M = 256: this CTA's 128 pixels and the peer's).
+template <bool PAIR>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum) {
+    if (PAIR) umma_bf16_pair(d, ad, bd, idesc, accum);
+    else umma_bf16(d, ad, bd, idesc, accum);
+}
+template <int MT, int NK, bool IL, bool PAIR>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint64_t ad, uint64_t bd, uint32_t idesc,
                                           uint32_t accum) {
     if (IL) {
@@ -72,14 +79,14 @@ __device__ __forceinline__ void issue_tap(uint32_t d_base, uint64_t ad, uint64_t
         for (int j = 0; j < NK; ++j) {
 #pragma unroll
             for (int t = 0; t < MT; ++t)
-                umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+                umma_any<PAIR>(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
         }
     } else {
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
 #pragma unroll
             for (int j = 0; j < NK; ++j)
-                umma_bf16(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
+                umma_any<PAIR>(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
         }
     }
 }
@@ -96,7 +103,7 @@ struct BRing {
 
 // All taps of one 64-channel chunk.  MT / NK are compile-time so the tap body is branch-free:
 // one mbarrier wait, MT*NK back-to-back tcgen05.mma, one tcgen05.commit.
-template <int MT, int NK, bool IL>
+template <int MT, int NK, bool IL, bool PAIR>
 __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int row_step, uint32_t a_lo,
                                           uint32_t a_hi, uint32_t b_hi, uint32_t lo_fixed, uint32_t d_base,
                                           uint32_t idesc, uint32_t& accum) {
@@ -105,9 +112,10 @@ __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int ro
         mbar_wait(&br.full[br.idx], br.phase);
         tc_fence_after();
         if (elect_one()) {
-            issue_tap<MT, NK, IL>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
-                              (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | br.cur_lo), idesc, accum);
-            umma_commit(&br.empty[br.idx]);
+            issue_tap<MT, NK, IL, PAIR>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
+                                        (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | br.cur_lo), idesc, accum);
+            if (PAIR) umma_commit_pair(&br.empty[br.idx], 3);
+            else umma_commit(&br.empty[br.idx]);
         }
         __syncwarp();
         accum = 1;
@@ -118,6 +126,33 @@ __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int ro
     }
 }
 
+// Work decomposition.  Single CTA: item -> (region, n tile).  CTA pair (cluster of 2, cta_group::2): the two
+// CTAs take two DIFFERENT regions (2*rp, 2*rp + 1) of the SAME n tile -- each loads its own halo into its own
+// shared memory, and one M = 256 MMA of the leader covers both (the A descriptor addresses the same offsets in
+// both CTAs); each CTA holds only half of the weight tile (N/2 rows), so the B operand traffic per CTA and the
+// shared-memory reads per MMA drop from 4 KB + nt*32 B to 4 KB + nt*16 B.  An odd region count leaves the last
+// pair with a dead second region (computed on the clamped region, never stored).
+struct Item {
+    int n, rx, ry, n0;
+    bool live;
+};
+template <bool PAIR>
+__device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int rank) {
+    Item it;
+    int r = item / p.n_tiles;
+    it.n0 = (item - r * p.n_tiles) * p.nt;
+    it.live = true;
+    if (PAIR) {
+        r = 2 * r + rank;
+        if (r >= p.total_regions) { r = p.total_regions - 1; it.live = false; }
+    }
+    it.rx = r % p.regions_x;
+    it.ry = (r / p.regions_x) % p.regions_y;
+    it.n = r / (p.regions_x * p.regions_y);
+    return it;
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                   const ConvParams p) {
@@ -139,6 +174,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // pair mode: cluster rank 0 is the leader (issues the MMAs, owns the full / acc_empty barriers)
+    const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+    const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int n_items = PAIR ? p.pair_items : p.total_items;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmx);
@@ -153,43 +193,56 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 256);
+            mbar_init(&acc_empty[i], PAIR ? 512 : 256);   // the epilogue threads of both CTAs release a buffer
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    __syncwarp();
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(tmem_ptr, 512);
+        else tmem_alloc(tmem_ptr, 512);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers and TMEM exist before anything is signalled to it
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     const int taps = p.ksize * p.ksize;
     const int region_w = 8 * p.mt;
     const uint32_t plane_bytes = static_cast<uint32_t>(p.halo_w * p.halo_h * 128);
-    const uint32_t b_bytes = static_cast<uint32_t>(p.nt * 128);
+    const uint32_t b_bytes = static_cast<uint32_t>(p.nt * 128);   // whole n tile (a pair CTA loads half of it)
 
     if (warp == 0) {
         // ---------------- halo producer ----------------
         if (lane == 0) {
             int ps = 0, ph = 0, loaded = 0;
             const bool dry = (p.flags & (1 << 17)) != 0;   // tuning knob: planes loaded once (wrong results)
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int r = item / p.n_tiles;
-                int rx = r % p.regions_x;
-                int ry = (r / p.regions_x) % p.regions_y;
-                int n = r / (p.regions_x * p.regions_y);
+            for (int item = item0; item < n_items; item += item_step) {
+                const Item w = decode_item<PAIR>(p, item, rank);
                 for (int c = 0; c < p.nch; ++c) {
                     mbar_wait(&plane_empty[ps], ph ^ 1);
                     if (dry && loaded >= kPlaneSlots) {
-                        mbar_arrive(&plane_full[ps]);
+                        if (rank == 0) mbar_arrive(&plane_full[ps]);
+                    } else if (PAIR) {
+                        // both halos are signalled on the leader's barrier, which expects the two of them
+                        if (rank == 0) mbar_expect_tx(&plane_full[ps], 2 * plane_bytes);
+                        tma_load_4d_pair(planes + ps * p.plane_stride, &tmx, mapa_u32(smem_u32(&plane_full[ps]), 0),
+                                         c * 64, w.rx * region_w - p.pad, w.ry * 16 - p.pad, w.n);
+                        ++loaded;
                     } else {
                         mbar_expect_tx(&plane_full[ps], plane_bytes);
                         tma_load_4d(planes + ps * p.plane_stride, &tmx, &plane_full[ps], c * 64,
-                                    rx * region_w - p.pad, ry * 16 - p.pad, n);
+                                    w.rx * region_w - p.pad, w.ry * 16 - p.pad, w.n);
                         ++loaded;
                     }
                     if (++ps == kPlaneSlots) { ps = 0; ph ^= 1; }
                 }
+            }
+            // tail: every slot released by the MMAs (a pair CTA must not exit while commits can still arrive)
+            for (int i = 0; i < kPlaneSlots; ++i) {
+                mbar_wait(&plane_empty[ps], ph ^ 1);
+                if (++ps == kPlaneSlots) { ps = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -197,13 +250,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         if (lane == 0) {
             int bs = 0, ph = 0, loaded = 0;
             const bool dry = (p.flags & (1 << 16)) != 0;   // tuning knob: weight ring filled once (wrong results)
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                int n0 = (item % p.n_tiles) * p.nt;
+            for (int item = item0; item < n_items; item += item_step) {
+                const int n0 = (item % p.n_tiles) * p.nt;
                 for (int c = 0; c < p.nch; ++c) {
                     for (int tap = 0; tap < taps; ++tap) {
                         mbar_wait(&b_empty[bs], ph ^ 1);
                         if (dry && loaded >= kBStages) {
-                            mbar_arrive(&b_full[bs]);
+                            if (rank == 0) mbar_arrive(&b_full[bs]);
+                        } else if (PAIR) {
+                            // this CTA's half of the n tile (the box of tmw is nt/2 rows tall in pair mode)
+                            if (rank == 0) mbar_expect_tx(&b_full[bs], b_bytes);
+                            tma_load_3d_pair(bst + bs * p.b_stride, &tmw, mapa_u32(smem_u32(&b_full[bs]), 0), c * 64,
+                                             tap, n0 + rank * (p.nt >> 1));
+                            ++loaded;
                         } else {
                             mbar_expect_tx(&b_full[bs], b_bytes);
                             tma_load_3d(bst + bs * p.b_stride, &tmw, &b_full[bs], c * 64, tap, n0);
@@ -213,6 +272,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     }
                 }
             }
+            for (int i = 0; i < kBStages; ++i) {   // tail, as for the halos
+                mbar_wait(&b_empty[bs], ph ^ 1);
+                if (++bs == kBStages) { bs = 0; ph ^= 1; }
+            }
         }
     } else if (warp == 2) {
         // ---------------- MMA issuer ----------------
@@ -220,14 +283,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         // and the tcgen05.mma of a tap issue back to back); one elected lane issues them.  Descriptors
         // are built once per plane / stage; per MMA only the 14-bit start-address field moves, by
         // compile-time constants (issue_tap).  The (mt, nk) dispatch happens once per chunk.
-        {
-            const uint32_t idesc = make_idesc_f16(128, p.nt, 0, 0, p.x_dtype, p.w_dtype);
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, p.nt, 0, 0, p.x_dtype, p.w_dtype);
             const uint32_t sbo = static_cast<uint32_t>(p.halo_w * 128);
             const uint32_t a_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 16, sbo, 0) >> 32);
             const uint32_t b_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 16, 1024, 0) >> 32);
             const uint32_t lo_fixed = 1u << 16;  // LBO field (16 B >> 4) sits in the low word
             const int row_step = (p.halo_w - p.ksize) * 8;
-            const int ksize = p.ksize, nch = p.nch, cin_p = p.cin_p, mt = p.mt, total = p.total_items;
+            const int ksize = p.ksize, nch = p.nch, cin_p = p.cin_p, mt = p.mt;
             const bool interleave = (p.flags & (1 << 19)) != 0;
             const uint32_t plane0_lo = smem_u32(planes) >> 4;
             const uint32_t plane_stride_lo = static_cast<uint32_t>(p.plane_stride) >> 4;
@@ -236,9 +299,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             br.base_lo = smem_u32(bst) >> 4; br.stride_lo = static_cast<uint32_t>(p.b_stride) >> 4;
             br.cur_lo = br.base_lo; br.stages = p.b_stages; br.idx = 0; br.phase = 0;
             int ps = 0, pph = 0, it = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+            for (int item = item0; item < n_items; item += item_step, ++it) {
                 const int buf = it & 1;
-                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                if (PAIR) mbar_wait_cluster(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                else mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + buf * 256;
                 uint32_t accum = 0;
@@ -251,9 +315,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
 #define WCMC_CHUNK(MT, NK)                                                                                      \
     do {                                                                                                        \
         if (MT > 1 && interleave)                                                                               \
-            mma_chunk<MT, NK, true>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum);  \
+            mma_chunk<MT, NK, true, PAIR>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum);  \
         else                                                                                                    \
-            mma_chunk<MT, NK, false>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum); \
+            mma_chunk<MT, NK, false, PAIR>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum); \
     } while (0)
                     switch (mt * 8 + nk) {
                         case 8 + 1: WCMC_CHUNK(1, 1); break;
@@ -266,11 +330,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                         default: WCMC_CHUNK(2, 4); break;
                     }
 #undef WCMC_CHUNK
-                    if (elect_one()) umma_commit(&plane_empty[ps]);
+                    if (elect_one()) {
+                        if (PAIR) umma_commit_pair(&plane_empty[ps], 3);
+                        else umma_commit(&plane_empty[ps]);
+                    }
                     __syncwarp();
                     if (++ps == kPlaneSlots) { ps = 0; pph ^= 1; }
                 }
-                if (elect_one()) umma_commit(&acc_full[buf]);
+                if (elect_one()) {
+                    if (PAIR) umma_commit_pair(&acc_full[buf], 3);
+                    else umma_commit(&acc_full[buf]);
+                }
                 __syncwarp();
             }
         }
@@ -287,20 +357,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         const int ccs = (p.mt == 2) ? 1 : 2;
         const int t = (p.mt == 2) ? half : 0;
         int it = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const uint32_t acc_empty_leader = PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;
+        for (int item = item0; item < n_items; item += item_step, ++it) {
             const int buf = it & 1;
-            int r = item / p.n_tiles;
-            const int n0 = (item % p.n_tiles) * p.nt;
-            const int rx = r % p.regions_x;
-            const int ry = (r / p.regions_x) % p.regions_y;
-            const int n = r / (p.regions_x * p.regions_y);
+            const Item w = decode_item<PAIR>(p, item, rank);
+            const int n0 = w.n0, rx = w.rx, ry = w.ry, n = w.n;
             int ncc = (p.cout_p - n0) >> 4;
             if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const int oy = ry * 16 + ty;
             const int ox = rx * region_w + 8 * t + tx;
-            const bool valid = (oy < p.Ho) && (ox < p.Wo);
+            const bool valid = w.live && (oy < p.Ho) && (ox < p.Wo);
             const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
 
@@ -394,13 +462,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
+            if (PAIR) mbar_arrive_cluster(acc_empty_leader + buf * 8);
+            else mbar_arrive(&acc_empty[buf]);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (PAIR) cluster_sync_all();   // nobody leaves while the peer may still read its shared memory / TMEM
+    else __syncthreads();
+    if (warp == 2) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 }  // namespace wcmc
@@ -418,6 +491,10 @@ static int pick_nt(int cout_p) {
 // the flags of every launch
 static int g_conv_interleave = 0;
 int wcmc_conv_set_interleave(int v) { g_conv_interleave = v ? 1 : 0; return 0; }
+// tuning hook: wcmc_tuning_set("conv_pair", 0 | 1): CTA-pair (cta_group::2, M = 256) launches for the k > 1
+// layers that fill the machine (flags bit 20 forces a pair launch, bit 21 forbids it)
+static int g_conv_pair = 0;
+int wcmc_conv_set_pair(int v) { g_conv_pair = v ? 1 : 0; return 0; }
 
 extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                            const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
@@ -466,6 +543,11 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.regions_x = (Wo + 8 * mt - 1) / (8 * mt);
     p.regions_y = (Ho + 15) / 16;
     p.total_items = N * p.regions_x * p.regions_y * p.n_tiles;
+    p.total_regions = N * p.regions_x * p.regions_y;
+    p.pair_items = ((p.total_regions + 1) / 2) * p.n_tiles;
+    bool pair = g_conv_pair && ksize > 1 && p.total_items >= sms;
+    if (flags & (1 << 20)) pair = true;
+    if (flags & (1 << 21)) pair = false;
     p.halo_w = 8 * mt + ksize - 1;
     p.halo_h = 16 + ksize - 1;
     p.out = y; p.out_cs = y_cs; p.out_coff = y_coff; p.out_dtype = y_dtype;
@@ -491,12 +573,12 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
         uint64_t dims[3] = {static_cast<uint64_t>(cin_p), static_cast<uint64_t>(taps),
                             static_cast<uint64_t>(cout_p)};
         uint64_t strides[2] = {static_cast<uint64_t>(cin_p) * 2, static_cast<uint64_t>(cin_p) * 2 * taps};
-        uint32_t box[3] = {64, 1, static_cast<uint32_t>(p.nt)};
+        uint32_t box[3] = {64, 1, static_cast<uint32_t>(pair ? p.nt / 2 : p.nt)};   // a pair CTA holds half the tile
         int rc = wcmc_encode_tmap_bf16(&tmw, w_packed, 3, dims, strides, box, 1);
         if (rc) return rc;
     }
     p.plane_stride = ((p.halo_w * p.halo_h * 128 + 1023) / 1024) * 1024;
-    p.b_stride = ((p.nt * 128 + 1023) / 1024) * 1024;
+    p.b_stride = (((pair ? p.nt / 2 : p.nt) * 128 + 1023) / 1024) * 1024;
     // Two halo slots are enough when a chunk carries k*k taps of MMAs (the next plane loads during a whole
     // chunk); 1x1 convolutions have one tap per region and are HBM-bound: give them a deeper plane ring.
     p.plane_slots = (ksize == 1) ? kMaxPlaneSlots : 2;
@@ -507,12 +589,32 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     const int smem_bytes = 1024 + kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
     static bool attr_set = false;
     if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kConvSmemMax + 1024));
+        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kConvSmemMax + 1024));
         attr_set = true;
     }
+    if (pair) {
+        WCMC_REQUIRE(p.nt % 16 == 0, WCMC_ESHAPE, "conv2d: pair launch needs an n tile that is a multiple of 16");
+        int grid = 2 * p.pair_items < (sms & ~1) ? 2 * p.pair_items : (sms & ~1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmx, tmw, p));
+        return WCMC_OK;
+    }
     int grid = p.total_items < sms ? p.total_items : sms;
-    conv_igemm_kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
+    conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
