@@ -228,3 +228,69 @@ def kpcn_validate(models, batch, *, use_llpm_buf, disentangle="m11r11"):
     out = models["dncnn"](batch)
     tgt = crop_like(batch["target_total"], out["radiance"])
     return out["radiance"], p_buffers, relative_mse(out["radiance"], tgt)
+
+
+# ------------------------------------------------------------------------------------------------
+# the ablation interfaces (re-wirings of the same step)
+# ------------------------------------------------------------------------------------------------
+def kpcn_ref_batch(batch):
+    """interfaces.py:543-552 / :566-575 (KPCNRefInterface): KPCN inputs = cat[inputs, reference image]."""
+    new = dict(batch)
+    new["kpcn_diffuse_in"] = torch.cat([batch["kpcn_diffuse_in"], batch["target_diffuse"]], 1)
+    new["kpcn_specular_in"] = torch.cat([batch["kpcn_specular_in"], batch["target_specular"]], 1)
+    return new
+
+
+def kpcn_ref_train_step(models, optims, batch, train_branches=True):
+    """KPCNRefInterface.train_batch (interfaces.py:540-561): the vanilla step on the widened inputs."""
+    return kpcn_train_step(models, optims, kpcn_ref_batch(batch), use_llpm_buf=False, manif_learn=False,
+                           train_branches=train_branches)
+
+
+def kpcn_pre_train_step(models, optims, batch, *, manif_learn, w_manif=0.1, train_branches=True, non_local=True):
+    """KPCNPreInterface.train_batch (interfaces.py:616-672) with its own _backward / _logging / _optimization
+    (:674-750).  manif_learn=True: only the two PathNets run, the manifold loss is taken on the UNcropped
+    p-buffers and targets (:686-699), only the backbones are clipped and stepped.  manif_learn=False: PathNets
+    forward (their graph is kept, as in the reference), KPCN trained on [in | mean p | var p]; only `dncnn` is
+    clipped and stepped.  Returns the loss dict."""
+    l1 = nn.functional.l1_loss
+    models["backbone_diffuse"].zero_grad()
+    models["backbone_specular"].zero_grad()
+    loss = {}
+    if manif_learn:
+        p = {"diffuse": models["backbone_diffuse"](batch), "specular": models["backbone_specular"](batch)}
+        Lm_d = feature_mse(p["diffuse"], batch["target_diffuse"], non_local) * w_manif
+        Lm_s = feature_mse(p["specular"], batch["target_specular"], non_local) * w_manif
+        loss["l_manif_diffuse"], loss["l_manif_specular"] = Lm_d.detach() / w_manif, Lm_s.detach() / w_manif
+        Lm_d.backward()
+        Lm_s.backward()
+    else:
+        models["dncnn"].zero_grad()
+        p = {"diffuse": models["backbone_diffuse"](batch), "specular": models["backbone_specular"](batch)}
+        nb = dict(batch)
+        nb["kpcn_diffuse_in"] = pbuffer_concat(batch["kpcn_diffuse_in"], p["diffuse"])
+        nb["kpcn_specular_in"] = pbuffer_concat(batch["kpcn_specular_in"], p["specular"])
+        out = models["dncnn"](nb)
+        total, diffuse, specular = out["radiance"], out["diffuse"], out["specular"]
+        tgt_total = crop_like(batch["target_total"], total)
+        if train_branches:
+            L_d = l1(diffuse, crop_like(batch["target_diffuse"], diffuse))
+            L_s = l1(specular, crop_like(batch["target_specular"], specular))
+            loss["l_diffuse"], loss["l_specular"] = L_d.detach(), L_s.detach()
+            L_d.backward()
+            L_s.backward()
+            with torch.no_grad():
+                loss["l_total"] = l1(total, tgt_total)
+        else:
+            L_t = l1(total, tgt_total)
+            loss["l_total"] = L_t.detach()
+            L_t.backward()
+    for k, v in loss.items():
+        if not torch.isfinite(v).all():
+            raise RuntimeError("%s: Non-finite loss at train time." % k)
+    trained = [n for n in models if (("backbone" in n) if manif_learn else ("dncnn" in n))]
+    for n in trained:
+        nn.utils.clip_grad_value_(models[n].parameters(), clip_value=1.0)
+    for n in trained:
+        optims["optim_" + n].step()
+    return loss

@@ -486,3 +486,83 @@ def test_fused_clip_adam_matches_torch(backend):
     for q, b in zip(pb, before):
         assert torch.equal(q.detach(), b)
     assert int(fused.t_dev) == 5
+
+
+# ---------------------------------------------------------------------------------------------
+# the ablation interfaces on the same kernels, against vectors produced by the REFERENCE's
+# own KPCNRefInterface / KPCNPreInterface (tests/golden/make_golden_n4.py)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden_n4():
+    import os
+    from tests.conftest import ROOT
+    return torch.load(os.path.join(ROOT, "tests", "golden", "ref_golden_n4.pt"), weights_only=False)
+
+
+def _loss_funcs(backend, manif):
+    lf = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+          "l_test": backend.losses.RelativeMSE()}
+    if manif:
+        lf["l_manif"] = backend.losses.FeatureMSE(non_local=True)
+    return lf
+
+
+def _check_step_vs_golden(models, itf, g):
+    assert set(itf.m_losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        assert rel(itf.m_losses[k].cpu(), v) < (TOL_MANIF if "manif" in k else TOL_IMG), k
+    for name, m in models.items():
+        assert m.training == g["training"][name], name
+        has_grads = float(g["grad_abs_sums"][name].min()) >= 0
+        if has_grads:
+            gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()]).cpu()
+            assert rel(gs, g["grad_abs_sums"][name]) < 3e-2, name
+        for p_, want in zip(m.parameters(), g["param_sums"][name]):
+            tol = 1e-4 * (6 * p_.numel() ** 0.5 + 0.03 * p_.numel()) + 1e-3 * abs(float(want))
+            assert abs(float(p_.detach().double().sum()) - float(want)) < tol, name
+
+
+def test_ref_interface_matches_reference_golden(backend, oracle, golden_n4):
+    g = golden_n4["ref"]
+    torch.manual_seed(0)
+    ref_models = {"dncnn": oracle.KPCN(g["n_in"])}
+    models = {"dncnn": backend.KPCN(g["n_in"])}
+    models["dncnn"].load_state_dict(ref_models["dncnn"].state_dict())
+    models["dncnn"].cuda()
+    optims = {"optim_dncnn": torch.optim.Adam(models["dncnn"].parameters(), lr=1e-4)}
+    itf = backend.itf.KPCNRefInterface(models, optims, _loss_funcs(backend, False), types.SimpleNamespace(model_name="t"))
+    batch = to_cuda(make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=False))
+    itf.to_train_mode()
+    itf.preprocess(batch)
+    itf.train_batch(batch)
+    _check_step_vs_golden(models, itf, g)
+    itf.to_eval_mode()
+    with torch.no_grad():
+        rad, pb = itf.validate_batch(batch)
+    assert pb is None
+    assert rel(rad.cpu(), g["val_radiance"]) < TOL_IMG
+    assert rel(itf.m_losses["m_val"].cpu(), g["m_val"]) < 5e-3
+
+
+@pytest.mark.parametrize("tag", ["pre_manifold", "pre_regress"])
+def test_pre_interface_matches_reference_golden(backend, oracle, golden_n4, tag):
+    g = golden_n4[tag]
+    ref_models = _build(oracle.KPCN, oracle.PathNet, 39, True, 3)
+    models = _build(backend.KPCN, backend.PathNet, 39, True, 3)
+    for k in models:
+        models[k].load_state_dict(ref_models[k].state_dict())
+        models[k].cuda()
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    before = {k: [p.detach().clone() for p in m.parameters()] for k, m in models.items()}
+    itf = backend.itf.KPCNPreInterface(models, optims, _loss_funcs(backend, True), types.SimpleNamespace(model_name="t"),
+                                       manif_learn=g["manif_learn"], w_manif=0.1)
+    batch = to_cuda(make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=True))
+    itf.to_train_mode()
+    itf.preprocess(batch)
+    torch.manual_seed(g["perm_seed"])
+    itf.train_batch(batch)
+    _check_step_vs_golden(models, itf, g)
+    # the frozen side is bit-for-bit untouched
+    frozen = ["dncnn"] if g["manif_learn"] else ["backbone_diffuse", "backbone_specular"]
+    for k in frozen:
+        assert all(torch.equal(a, b) for a, b in zip(before[k], models[k].parameters())), k

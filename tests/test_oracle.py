@@ -124,3 +124,58 @@ def test_crop_like_matches_reference_rule(oracle):
     assert torch.equal(oracle.modules.crop_like(x, t), x[..., 18:110, 18:110])
     t = torch.zeros(1, 1, 91, 90)  # odd deltas: crop = delta//2, crop2 = delta - crop
     assert torch.equal(oracle.modules.crop_like(x, t), x[..., 18:109, 19:109])
+
+
+# ---- KPCNRefInterface / KPCNPreInterface restatements vs the reference's own classes ----
+@pytest.fixture(scope="module")
+def golden_n4():
+    import os
+    from tests.conftest import ROOT
+    return torch.load(os.path.join(ROOT, "tests", "golden", "ref_golden_n4.pt"), weights_only=False)
+
+
+def _check_models(models, g, grads_of):
+    for name, m in models.items():
+        sums = torch.stack([p.detach().double().sum() for p in m.parameters()])
+        _close(sums, g["param_sums"][name], rtol=1e-5, atol=1e-5)
+        if name in grads_of:
+            gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()])
+            _close(gs, g["grad_abs_sums"][name], rtol=1e-3, atol=1e-6)
+
+
+def test_ref_interface_step_matches_reference(golden_n4, oracle):
+    g = golden_n4["ref"]
+    torch.manual_seed(0)
+    models = {"dncnn": oracle.KPCN(g["n_in"])}
+    optims = {"optim_dncnn": torch.optim.Adam(models["dncnn"].parameters(), lr=1e-4)}
+    batch = make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=False)
+    models["dncnn"].train()
+    loss, _, _ = oracle.ref.kpcn_ref_train_step(models, optims, batch)
+    assert set("m_" + k for k in loss) == set(g["losses"])
+    for k, v in loss.items():
+        _close(v, g["losses"]["m_" + k], rtol=1e-4, atol=1e-7)
+    _check_models(models, g, ("dncnn",))
+    models["dncnn"].eval()
+    rad, pb, relmse = oracle.ref.kpcn_validate(models, oracle.ref.kpcn_ref_batch(batch), use_llpm_buf=False)
+    assert pb is None and g["p_buffers_none"]
+    _close(rad, g["val_radiance"], rtol=1e-4, atol=1e-6)
+    _close(relmse, g["m_val"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["pre_manifold", "pre_regress"])
+def test_pre_interface_step_matches_reference(golden_n4, oracle, tag):
+    g = golden_n4[tag]
+    torch.manual_seed(0)
+    models = {"dncnn": oracle.KPCN(39), "backbone_diffuse": oracle.PathNet(ic=36, outc=3),
+              "backbone_specular": oracle.PathNet(ic=36, outc=3)}
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+    batch = make_batch(batch=2, spp=2, size=40, seed=g["data_seed"], paths=True)
+    for k, m in models.items():
+        m.train(g["training"][k])
+    torch.manual_seed(g["perm_seed"])
+    loss = oracle.ref.kpcn_pre_train_step(models, optims, batch, manif_learn=g["manif_learn"], w_manif=0.1)
+    assert set("m_" + k for k in loss) == set(g["losses"])
+    for k, v in loss.items():
+        _close(v, g["losses"]["m_" + k], rtol=1e-4, atol=1e-7)
+    # parameters of the frozen models must not move; gradients are compared where the reference has them
+    _check_models(models, g, [n for n in models if float(g["grad_abs_sums"][n].min()) >= 0])

@@ -299,3 +299,133 @@ class KPCNInterface(BaseInterface):
             print("")
             return -1.0
         return self.m_losses["m_val"].item() / (norm * 2)
+
+
+_BATCH_KEYS = ("target_total", "target_diffuse", "target_specular", "kpcn_diffuse_buffer", "kpcn_specular_buffer",
+               "kpcn_albedo")
+
+
+class KPCNRefInterface(KPCNInterface):
+    """Upper-bound ablation of /root/reference/support/interfaces.py:526-585: the KPCN inputs are concatenated
+    with the reference images themselves (34 + 3 channels), no path embedding, no manifold loss.  Same kernels
+    as KPCNInterface; only the batch wiring differs."""
+
+    def __init__(self, models, optims, loss_funcs, args, visual=False, use_llpm_buf=False, manif_learn=False,
+                 w_manif=0.1, train_branches=True):
+        assert not use_llpm_buf
+        assert not manif_learn
+        super().__init__(models, optims, loss_funcs, args, visual, use_llpm_buf, manif_learn, w_manif, train_branches)
+
+    def __str__(self):
+        return "KPCNRefInterface"
+
+    @staticmethod
+    def _with_targets(batch):
+        new = {k: batch[k] for k in _BATCH_KEYS}
+        for name in ("diffuse", "specular"):
+            new["kpcn_%s_in" % name] = torch.cat([batch["kpcn_%s_in" % name], batch["target_" + name]], 1)
+        return new
+
+    def train_batch(self, batch):
+        batch = self._with_targets(batch)
+        self.models["dncnn"].zero_grad()
+        out = self._regress_forward(batch)
+        loss_dict = self._backward(batch, out, None)
+        self._logging(loss_dict)
+        self._optimization()
+
+    def validate_batch(self, batch):
+        batch = self._with_targets(batch)
+        out = self._regress_forward(batch)
+        tgt_total = crop_like(batch["target_total"], out["radiance"])
+        l_total = self.loss_funcs["l_test"](out["radiance"], tgt_total)
+        if self.m_losses["m_val"].device != l_total.device:
+            self.m_losses["m_val"] = self.m_losses["m_val"].to(l_total.device)
+        self.m_losses["m_val"] += l_total.detach()
+        return out["radiance"], None
+
+
+class KPCNPreInterface(KPCNInterface):
+    """Two-stage training of /root/reference/support/interfaces.py:588-750.
+    manif_learn=True : pre-train the two path-embedding networks alone on the manifold loss (UNcropped p-buffers
+                       and targets, :686-699); the KPCN is in eval mode and never runs.
+    manif_learn=False: train the KPCN on [inputs | mean_S(p) | var_S(p)] with the embedding networks frozen in
+                       eval mode: they run forward, nothing is propagated into their parameters' optimisers
+                       (only `optim_dncnn` steps, only `dncnn` is clipped, :722-750)."""
+
+    def __init__(self, models, optims, loss_funcs, args, visual=False, manif_learn=False, w_manif=0.1,
+                 train_branches=True):
+        super().__init__(models, optims, loss_funcs, args, visual, True, manif_learn, w_manif, train_branches)
+        # the fused clip+Adam kernel covers every model of the interface; this one updates a subset
+        self.fused_optim = False
+
+    def __str__(self):
+        return "KPCNPreInterface"
+
+    def _trained(self, model_name):
+        return ("backbone" in model_name) if self.manif_learn else ("dncnn" in model_name)
+
+    def to_train_mode(self):
+        for name, model in self.models.items():
+            if "dncnn" in name or "backbone" in name:
+                model.train(self._trained(name))
+            assert "optim_" + name in self.optims, "`optim_%s`: an optimization algorithm is not defined." % name
+
+    def train_batch(self, batch):
+        self.models["backbone_diffuse"].zero_grad()
+        self.models["backbone_specular"].zero_grad()
+        if self.manif_learn:
+            p_buffers = self._manifold_forward(batch)
+            if self.iters % 1000 == 1:
+                self._dump_pbuffers(p_buffers)
+            loss_dict = self._backward(batch, None, p_buffers)
+        else:
+            self.models["dncnn"].zero_grad()
+            p_buffers = self._manifold_forward(batch)
+            batch = _with_pbuffer(batch, p_buffers)
+            out = self._regress_forward(batch)
+            loss_dict = self._backward(batch, out, None)
+        self._logging(loss_dict)
+        self._optimization()
+
+    def _backward(self, batch, out, p_buffers):
+        assert not out or ("radiance" in out and "diffuse" in out and "specular" in out)
+        losses = {}
+        if self.manif_learn:
+            roots = []
+            for name in ("diffuse", "specular"):
+                l_manif = self.loss_funcs["l_manif"](p_buffers[name], batch["target_" + name]) * self.w_manif
+                losses["l_manif_" + name] = l_manif.detach() / self.w_manif
+                roots.append(l_manif)
+            torch.autograd.backward(roots)   # the two networks share no parameter (:701-702)
+            return losses
+        total, diffuse, specular = out["radiance"], out["diffuse"], out["specular"]
+        tgt_total = crop_like(batch["target_total"], total)
+        if self.train_branches:
+            roots = []
+            for name, pred in (("diffuse", diffuse), ("specular", specular)):
+                loss = self.loss_funcs["l_" + name](pred, crop_like(batch["target_" + name], pred))
+                losses["l_" + name] = loss.detach()
+                roots.append(loss)
+            torch.autograd.backward(roots)
+            with torch.no_grad():
+                losses["l_total"] = self.loss_funcs["l_recon"](total, tgt_total).detach()
+        else:
+            l_total = self.loss_funcs["l_recon"](total, tgt_total)
+            losses["l_total"] = l_total.detach()
+            l_total.backward()
+        return losses
+
+    def _logging(self, loss_dict):
+        self._assert_finite(loss_dict)
+        if self.grad_sync is not None:
+            self.grad_sync({k: m for k, m in self.models.items() if self._trained(k)})
+        for name, model in self.models.items():
+            if self._trained(name):
+                nn.utils.clip_grad_value_(model.parameters(), clip_value=1.0)
+        self._accumulate(loss_dict)
+
+    def _optimization(self):
+        for name in self.models:
+            if self._trained(name):
+                self.optims["optim_" + name].step()
