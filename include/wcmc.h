@@ -95,9 +95,9 @@ int wcmc_pack_weights_batch(const wcmc_pack_desc* host_descs, int n, int dtype, 
  * the layer below it.
  * flags: 0 for production (test knobs: bits 4-5 force m tiles per region, bits 8-15 force the
  * n tile; tuning knobs that give WRONG results, used by tools/conv_bench.py to find the bound:
- * bit 16 weights loaded once, bit 17 halos loaded once, bit 18 epilogue skipped.  Bit 19 (correct
- * results) alternates the M tiles of a region inside a tap so consecutive MMAs hit different
- * accumulators; wcmc_tuning_set("conv_interleave", 1) sets it for every launch).                                                                                  */
+ * bit 16 weights loaded once, bit 17 halos loaded once, bit 18 epilogue skipped.  Launch-shape knobs with
+ * identical results: bit 20 forces / bit 21 forbids the CTA-pair launch (cluster of 2, tcgen05
+ * cta_group::2, M = 256), bit 22 forbids weight stages that carry a whole kernel row of taps).             */
 int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                 const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
                 void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask, int mask_cs,

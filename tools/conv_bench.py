@@ -47,7 +47,8 @@ for name, n, h, w, cin, cout, k, pad in cfgs:
         for label, flags in (("production", 0), ("weights once", 1 << 16), ("halos once", 1 << 17),
                              ("weights+halos once", 3 << 16), ("no epilogue", 1 << 18), ("MMA only", 7 << 16),
                              ("mt=1", 1 << 4), ("mt=1 MMA only", (7 << 16) | (1 << 4)),
-                             ("interleaved tiles", 1 << 19), ("interleaved MMA only", (7 << 16) | (1 << 19))):
+                             ("single CTA", 1 << 21), ("single CTA, tap stages", (1 << 21) | (1 << 22)),
+                             ("pair, tap stages", 1 << 22), ("pair MMA only", (7 << 16))):
             timeit(lambda: lib.conv2d(x, wf, bp, k, pad, act=1, flags=flags), fl, "fwd %-22s %s" % (name, label))
         continue
     if what in ("fwd", "all"):

@@ -1,8 +1,9 @@
 """CTA-pair (cta_group::2) conv launches against the single-CTA launches of the same kernel.
    python tools/pair_check.py [reps]
-For every layer shape: forward and data-gradient with flags bit 20 (pair) and bit 21 (single); the outputs
-must be bit-identical (same MMAs per output element, same K order), then both are timed (CUDA events, L2
-flushed between reps).  Run in its own process: a pipeline bug traps the context (bounded mbarrier waits).
+For every layer shape: forward and data-gradient with flags bit 20 (pair) and bit 21 (single), each with row
+stages (a weight stage = one kernel row of taps) and with bit 22 (one tap per stage); the outputs must be
+bit-identical (same MMAs per output element, same K order), then they are timed (CUDA events, L2 flushed
+between reps).  Run in its own process: a pipeline bug traps the context (bounded mbarrier waits).
 Exit code 1 on any mismatch."""
 import os
 import sys
@@ -48,8 +49,10 @@ cfgs = [("odd regions 3x3 n=1 100->100 @44", 1, 44, 44, 100, 100, 5, 0, False),
         ("unet 384->128 3x3 @64", 8, 64, 64, 384, 128, 3, 1, False),
         ("unet 256->256 3x3 @32", 8, 32, 32, 256, 256, 3, 1, False)]
 bad = 0
+TAPS = 1 << 22
 for il in (0, 1):
-    lib.load().wcmc_tuning_set(b"conv_interleave", il)
+    if il:
+        PAIR, SINGLE = PAIR | TAPS, SINGLE | TAPS
     for name, n, h, w, cin, cout, k, pad, f32 in cfgs:
         ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
         x = lib.nchw_to_nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype=dt)
@@ -66,9 +69,9 @@ for il in (0, 1):
         def dgrad(flags, colsum=None):
             return lib.conv2d(dy, wd, None, k, k - 1 - pad, act=0, mask=x, flags=flags, colsum=colsum)
 
-        a, b = fwd(SINGLE), fwd(PAIR)
+        a, b, base = fwd(SINGLE), fwd(PAIR), fwd((1 << 21) | TAPS)   # base: single CTA, one tap per stage
         torch.cuda.synchronize()
-        ok_f = torch.equal(a, b)
+        ok_f = torch.equal(a, b) and torch.equal(a, base)
         cs_a = torch.zeros(lib.pad16(cin), device="cuda")
         cs_b = torch.zeros(lib.pad16(cin), device="cuda")
         da, db = dgrad(SINGLE, cs_a), dgrad(PAIR, cs_b)
@@ -83,10 +86,9 @@ for il in (0, 1):
                      "ok" if ok_d else "BAD", "ok" if ok_c else "BAD", t_ds * 1e3, t_dp * 1e3), flush=True)
         else:
             t_fs, t_fp = timeit(lambda: fwd(SINGLE)), timeit(lambda: fwd(PAIR))
-            print("%-38s [interleaved] fwd %s dgrad %s/%s  single %7.1f us  pair %7.1f us (%6.1f TF/s)"
+            print("%-38s [tap stages] fwd %s dgrad %s/%s  single %7.1f us  pair %7.1f us (%6.1f TF/s)"
                   % (name, "ok" if ok_f else "BAD", "ok" if ok_d else "BAD", "ok" if ok_c else "BAD", t_fs * 1e3,
                      t_fp * 1e3, fl / t_fp / 1e9), flush=True)
         bad += (not ok_f) + (not ok_d) + (not ok_c)
-lib.load().wcmc_tuning_set(b"conv_interleave", 0)
 print("pair_check: %s" % ("all identical" if bad == 0 else "%d MISMATCHES" % bad))
 sys.exit(1 if bad else 0)

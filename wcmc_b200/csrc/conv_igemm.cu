@@ -42,6 +42,7 @@ struct ConvParams {
     int total_regions, pair_items;   // CTA-pair mode: regions over the batch; (region pair, n tile) work items
     int halo_w, halo_h;
     int plane_stride, b_stride, b_stages, plane_slots;  // shared-memory carve-up
+    int tap_stride;                                      // bytes between the taps of one weight stage
     void* out;
     int out_cs, out_coff, out_dtype;
     int x_dtype, w_dtype;
@@ -63,31 +64,20 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 
 // One tap = MT x NK tcgen05.mma (compile-time counts: no branches between the MMAs, descriptor
 // deltas are immediates).  Executed by the single elected lane.
-// IL = true alternates the M tiles inside a tap (t is the inner loop), so two consecutive MMAs never
-// accumulate into the same TMEM tile (tuning bit 19 of `flags`; measured with tools/conv_bench.py knobs).
 // PAIR = true issues tcgen05.mma.cta_group::2 (M = 256: this CTA's 128 pixels and the peer's).
 template <bool PAIR>
 __device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t accum) {
     if (PAIR) umma_bf16_pair(d, ad, bd, idesc, accum);
     else umma_bf16(d, ad, bd, idesc, accum);
 }
-template <int MT, int NK, bool IL, bool PAIR>
+template <int MT, int NK, bool PAIR>
 __device__ __forceinline__ void issue_tap(uint32_t d_base, uint64_t ad, uint64_t bd, uint32_t idesc,
                                           uint32_t accum) {
-    if (IL) {
 #pragma unroll
-        for (int j = 0; j < NK; ++j) {
+    for (int t = 0; t < MT; ++t) {
 #pragma unroll
-            for (int t = 0; t < MT; ++t)
-                umma_any<PAIR>(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < MT; ++t) {
-#pragma unroll
-            for (int j = 0; j < NK; ++j)
-                umma_any<PAIR>(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
-        }
+        for (int j = 0; j < NK; ++j)
+            umma_any<PAIR>(d_base + t * 128, ad + (64 * t + 2 * j), bd + 2 * j, idesc, j > 0 ? 1u : accum);
     }
 }
 
@@ -98,22 +88,29 @@ struct BRing {
     uint32_t base_lo;   // (address of stage 0) >> 4
     uint32_t stride_lo; // stage stride >> 4
     uint32_t cur_lo;    // (address of the current stage) >> 4
+    uint32_t tap_lo;    // stride between the taps of one stage >> 4
     int stages, idx, phase;
 };
 
-// All taps of one 64-channel chunk.  MT / NK are compile-time so the tap body is branch-free:
-// one mbarrier wait, MT*NK back-to-back tcgen05.mma, one tcgen05.commit.
-template <int MT, int NK, bool IL, bool PAIR>
+// All taps of one 64-channel chunk.  A weight stage carries TPS taps (1, or a whole kernel row: TPS = ksize), so
+// the issuing thread pays one mbarrier wait and one tcgen05.commit per TPS*MT*NK MMAs -- with one tap per stage
+// that fixed cost (~200 clocks of uniform-register traffic around the barrier) is serialised with the 8 MMAs of
+// a tap often enough to matter (tools/mma_probe.cu: the issue rate, not the tensor pipe, sets the pace).
+// MT / NK / TPS are compile-time, the body is branch-free and the descriptor deltas are immediates.
+template <int MT, int NK, bool PAIR, int TPS>
 __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int row_step, uint32_t a_lo,
                                           uint32_t a_hi, uint32_t b_hi, uint32_t lo_fixed, uint32_t d_base,
                                           uint32_t idesc, uint32_t& accum) {
     int kx = 0;
-    for (int tap = 0; tap < taps; ++tap) {
+    for (int tap = 0; tap < taps; tap += TPS) {
         mbar_wait(&br.full[br.idx], br.phase);
         tc_fence_after();
         if (elect_one()) {
-            issue_tap<MT, NK, IL, PAIR>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | a_lo),
-                                        (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | br.cur_lo), idesc, accum);
+#pragma unroll
+            for (int u = 0; u < TPS; ++u)
+                issue_tap<MT, NK, PAIR>(d_base, (static_cast<uint64_t>(a_hi) << 32) | (lo_fixed | (a_lo + 8 * u)),
+                                        (static_cast<uint64_t>(b_hi) << 32) | (lo_fixed | (br.cur_lo + u * br.tap_lo)),
+                                        idesc, u > 0 ? 1u : accum);
             if (PAIR) umma_commit_pair(&br.empty[br.idx], 3);
             else umma_commit(&br.empty[br.idx]);
         }
@@ -121,8 +118,9 @@ __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int ro
         accum = 1;
         br.cur_lo += br.stride_lo;
         if (++br.idx == br.stages) { br.idx = 0; br.phase ^= 1; br.cur_lo = br.base_lo; }
-        a_lo += 8;                                   // next tap: one halo pixel (128 B) to the right ...
-        if (++kx == ksize) { kx = 0; a_lo += row_step; }  // ... or down to the next halo row
+        a_lo += 8 * TPS;                                // next taps: TPS halo pixels (128 B each) to the right ...
+        kx += TPS;
+        if (kx == ksize) { kx = 0; a_lo += row_step; }  // ... or down to the next halo row
     }
 }
 
@@ -152,7 +150,7 @@ __device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int r
     return it;
 }
 
-template <bool PAIR>
+template <bool PAIR, int TPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                   const ConvParams p) {
@@ -253,19 +251,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             for (int item = item0; item < n_items; item += item_step) {
                 const int n0 = (item % p.n_tiles) * p.nt;
                 for (int c = 0; c < p.nch; ++c) {
-                    for (int tap = 0; tap < taps; ++tap) {
+                    for (int tap = 0; tap < taps; tap += TPS) {   // one stage = TPS taps, one box each
                         mbar_wait(&b_empty[bs], ph ^ 1);
+                        uint8_t* dst = bst + bs * p.b_stride;
                         if (dry && loaded >= kBStages) {
                             if (rank == 0) mbar_arrive(&b_full[bs]);
                         } else if (PAIR) {
                             // this CTA's half of the n tile (the box of tmw is nt/2 rows tall in pair mode)
-                            if (rank == 0) mbar_expect_tx(&b_full[bs], b_bytes);
-                            tma_load_3d_pair(bst + bs * p.b_stride, &tmw, mapa_u32(smem_u32(&b_full[bs]), 0), c * 64,
-                                             tap, n0 + rank * (p.nt >> 1));
+                            if (rank == 0) mbar_expect_tx(&b_full[bs], TPS * b_bytes);
+                            const uint32_t bar = mapa_u32(smem_u32(&b_full[bs]), 0);
+#pragma unroll
+                            for (int u = 0; u < TPS; ++u)
+                                tma_load_3d_pair(dst + u * p.tap_stride, &tmw, bar, c * 64, tap + u,
+                                                 n0 + rank * (p.nt >> 1));
                             ++loaded;
                         } else {
-                            mbar_expect_tx(&b_full[bs], b_bytes);
-                            tma_load_3d(bst + bs * p.b_stride, &tmw, &b_full[bs], c * 64, tap, n0);
+                            mbar_expect_tx(&b_full[bs], TPS * b_bytes);
+#pragma unroll
+                            for (int u = 0; u < TPS; ++u)
+                                tma_load_3d(dst + u * p.tap_stride, &tmw, &b_full[bs], c * 64, tap + u, n0);
                             ++loaded;
                         }
                         if (++bs == kBStages) { bs = 0; ph ^= 1; }
@@ -291,13 +295,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const uint32_t lo_fixed = 1u << 16;  // LBO field (16 B >> 4) sits in the low word
             const int row_step = (p.halo_w - p.ksize) * 8;
             const int ksize = p.ksize, nch = p.nch, cin_p = p.cin_p, mt = p.mt;
-            const bool interleave = (p.flags & (1 << 19)) != 0;
             const uint32_t plane0_lo = smem_u32(planes) >> 4;
             const uint32_t plane_stride_lo = static_cast<uint32_t>(p.plane_stride) >> 4;
             BRing br;
             br.full = b_full; br.empty = b_empty;
             br.base_lo = smem_u32(bst) >> 4; br.stride_lo = static_cast<uint32_t>(p.b_stride) >> 4;
-            br.cur_lo = br.base_lo; br.stages = p.b_stages; br.idx = 0; br.phase = 0;
+            br.cur_lo = br.base_lo; br.tap_lo = static_cast<uint32_t>(p.tap_stride) >> 4;
+            br.stages = p.b_stages; br.idx = 0; br.phase = 0;
             int ps = 0, pph = 0, it = 0;
             for (int item = item0; item < n_items; item += item_step, ++it) {
                 const int buf = it & 1;
@@ -312,13 +316,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     const uint32_t a_lo = plane0_lo + ps * plane_stride_lo;
                     int nk = (cin_p - c * 64) >> 4;
                     if (nk > 4) nk = 4;
-#define WCMC_CHUNK(MT, NK)                                                                                      \
-    do {                                                                                                        \
-        if (MT > 1 && interleave)                                                                               \
-            mma_chunk<MT, NK, true, PAIR>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum);  \
-        else                                                                                                    \
-            mma_chunk<MT, NK, false, PAIR>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum); \
-    } while (0)
+#define WCMC_CHUNK(MT, NK) \
+    mma_chunk<MT, NK, PAIR, TPS>(br, taps, ksize, row_step, a_lo, a_hi, b_hi, lo_fixed, d_base, idesc, accum)
                     switch (mt * 8 + nk) {
                         case 8 + 1: WCMC_CHUNK(1, 1); break;
                         case 8 + 2: WCMC_CHUNK(1, 2); break;
@@ -487,14 +486,44 @@ static int pick_nt(int cout_p) {
     return 128;
 }
 
-// tuning hook: wcmc_tuning_set("conv_interleave", 0 | 1) ORs bit 19 (alternate the M tiles inside a tap) into
-// the flags of every launch
-static int g_conv_interleave = 0;
-int wcmc_conv_set_interleave(int v) { g_conv_interleave = v ? 1 : 0; return 0; }
-// tuning hook: wcmc_tuning_set("conv_pair", 0 | 1): CTA-pair (cta_group::2, M = 256) launches for the k > 1
-// layers that fill the machine (flags bit 20 forces a pair launch, bit 21 forbids it)
-static int g_conv_pair = 0;
+// tuning hooks: wcmc_tuning_set("conv_pair", 0 | 1): CTA-pair (cta_group::2, M = 256) launches for the k > 1
+// layers that fill the machine (flags bit 20 forces a pair launch, bit 21 forbids it);
+// wcmc_tuning_set("conv_row_stages", 0 | 1): a weight stage carries a whole kernel row of taps when at least
+// three such stages fit (flags bit 22 forbids it)
+static int g_conv_pair = 1;
 int wcmc_conv_set_pair(int v) { g_conv_pair = v ? 1 : 0; return 0; }
+static int g_conv_row_stages = 1;
+int wcmc_conv_set_row_stages(int v) { g_conv_row_stages = v ? 1 : 0; return 0; }
+
+template <bool PAIR, int TPS>
+static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams& p, int grid, int smem_bytes,
+                       cudaStream_t stream) {
+    static bool attr_set = false;   // one flag per instantiation
+    if (!attr_set) {
+        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<PAIR, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kConvSmemMax + 1024));
+        attr_set = true;
+    }
+    if (PAIR) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<PAIR, TPS>, tmx, tmw, p));
+        return WCMC_OK;
+    }
+    conv_igemm_kernel<PAIR, TPS><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
+    WCMC_LAUNCH_CHECK();
+    return WCMC_OK;
+}
 
 extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
                            const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
@@ -554,7 +583,7 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.x_dtype = x_dtype; p.w_dtype = w_dtype;
     p.bias = bias; p.act = act;
     p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
-    p.slope = slope; p.flags = flags | (g_conv_interleave ? (1 << 19) : 0);
+    p.slope = slope; p.flags = flags;
     p.colsum = colsum; p.colsum_scale = colsum_scale;
 
     CUtensorMap tmx, tmw;
@@ -578,43 +607,28 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
         if (rc) return rc;
     }
     p.plane_stride = ((p.halo_w * p.halo_h * 128 + 1023) / 1024) * 1024;
-    p.b_stride = (((pair ? p.nt / 2 : p.nt) * 128 + 1023) / 1024) * 1024;
+    p.tap_stride = (((pair ? p.nt / 2 : p.nt) * 128 + 1023) / 1024) * 1024;
     // Two halo slots are enough when a chunk carries k*k taps of MMAs (the next plane loads during a whole
     // chunk); 1x1 convolutions have one tap per region and are HBM-bound: give them a deeper plane ring.
     p.plane_slots = (ksize == 1) ? kMaxPlaneSlots : 2;
-    p.b_stages = (kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride) / p.b_stride;
+    const int b_room = kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride;
+    int tps = 1;
+    if (g_conv_row_stages && !(flags & (1 << 22)) && ksize > 1 && b_room / (ksize * p.tap_stride) >= 3) tps = ksize;
+    p.b_stride = tps * p.tap_stride;
+    p.b_stages = b_room / p.b_stride;
     if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
     if (ksize == 1 && p.b_stages > 4) p.b_stages = 4;
     WCMC_REQUIRE(p.b_stages >= 2, WCMC_ESHAPE, "conv2d: shared memory carve-up failed");
     const int smem_bytes = 1024 + kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kConvSmemMax + 1024));
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kConvSmemMax + 1024));
-        attr_set = true;
-    }
     if (pair) {
         WCMC_REQUIRE(p.nt % 16 == 0, WCMC_ESHAPE, "conv2d: pair launch needs an n tile that is a multiple of 16");
-        int grid = 2 * p.pair_items < (sms & ~1) ? 2 * p.pair_items : (sms & ~1);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kConvThreads);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmx, tmw, p));
-        return WCMC_OK;
+        const int grid = 2 * p.pair_items < (sms & ~1) ? 2 * p.pair_items : (sms & ~1);
+        if (tps == 5) return launch_conv<true, 5>(tmx, tmw, p, grid, smem_bytes, stream);
+        if (tps == 3) return launch_conv<true, 3>(tmx, tmw, p, grid, smem_bytes, stream);
+        return launch_conv<true, 1>(tmx, tmw, p, grid, smem_bytes, stream);
     }
-    int grid = p.total_items < sms ? p.total_items : sms;
-    conv_igemm_kernel<false><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
-    WCMC_LAUNCH_CHECK();
-    return WCMC_OK;
+    const int grid = p.total_items < sms ? p.total_items : sms;
+    if (tps == 5) return launch_conv<false, 5>(tmx, tmw, p, grid, smem_bytes, stream);
+    if (tps == 3) return launch_conv<false, 3>(tmx, tmw, p, grid, smem_bytes, stream);
+    return launch_conv<false, 1>(tmx, tmw, p, grid, smem_bytes, stream);
 }

@@ -84,12 +84,12 @@ int wcmc_encode_tmap(CUtensorMap* map, int dtype, const void* base, int rank, co
 // Tuning hooks for the micro-benchmarks under tools/ (never used by the product path).
 int wcmc_ka_set_tile(int w);         // kernel_apply.cu
 int wcmc_wgrad_set_uniform(int v);   // conv_wgrad.cu
-int wcmc_conv_set_interleave(int v); // conv_igemm.cu
+int wcmc_conv_set_row_stages(int v); // conv_igemm.cu
 int wcmc_conv_set_pair(int v);       // conv_igemm.cu
 extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "ka_tile_w") == 0 && wcmc_ka_set_tile(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_uniform") == 0) return wcmc_wgrad_set_uniform(value);
-    if (name != nullptr && strcmp(name, "conv_interleave") == 0) return wcmc_conv_set_interleave(value);
+    if (name != nullptr && strcmp(name, "conv_row_stages") == 0) return wcmc_conv_set_row_stages(value);
     if (name != nullptr && strcmp(name, "conv_pair") == 0) return wcmc_conv_set_pair(value);
     wcmc_set_error("wcmc_tuning_set: unknown knob or bad value (%s = %d)", name ? name : "(null)", value);
     return WCMC_ESHAPE;
