@@ -561,22 +561,46 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     WCMC_REQUIRE(p.nt % 16 == 0 && p.nt >= 16 && p.nt <= 128, WCMC_ESHAPE, "conv2d: bad n tile %d", p.nt);
     p.n_tiles = (cout_p + p.nt - 1) / p.nt;
     const int sms = wcmc_num_sms();
-    // Two M tiles per region (B streamed once for 256 pixels) unless that leaves SMs idle.
+    // Launch shape.  Single CTA: two M tiles per region (B streamed once for 256 pixels) unless that leaves SMs
+    // idle.  CTA pair (measured, profiles/r01e_pair_check.txt): worth it for the MMA-bound layers that fill the
+    // machine; the 64- and 128-channel 3x3 U-Net layers are epilogue-bound and lose ~2 us to the cluster launch.  With the B operand already halved per CTA, one M
+    // tile per region often wins: less quantisation of the 8-pixel-wide tiles and a fuller last wave, so mt
+    // minimises waves x (mt x MMA clocks per tile + a fixed per-item cost).
+    const int ksteps = (cin_p + 15) / 16;
+    const long mmas_per_tile = static_cast<long>(ksize) * ksize * ksteps;
+    const int ry16 = (Ho + 15) / 16;
     int mt = 2;
     {
-        long items2 = static_cast<long>(N) * ((Wo + 15) / 16) * ((Ho + 15) / 16) * p.n_tiles;
+        long items2 = static_cast<long>(N) * ((Wo + 15) / 16) * ry16 * p.n_tiles;
         if (items2 < 2L * sms) mt = 1;
+    }
+    bool pair = false;
+    if (g_conv_pair && ksize > 1) {
+        // MMA clocks of the single-CTA launch: below ~20k (about 10 us) the kernel is launch / epilogue bound
+        const long items1 = static_cast<long>(N) * ((Wo + 8 * mt - 1) / (8 * mt)) * ry16 * p.n_tiles;
+        const long clk1 = ((items1 + sms - 1) / sms) * mt * mmas_per_tile * (p.nt / 2);
+        pair = items1 >= sms && clk1 >= 20000;
+    }
+    if (flags & (1 << 20)) pair = true;
+    if (flags & (1 << 21)) pair = false;
+    if (pair) {
+        const long tile_clk = mmas_per_tile * (p.nt / 2), fixed_clk = 1000;
+        long best = -1;
+        for (int m = 1; m <= 2; ++m) {
+            const long regions = static_cast<long>(N) * ((Wo + 8 * m - 1) / (8 * m)) * ry16;
+            const long items = ((regions + 1) / 2) * p.n_tiles;
+            const long workers = sms / 2;
+            const long cost = ((items + workers - 1) / workers) * (m * tile_clk + fixed_clk);
+            if (best < 0 || cost < best) { best = cost; mt = m; }
+        }
     }
     if ((flags >> 4) & 3) mt = (flags >> 4) & 3;              // test override: m tiles
     p.mt = mt;
     p.regions_x = (Wo + 8 * mt - 1) / (8 * mt);
-    p.regions_y = (Ho + 15) / 16;
+    p.regions_y = ry16;
     p.total_items = N * p.regions_x * p.regions_y * p.n_tiles;
     p.total_regions = N * p.regions_x * p.regions_y;
     p.pair_items = ((p.total_regions + 1) / 2) * p.n_tiles;
-    bool pair = g_conv_pair && ksize > 1 && p.total_items >= sms;
-    if (flags & (1 << 20)) pair = true;
-    if (flags & (1 << 21)) pair = false;
     p.halo_w = 8 * mt + ksize - 1;
     p.halo_h = 16 + ksize - 1;
     p.out = y; p.out_cs = y_cs; p.out_coff = y_coff; p.out_dtype = y_dtype;
