@@ -566,3 +566,36 @@ def test_pre_interface_matches_reference_golden(backend, oracle, golden_n4, tag)
     frozen = ["dncnn"] if g["manif_learn"] else ["backbone_diffuse", "backbone_specular"]
     for k in frozen:
         assert all(torch.equal(a, b) for a, b in zip(before[k], models[k].parameters())), k
+
+
+def test_tile_protocol_vs_one_pass(backend, oracle):
+    """`wcmc_b200.inference.inference` (the reference's tile protocol, test_models.py:49-101,
+    through KPCNInterface.validate_batch) against the same frame in ONE pass: identical inside the 28-pixel
+    margin `test_models.denoise` crops (:217-219), and the tiled result equals the oracle KPCN tile by tile."""
+    from wcmc_b200 import inference as inf
+    torch.manual_seed(0)
+    ref = oracle.KPCN(34)
+    net = backend.KPCN(34)
+    net.load_state_dict(ref.state_dict())
+    net.cuda()
+    ref.cuda().eval()
+    itf = backend.itf.KPCNInterface({"dncnn": net}, {"optim_dncnn": torch.optim.Adam(net.parameters(), lr=1e-4)},
+                                    _loss_funcs(backend, False), types.SimpleNamespace(model_name="t"))
+    h, w = 192, 256
+    b = make_batch(batch=1, size=0, height=h, width=w, seed=12, paths=False, llpm_channel=False)
+    frame = {k: v[0] for k, v in b.items()}
+    ds = inf.FrameTiles(frame)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False)
+    tiled, pb = inf.inference(itf, loader)
+    assert pb is None and tuple(tiled.shape) == (3, h, w)
+    m_val_tiled = float(itf.m_losses["m_val"])
+    one, _ = inf.inference_one_pass(itf, frame)
+    c = 28
+    assert rel(one[:, c:-c, c:-c], tiled[:, c:-c, c:-c]) < 1e-5
+    # oracle on one tile, stitched region of that tile
+    patch, i0, j0, i1, j1, i, j = ds[4]
+    with torch.no_grad():
+        want = ref({k: v.unsqueeze(0).cuda() for k, v in patch.items()})["radiance"]
+    want = F.pad(want, (18, 18, 18, 18), "replicate")[0]
+    assert rel(tiled[:, i0:i1, j0:j1], want[:, i0 - i:i1 - i, j0 - j:j1 - j]) < TOL_IMG
+    assert m_val_tiled > 0

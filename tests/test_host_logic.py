@@ -73,3 +73,72 @@ def test_allpairs_oracle_vs_brute_force():
     x = 2.0 * torch.cat([e[off], -e[off], torch.zeros(1, dtype=torch.float64)])
     want = (torch.logsumexp(x, 0) - torch.log(torch.tensor(1.0 + 2 * int(off.sum())))) / 2 ** 0.5
     torch.testing.assert_close(ref.allpairs_loss(p, r, mode="lse", chunk=16), want)
+
+
+def _ref_tile_coords(h, w, patch_size=128, pad_size=32):
+    """Line-by-line restatement of /root/reference/support/datasets.py:1277-1296 (test infrastructure)."""
+    stride = patch_size - 2 * pad_size
+    assert (h - 2 * pad_size) % stride == 0 and (w - 2 * pad_size) % stride == 0
+    coords = []
+    for i in range(0, h - 2 * pad_size, stride):
+        for j in range(0, w - 2 * pad_size, stride):
+            i_start = i + pad_size
+            j_start = j + pad_size
+            i_end = i + patch_size - pad_size
+            j_end = j + patch_size - pad_size
+            if i == 0:
+                i_start = 0
+            if j == 0:
+                j_start = 0
+            if i == h - patch_size:
+                i_end = i + patch_size
+            if j == w - patch_size:
+                j_end = j + patch_size
+            coords.append((i_start, j_start, i_end, j_end, i, j))
+    return coords
+
+
+class _CropInterface:
+    """Stand-in for KPCNInterface.validate_batch: 'denoises' by returning the 92x92 centre of the noisy buffer."""
+    use_llpm_buf = False
+
+    def to_eval_mode(self):
+        pass
+
+    def validate_batch(self, batch):
+        return batch["kpcn_diffuse_buffer"][..., 18:-18, 18:-18], None
+
+
+def test_tile_protocol_matches_reference_rule():
+    """wcmc_b200.inference: tile coordinates of FullImageDataset and the stitching of test_models.inference
+    (test_models.py:49-90), driven on CPU with a stand-in interface."""
+    import pytest
+    from wcmc_b200 import inference as inf
+    for h, w in ((128, 128), (192, 256), (256, 320), (704, 1280)):
+        coords = inf.tile_coords(h, w)
+        assert coords == _ref_tile_coords(h, w)
+        cover = torch.zeros(h, w)
+        for i0, j0, i1, j1, _, _ in coords:   # owned regions partition the frame
+            cover[i0:i1, j0:j1] += 1
+        assert bool((cover == 1).all())
+    with pytest.raises(AssertionError):
+        inf.tile_coords(720, 1280)      # (720 - 64) % 64 != 0: the reference cannot tile 720 rows either
+    g = torch.Generator().manual_seed(5)
+    frame = {"kpcn_diffuse_buffer": torch.rand(3, 192, 256, generator=g), "paths": torch.rand(2, 4, 192, 256, generator=g),
+             "note": "kept"}
+    ds = inf.FrameTiles(frame)
+    assert len(ds) == 6 and ds.h == 192 and ds.w == 256 and ds.PATCH_SIZE == 128
+    patch, i0, j0, i1, j1, i, j = ds[4]
+    assert tuple(patch["paths"].shape) == (2, 4, 128, 128) and (i, j) == (64, 64) and patch["note"] == "kept"
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False)
+    rad, pb = inf.inference(_CropInterface(), loader)
+    assert pb is None and tuple(rad.shape) == (3, 192, 256)
+    src = frame["kpcn_diffuse_buffer"]
+    # wherever the owning tile's 92x92 valid centre covers the pixel, the stitched frame is the source
+    assert torch.equal(rad[:, 18:-18, 18:-18], src[:, 18:-18, 18:-18])
+    # the outer 18 pixels come from the replicate padding of the border tiles (test_models.py:66-69)
+    assert torch.equal(rad[:, 0, 0], src[:, 18, 18]) and torch.equal(rad[:, -1, 100], src[:, -19, 100])
+    one, _ = inf.inference_one_pass(_CropInterface(), frame)
+    assert torch.equal(one, rad)
+    np_rad, _ = inf.to_numpy_hwc(rad, None)
+    assert np_rad.shape == (192, 256, 3)

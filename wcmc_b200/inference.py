@@ -37,3 +37,126 @@ def denoise_frame(kpcn, batch, padded=False):
     if not padded:
         batch = pad_frame(batch, (kpcn.depth * 4) // 2)
     return kpcn(batch)
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md §8(f) N2: the reference's tile protocol (FullImageDataset + test_models.inference) and its
+# one-pass equivalent
+# ------------------------------------------------------------------------------------------------
+PATCH_SIZE = 128   # datasets.py:1207
+PAD_SIZE = 32      # datasets.py:1208
+
+
+def tile_coords(h, w, patch_size=PATCH_SIZE, pad_size=PAD_SIZE):
+    """[(i_start, j_start, i_end, j_end, i, j)] exactly as FullImageDataset builds them (datasets.py:1277-1296):
+    tiles of `patch_size` at stride patch_size - 2*pad_size; a tile owns its centre, extended to the frame border
+    for the first / last tile of a row or column."""
+    stride = patch_size - 2 * pad_size
+    assert (h - 2 * pad_size) % stride == 0 and (w - 2 * pad_size) % stride == 0, \
+        "frame %dx%d does not tile with patch %d / pad %d" % (h, w, patch_size, pad_size)
+    coords = []
+    for i in range(0, h - 2 * pad_size, stride):
+        for j in range(0, w - 2 * pad_size, stride):
+            i_start, j_start = (0 if i == 0 else i + pad_size), (0 if j == 0 else j + pad_size)
+            i_end = i + patch_size if i == h - patch_size else i + patch_size - pad_size
+            j_end = j + patch_size if j == w - patch_size else j + patch_size - pad_size
+            coords.append((i_start, j_start, i_end, j_end, i, j))
+    return coords
+
+
+class FrameTiles(torch.utils.data.Dataset):
+    """The item contract of `FullImageDataset.__getitem__` (datasets.py:1417-1421) over an in-memory frame:
+    (patch dict, i_start, j_start, i_end, j_end, i, j); tensors are sliced on their last two dimensions
+    (`sample[k][..., i:i+P, j:j+P]`, :1298-1300).  `frame` holds un-batched tensors: (C,H,W) buffers and
+    (S,C,H,W) paths.  Attributes h, w, PATCH_SIZE, has_hit as test_models.py:52-53, :227 read them."""
+
+    def __init__(self, frame, patch_size=PATCH_SIZE, pad_size=PAD_SIZE, has_hit=None):
+        t = next(v for v in frame.values() if torch.is_tensor(v))
+        self.h, self.w = int(t.shape[-2]), int(t.shape[-1])
+        self.PATCH_SIZE, self.pad_size = patch_size, pad_size
+        self.frame = frame
+        self.coords = tile_coords(self.h, self.w, patch_size, pad_size)
+        self.has_hit = has_hit
+
+    def __len__(self):
+        return len(self.coords)
+
+    def __getitem__(self, idx):
+        i_start, j_start, i_end, j_end, i, j = self.coords[idx]
+        p = self.PATCH_SIZE
+        patch = {k: (v[..., i:i + p, j:j + p] if torch.is_tensor(v) else v) for k, v in self.frame.items()}
+        return patch, i_start, j_start, i_end, j_end, i, j
+
+
+@torch.no_grad()
+def inference(interface, dataloader, spp=None, args=None, device=None):
+    """Drop-in for `test_models.inference` (test_models.py:49-101): runs `interface.validate_batch` tile by tile,
+    replicate-pads each output back to the tile size and stitches the owned region of every tile.
+    Returns (radiance (3,H,W), p-buffers {name: (S,C,H,W)} or tensor or None) as torch tensors on the device
+    (the reference converts to numpy HWC afterwards, :92-99 -- `to_numpy_hwc` does that)."""
+    interface.to_eval_mode()
+    ds = dataloader.dataset
+    H, W, P = ds.h, ds.w, ds.PATCH_SIZE
+    out_rad, out_path = None, None
+    for batch, i_start, j_start, i_end, j_end, i, j in dataloader:
+        if torch.cuda.is_available():   # (host-logic tests drive this loop with a stand-in interface on CPU)
+            batch = {k: (v.cuda(device, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v)
+                     for k, v in batch.items()}
+        out, p_buffers = interface.validate_batch(batch)
+        pad_h, pad_w = P - out.shape[2], P - out.shape[3]
+        if pad_h != 0 and pad_w != 0:
+            out = F.pad(out, (pad_w // 2, pad_w - pad_w // 2, pad_h // 2, pad_h - pad_h // 2), "replicate")
+        if out_rad is None:
+            out_rad = torch.zeros((3, H, W), device=out.device)
+        if p_buffers is not None and out_path is None:
+            if isinstance(p_buffers, dict):
+                out_path = {k: torch.zeros((v.shape[1], v.shape[2], H, W), device=out.device) for k, v in p_buffers.items()}
+            else:
+                out_path = torch.zeros((p_buffers.shape[1], p_buffers.shape[2], H, W), device=out.device)
+        for b in range(out.shape[0]):
+            i0, i1, j0, j1, ti, tj = (int(i_start[b]), int(i_end[b]), int(j_start[b]), int(j_end[b]), int(i[b]), int(j[b]))
+            out_rad[:, i0:i1, j0:j1] = out[b, :, i0 - ti:i1 - ti, j0 - tj:j1 - tj]
+            if isinstance(p_buffers, dict):
+                for k, v in p_buffers.items():
+                    out_path[k][:, :, i0:i1, j0:j1] = v[b, :, :, i0 - ti:i1 - ti, j0 - tj:j1 - tj]
+            elif p_buffers is not None:
+                out_path[:, :, i0:i1, j0:j1] = p_buffers[b, :, :, i0 - ti:i1 - ti, j0 - tj:j1 - tj]
+    return out_rad, out_path
+
+
+def to_numpy_hwc(out_rad, out_path):
+    """The layout `test_models.inference` returns (test_models.py:92-99): radiance (H,W,3), p-buffers (H,W,S,C)."""
+    rad = out_rad.detach().cpu().numpy().transpose([1, 2, 0])
+    if isinstance(out_path, dict):
+        out_path = {k: v.detach().cpu().numpy().transpose([2, 3, 0, 1]) for k, v in out_path.items()}
+    elif torch.is_tensor(out_path):
+        out_path = out_path.detach().cpu().numpy().transpose([2, 3, 0, 1])
+    return rad, out_path
+
+
+@torch.no_grad()
+def inference_one_pass(interface, frame, allow_pathnet=False):
+    """The same frame through `interface.validate_batch` ONCE (batch of one, no tiling): the networks are fully
+    convolutional, so a pixel at least `SHRINK + 10` (= 28, the crop `test_models.denoise` applies, :217-219)
+    pixels away from the frame border sees exactly the inputs it sees in the tile that owns it -- the tiled
+    protocol costs (H-64)/64 x (W-64)/64 tiles x 124.7 GFLOP, this costs the frame's own valid-convolution
+    FLOPs once.  The (H-36, W-36) output is replicate-padded back to (H, W) as the tiles are.
+    That equivalence holds for the KPCN alone: PathNet's U-Net pools and zero-pads, so with `use_llpm_buf` a
+    tile's p-buffers depend on where the tile was cut; the one-pass result is then a (seam-free) different
+    function of the frame and must be asked for explicitly (`allow_pathnet=True`).
+    `frame`: un-batched tensors as for FrameTiles.  Returns (radiance (3,H,W), p-buffers or None)."""
+    assert allow_pathnet or not getattr(interface, "use_llpm_buf", False), \
+        "one-pass inference is exact only without the path-embedding network (see docstring)"
+    interface.to_eval_mode()
+    dev = "cuda" if torch.cuda.is_available() else None
+    batch = {k: (v.unsqueeze(0).to(dev) if torch.is_tensor(v) else v) for k, v in frame.items()}
+    out, p_buffers = interface.validate_batch(batch)
+    h, w = next(v for v in batch.values() if torch.is_tensor(v)).shape[-2:]
+    ph, pw = h - out.shape[2], w - out.shape[3]
+    if ph or pw:
+        out = F.pad(out, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2), "replicate")
+    if isinstance(p_buffers, dict):
+        p_buffers = {k: v[0] for k, v in p_buffers.items()}
+    elif p_buffers is not None:
+        p_buffers = p_buffers[0]
+    return out[0], p_buffers
