@@ -235,6 +235,32 @@ int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff, const void
                            int outc, int outc_p, int dtype, int act1, int act2, float slope, void* h,
                            float* out, int B, int S, int HW, void* stream);
 
+/* ---- K8 / K9: the backward passes of the two MLPs, each ONE tensor-core kernel + a slab reduction
+ * (autograd of networks.py:29-42; replaces the 1x1-conv dgrad / wgrad / bias / activation launches) ----
+ * Gradients between kernels stay 16-bit and loss-scaled: *gscale multiplies the incoming fp32 gradient,
+ * *inv_scale multiplies the fp32 parameter gradients on the way out (either may be NULL = 1).
+ * wcmc_pathnet_bwd_workspace(which): bytes of per-CTA partial slabs, which = 0 (final) / 1 (embed).
+ * K8: g, out (B,S,outc,HW) fp32 (dL/dout and the forward output); emb (B*S*HW, emb_cs) channels [0,64),
+ *     prop (B*HW, prop_cs) channels [0,64), hfin (B*S*HW,128) 16-bit; w1t [128 cin][128 cout],
+ *     w2t [128 cin][outc_p cout] = the data-gradient packing of wcmc_pack_weights.  Outputs: d_emb
+ *     (B*S*HW,64), d_prop (B*HW,64) = sum over spp, 16-bit; dw1 (128,128), db1 (128), dw2 (outc,128),
+ *     db2 (outc) fp32 (torch layout, overwritten).
+ * K9: d_emb as above, d_red (B*HW,64) gradient of the spp mean (NULL = none; the kernel applies 1/S),
+ *     saved activations emb, h2, h1, x16 (64 channels each; x16 zero padded beyond cin), w3t / w2t
+ *     [64 cin][64 cout].  Outputs dw3, dw2 (64,64), dw1 (64,cin), db3, db2, db1 (64) fp32.          */
+size_t wcmc_pathnet_bwd_workspace(int which);
+int wcmc_pathnet_final_bwd(const float* g, const float* out, const float* gscale, const float* inv_scale,
+                           const void* emb, int emb_cs, const void* prop, int prop_cs, const void* hfin,
+                           const void* w1t, const void* w2t, int outc, int outc_p, int dtype, int act1,
+                           int act2, float slope, void* d_emb, void* d_prop, float* dw1, float* db1,
+                           float* dw2, float* db2, int B, int S, int HW, void* workspace,
+                           size_t workspace_bytes, void* stream);
+int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, const float* inv_scale, const void* emb,
+                           int emb_cs, const void* h2, const void* h1, const void* x16, const void* w3t,
+                           const void* w2t, int cin, int dtype, int act1, int act2, int act3, float slope,
+                           float* dw3, float* db3, float* dw2, float* db2, float* dw1, float* db1, int B,
+                           int S, int HW, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K12: clip_grad_value_ + Adam for all parameter tensors in one launch
  * (/root/reference/support/interfaces.py:261 clip, :269-271 three optimiser steps; Adam with torch's
  * defaults as constructed at /root/reference/train_kpcn.py:277) -----------------------------------

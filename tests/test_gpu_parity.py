@@ -599,3 +599,42 @@ def test_tile_protocol_vs_one_pass(backend, oracle):
     want = F.pad(want, (18, 18, 18, 18), "replicate")[0]
     assert rel(tiled[:, i0:i1, j0:j1], want[:, i0 - i:i1 - i, j0 - j:j1 - j]) < TOL_IMG
     assert m_val_tiled > 0
+
+
+@pytest.mark.parametrize("size,batch,spp,outc", [(20, 2, 3, 3), (32, 1, 2, 12), (64, 3, 4, 3)])
+def test_fused_mlp_backward_vs_generic_path(backend, oracle, size, batch, spp, outc):
+    """K8 / K9 (one kernel per MLP backward) against the generic 1x1-conv dgrad / wgrad launches of the same
+    backend and against the fp32 oracle: same gradients for every PathNet parameter.  20x20 = 400 pixels is not a
+    multiple of the 128-row tile (partial tiles), batch 3 x 32 tiles x 2 groups exercises the persistent loop."""
+    from wcmc_b200 import ops
+    torch.manual_seed(0)
+    ref = oracle.PathNet(36, outc=outc).cuda()
+    ours = backend.PathNet(36, outc=outc).cuda()
+    ours.load_state_dict(ref.state_dict())
+    data = to_cuda(make_batch(batch=batch, spp=spp, size=size, seed=6))
+    w = None
+    res = {}
+    saved = ops.FUSED_MLP_BWD
+    try:
+        for mode in (True, False):
+            ops.FUSED_MLP_BWD = mode
+            ours.zero_grad()
+            po = ours(data)
+            if w is None:
+                w = torch.randn_like(po)
+            (po * w).mean().backward()
+            res[mode] = _grads(ours)
+    finally:
+        ops.FUSED_MLP_BWD = saved
+    ref.zero_grad()
+    (ref(data) * w).mean().backward()
+    g_ref = _grads(ref)
+    e_fused, e_generic = _global_rel(res[True], g_ref), _global_rel(res[False], g_ref)
+    print("PathNet grads vs fp32 oracle: fused MLP backward %.2e, generic %.2e" % (e_fused, e_generic))
+    per = {k: rel(res[True][k], res[False][k]) for k in res[True]}
+    worst = sorted(per.items(), key=lambda kv: -kv[1])[:4]
+    print("fused vs generic, worst tensors:", ["%s %.2e" % kv for kv in worst])
+    assert e_fused < max(2e-2, 1.5 * e_generic)
+    # every tensor separately (a wrong bias / small weight block would hide in the global norm)
+    for k, e in per.items():
+        assert e < 5e-2, "%s: fused vs generic rel-L2 %.3e" % (k, e)

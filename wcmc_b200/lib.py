@@ -77,6 +77,11 @@ SIGNATURES = {
                                   c_void_p]),
     "wcmc_pathnet_final_fwd": (c_int, [c_void_p, c_int, c_int] * 2 + [c_void_p] * 4 + [c_int] * 5 + [c_float]
                                + [c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]),
+    "wcmc_pathnet_bwd_workspace": (c_size_t, [c_int]),
+    "wcmc_pathnet_final_bwd": (c_int, [c_void_p] * 4 + [c_void_p, c_int] * 2 + [c_void_p] * 3 + [c_int] * 5 + [c_float]
+                               + [c_void_p] * 6 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "wcmc_pathnet_embed_bwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float]
+                               + [c_void_p] * 6 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
@@ -94,7 +99,7 @@ class WcmcError(RuntimeError):
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
 _KERNELS_PER_CALL = {"conv2d_wgrad": 2, "conv2d_wgrad_k1": 2, "conv2d_wgrad_k3": 2, "conv2d_wgrad_k5": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
-                     "fmse_allpairs_fwd": 3}
+                     "fmse_allpairs_fwd": 3, "pathnet_final_bwd": 2, "pathnet_embed_bwd": 2}
 _pending_wgrad = []  # (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
 
 
@@ -603,6 +608,65 @@ def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc,
          prop.shape[-1], prop_coff, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), outc, outc_p,
          _dt(emb), acts[0], acts[1], float(slope), _p(hfin), out.data_ptr(), b, s, hw, _stream())
     return out
+
+
+# ---- K8/K9: fused PathNet MLP backward passes -------------------------------------------------------
+def pathnet_final_bwd(g, out, gscale, inv_scale, emb, prop, hfin, packed, acts, slope, outc, b, s):
+    """g, out (B,S,outc,H,W) fp32; emb (B*S,H,W,cs>=64) [channels 0..63], prop (B,H,W,cs') [0..63], hfin (B*S,H,W,128)
+    16-bit; packed = [(_, w_dgrad, _)] x 2.  -> (d_emb (B*S,H,W,64), d_prop (B,H,W,64) 16-bit loss-scaled,
+    [dw1, db1, dw2, db2] fp32 in torch layout)."""
+    lib = init(emb.device)
+    bs, h, w, ecs = _h16(emb).shape
+    assert bs == b * s and tuple(_h16(prop).shape[:3]) == (b, h, w) and prop.dtype == emb.dtype
+    assert g.dtype == torch.float32 and g.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    assert tuple(g.shape) == tuple(out.shape) == (b, s, outc, h, w)
+    assert hfin.dtype == emb.dtype and hfin.is_contiguous() and hfin.shape[-1] == 128
+    (_, w1t, _), (_, w2t, _) = packed
+    outc_p = w2t.shape[2]
+    assert tuple(w1t.shape) == (128, 1, 128) and tuple(w2t.shape) == (128, 1, outc_p) and w1t.dtype == emb.dtype
+    dev = emb.device
+    d_emb = torch.empty((bs, h, w, 64), dtype=emb.dtype, device=dev)
+    d_prop = torch.empty((b, h, w, 64), dtype=emb.dtype, device=dev)
+    dw1 = torch.empty((128, 128, 1, 1), dtype=torch.float32, device=dev)
+    db1 = torch.empty((128,), dtype=torch.float32, device=dev)
+    dw2 = torch.empty((outc, 128, 1, 1), dtype=torch.float32, device=dev)
+    db2 = torch.empty((outc,), dtype=torch.float32, device=dev)
+    need = lib.wcmc_pathnet_bwd_workspace(0)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    hw = h * w
+    work = bs * hw * (outc * 8.0 + 256.0 + 128.0 + 128.0) + b * hw * 256.0
+    _run(lib.wcmc_pathnet_final_bwd, "pathnet_final_bwd", work, g.data_ptr(), out.data_ptr(), _p(gscale), _p(inv_scale),
+         emb.data_ptr(), ecs, prop.data_ptr(), prop.shape[-1], hfin.data_ptr(), w1t.data_ptr(), w2t.data_ptr(), outc,
+         outc_p, _dt(emb), acts[0], acts[1], float(slope), d_emb.data_ptr(), d_prop.data_ptr(), dw1.data_ptr(),
+         db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), b, s, hw, ws.data_ptr(), need, _stream())
+    return d_emb, d_prop, [dw1, db1, dw2, db2]
+
+
+def pathnet_embed_bwd(d_emb, d_red, inv_scale, emb, h2, h1, x16, packed, acts, slope, cin, b, s):
+    """d_emb (B*S,H,W,64), d_red (B,H,W,>=64 contiguous 64-channel) or None, saved activations (64 channels each);
+    packed = [(_, w_dgrad, _)] x 3 (layer order 1, 2, 3).  -> [dw1, db1, dw2, db2, dw3, db3] fp32."""
+    lib = init(d_emb.device)
+    bs, h, w, _ = _h16(d_emb).shape
+    assert bs == b * s and d_emb.shape[-1] == 64
+    for t in (h2, h1, x16):
+        assert t.dtype == d_emb.dtype and t.is_contiguous() and tuple(t.shape) == (bs, h, w, 64)
+    assert emb.dtype == d_emb.dtype and emb.is_contiguous() and tuple(emb.shape[:3]) == (bs, h, w)
+    assert d_red is None or (d_red.dtype == d_emb.dtype and d_red.is_contiguous() and tuple(d_red.shape) == (b, h, w, 64))
+    (_, _w1t, _), (_, w2t, _), (_, w3t, _) = packed
+    assert tuple(w2t.shape) == (64, 1, 64) and tuple(w3t.shape) == (64, 1, 64)
+    dev = d_emb.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    dw1, dw2, dw3 = torch.empty((64, cin, 1, 1), **f32), torch.empty((64, 64, 1, 1), **f32), torch.empty((64, 64, 1, 1), **f32)
+    db1, db2, db3 = torch.empty((64,), **f32), torch.empty((64,), **f32), torch.empty((64,), **f32)
+    need = lib.wcmc_pathnet_bwd_workspace(1)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    hw = h * w
+    work = bs * hw * 5 * 128.0 + b * hw * 128.0 * s
+    _run(lib.wcmc_pathnet_embed_bwd, "pathnet_embed_bwd", work, d_emb.data_ptr(), _p(d_red), _p(inv_scale),
+         emb.data_ptr(), emb.shape[-1], h2.data_ptr(), h1.data_ptr(), x16.data_ptr(), w3t.data_ptr(), w2t.data_ptr(), cin,
+         _dt(d_emb), acts[0], acts[1], acts[2], float(slope), dw3.data_ptr(), db3.data_ptr(), dw2.data_ptr(),
+         db2.data_ptr(), dw1.data_ptr(), db1.data_ptr(), b, s, hw, ws.data_ptr(), need, _stream())
+    return [dw1, db1, dw2, db2, dw3, db3]
 
 
 # ---- K12: fused clip + Adam ------------------------------------------------------------------------

@@ -369,6 +369,8 @@ def fused_mlp_ok(spec):
 
 
 FUSED_MLP = os.environ.get("WCMC_FUSED_MLP", "1") != "0"
+# K8 / K9: the backward passes of the two MLPs as one kernel each (0: generic 1x1 conv dgrad / wgrad launches)
+FUSED_MLP_BWD = os.environ.get("WCMC_FUSED_MLP_BWD", "1") != "0"
 
 
 class PathNetFn(torch.autograd.Function):
@@ -387,7 +389,9 @@ class PathNetFn(torch.autograd.Function):
         if FUSED_MLP and fused_mlp_ok(spec):
             # K6: fp32 NCHW paths -> 3-layer MLP -> emb (+ spp mean) in one kernel; K7: [emb | prop] -> out
             px = paths.contiguous().float()
-            both = torch.empty((b * s, h, w, c_emb + c_prop if need else c_emb), dtype=ACT_DTYPE, device=dev)
+            fused_bwd = need and FUSED_MLP_BWD and c_emb == 64 and c_prop == 64
+            both = torch.empty((b * s, h, w, c_emb + c_prop if (need and not fused_bwd) else c_emb), dtype=ACT_DTYPE,
+                               device=dev)
             reduced = torch.empty((b, h, w, c_emb), dtype=ACT_DTYPE, device=dev)
             x16 = h1 = h2 = hfin = None
             if need:
@@ -401,7 +405,13 @@ class PathNetFn(torch.autograd.Function):
             assert prop.c == c_prop
             out = lib.pathnet_final_fwd(both, 0, prop.t, prop.coff, p_fin, [l.act for l in spec.final], LEAKY_SLOPE,
                                         outc, b, s, hfin=hfin)
-            if need:
+            if fused_bwd:
+                # K8 / K9 read emb per sample and prop per pixel: no materialised [emb | prop] tensor at all
+                prop_t = prop.t if (prop.coff == 0 and prop.t.is_contiguous()) else \
+                    prop.t[..., prop.coff:prop.coff + c_prop].contiguous()
+                acts_emb = ("fused", x16, h1, h2, both)
+                acts_fin = ("fused", prop_t, hfin)
+            elif need:
                 # the backward pass (generic wgrad / dgrad kernels) reads [emb | prop] as one 128-channel tensor
                 lib.spp_broadcast(prop.t, b, s, c_prop, 1.0, x_coff=prop.coff, out=both, out_coff=c_emb)
                 acts_emb = [Slice(x16, 0, nf), Slice(h1, 0, c_emb), Slice(h2, 0, c_emb), Slice(both, 0, c_emb)]
@@ -430,6 +440,21 @@ class PathNetFn(torch.autograd.Function):
         acts_emb, p_emb, uctx, acts_fin, p_fin = ctx.saved
         (out,) = ctx.saved_tensors
         last = spec.final[-1]
+        if isinstance(acts_fin, tuple) and acts_fin[0] == "fused":
+            _, prop_t, hfin = acts_fin
+            _, x16, h1, h2, emb = acts_emb
+            g = g.reshape(b, s, outc, h, w).float().contiguous()
+            gs, inv_s = grad_scale(g)
+            d_emb, d_prop, g_fin = lib.pathnet_final_bwd(g, out, gs, inv_s, emb, prop_t, hfin, p_fin,
+                                                         [l.act for l in spec.final], LEAKY_SLOPE, outc, b, s)
+            d_red, g_unet = unet_backward(spec.unet, uctx, Slice(d_prop, 0, c_prop), True, inv_s)
+            dr = d_red.t if (d_red.coff == 0 and d_red.t.shape[-1] == c_emb) else \
+                d_red.t[..., d_red.coff:d_red.coff + c_emb].contiguous()
+            g_emb = lib.pathnet_embed_bwd(d_emb, dr, inv_s, emb, h2, h1, x16, p_emb, [l.act for l in spec.embedding],
+                                          LEAKY_SLOPE, spec.embedding[0].cin, b, s)
+            lib.wgrad_flush()
+            ctx.saved = None
+            return (None, None) + tuple(g_emb) + tuple(g_unet) + tuple(g_fin)
         g = g.reshape(b * s, outc, h, w).float()
         o = out.reshape(b * s, outc, h, w)
         if last.act == 1:
