@@ -11,8 +11,9 @@
 // activation kernels) moves ~2.6 GB + ~1.5 GB per network at B=8, S=8; fused, every saved activation is read
 // exactly once and only d_emb / d_prop are written (0.56 GB + 0.64 GB).
 //
-// Structure.  A CTA is two independent groups of 128 threads (thread <-> sample-pixel row <-> TMEM lane) plus one
-// MMA-issuing warp.  A group owns its own shared-memory tiles and 128 TMEM columns for the data gradients and walks
+// Structure.  A CTA is two independent groups of 256 threads (two threads per sample-pixel row = TMEM lane, each
+// owning one 64-column half of the row: the epilogues are latency chains, so warps, not instructions, are what was
+// missing -- ncu: 9 warps per SM issued one instruction every 14 clocks) plus one MMA-issuing warp.  A group owns its own shared-memory tiles and 128 TMEM columns for the data gradients and walks
 // (pixel tile, image) items, looping over the spp samples of a tile; while one group waits for its TMA loads or runs
 // an epilogue, the other group's MMAs run.  Every tile is a [128 rows][64 channels] 16-bit SWIZZLE_128B tile, which
 // is at once the K-major A operand of the data-gradient MMA  dX[row][cin] = sum_cout dZ[row][cout] W[cout][cin]
@@ -27,7 +28,8 @@
 
 namespace wcmc {
 
-constexpr int kBwdThreads = 288;             // 2 groups x 128 + issuer warp
+constexpr int kBwdThreads = 544;             // 2 groups x 256 + issuer warp
+constexpr int kGroupThreads = 256;
 constexpr int kTile = 128 * 128;             // bytes of a [128][64] 16-bit tile
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {   // byte offset of 16-byte chunk `chunk` of row `row`
@@ -105,7 +107,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
     float* db2_smem = reinterpret_cast<float*>(tmem_ptr + 2);   // [8 warps][32]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = tid >> 7;            // 0, 1, or 2 (issuer warp)
+    const int grp = tid >> 8;            // 0, 1, or 2 (issuer warp)
 
     if (tid == 0) {
         tma_prefetch_desc(&tmh);
@@ -113,7 +115,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
         tma_prefetch_desc(&tmpr);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&sync[g].tma_full, 1);
-            mbar_init(&sync[g].req, 128);
+            mbar_init(&sync[g].req, kGroupThreads);
             mbar_init(&sync[g].done, 1);
         }
         fence_barrier_init();
@@ -131,7 +133,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
         load_rows_swizzled(gbase + 4 * kTile, 0, p.w2t, 128, p.outc_p, 4, tid, kBwdThreads);
         load_rows_swizzled(gbase + kFinGroupBytes + 4 * kTile, 0, p.w2t, 128, p.outc_p, 4, tid, kBwdThreads);
     }
-    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    if (warp == 16) tmem_alloc(tmem_ptr, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -198,7 +200,8 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
         }
     } else {
         // ------------------------------------------ row groups ------------------------------------------
-        const int r = tid & 127;
+        const int r = tid & 127;                 // row of the tile = TMEM lane
+        const int half = (tid >> 7) & 1;         // which 64-column half of the row this thread owns
         uint8_t* base = gbase + grp * kFinGroupBytes;
         uint8_t* h0 = base;
         uint8_t* et = base + 2 * kTile;
@@ -217,10 +220,10 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
             const int b = item / p.tiles, pix0 = (item - b * p.tiles) * 128;
             const int pix = pix0 + r;
             const bool valid = pix < p.HW;
-            float acc[64];
+            float acc[32];   // running sum over spp of this thread's 32 prop-gradient columns
 #pragma unroll
-            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-            if (r == 0) {
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            if (r == 0 && half == 0) {
                 mbar_expect_tx(&sy.tma_full, 4 * kTile);
                 tma_load_3d(pt, &tmpr, &sy.tma_full, 0, pix0, b);
                 tma_load_3d(h0, &tmh, &sy.tma_full, 0, pix0, b * p.S);
@@ -230,7 +233,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
             for (int s = 0; s < p.S; ++s) {
                 const int img = b * p.S + s;
                 // ---- (a) dz2 = scale * g * act2'(out) -> ZW chunks [0, outc_p/8) ----
-                {
+                if (half == 0) {
                     const size_t o = static_cast<size_t>(img) * p.outc * p.HW + pix;
                     float z[OP];
 #pragma unroll
@@ -260,24 +263,25 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                 done_ph ^= 1;
                 tc_fence_after();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[4][16];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld16(tlane + half * 64 + cc * 16, v[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld_wait16(v[cc]);
+                for (int pass = 0; pass < 2; ++pass) {
+                    uint32_t v[2][16];
+                    tmem_ld16(tlane + half * 64 + pass * 32, v[0]);
+                    tmem_ld16(tlane + half * 64 + pass * 32 + 16, v[1]);
+                    tmem_ld_wait16(v[0]);
+                    tmem_ld_wait16(v[1]);
                     uint8_t* tile = h0 + half * kTile;
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) {
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int ch = pass * 4 + c4;
                         uint4* ptr = reinterpret_cast<uint4*>(tile + swz(r, ch));
                         const uint4 hv = *ptr;
                         const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
                         uint32_t o[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int col = (ch & 1) * 8 + 2 * i;
-                            const float a = __uint_as_float(v[ch >> 1][col]) * dact(hw[i] & 0xFFFFu, p.act1, p.slope);
-                            const float c2 = __uint_as_float(v[ch >> 1][col + 1]) * dact(hw[i] >> 16, p.act1, p.slope);
+                            const int col = (c4 & 1) * 8 + 2 * i;
+                            const float a = __uint_as_float(v[c4 >> 1][col]) * dact(hw[i] & 0xFFFFu, p.act1, p.slope);
+                            const float c2 = __uint_as_float(v[c4 >> 1][col + 1]) * dact(hw[i] >> 16, p.act1, p.slope);
                             o[i] = pack_h2(a, c2, dt);
                         }
                         *ptr = make_uint4(o[0], o[1], o[2], o[3]);
@@ -290,52 +294,57 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                 mbar_wait(&sy.done, done_ph);
                 done_ph ^= 1;
                 tc_fence_after();
-                if (r == 0 && s + 1 < p.S) {   // the h / emb tiles are free: next sample's
+                if (r == 0 && half == 0 && s + 1 < p.S) {   // the h / emb tiles are free: next sample's
                     mbar_expect_tx(&sy.tma_full, 3 * kTile);
                     tma_load_3d(h0, &tmh, &sy.tma_full, 0, pix0, img + 1);
                     tma_load_3d(h0 + kTile, &tmh, &sy.tma_full, 64, pix0, img + 1);
                     tma_load_3d(et, &tme, &sy.tma_full, 0, pix0, img + 1);
                 }
                 {
-                    uint32_t v[4][16];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld16(tlane + cc * 16, v[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld_wait16(v[cc]);
+                    // d_emb: this thread's 32 of the row's 64 channels
+                    uint32_t v[2][16];
+                    tmem_ld16(tlane + half * 32, v[0]);
+                    tmem_ld16(tlane + half * 32 + 16, v[1]);
+                    tmem_ld_wait16(v[0]);
+                    tmem_ld_wait16(v[1]);
                     if (valid) {
                         uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.d_emb) +
-                                                              (static_cast<size_t>(img) * p.HW + pix) * 128);
+                                                              (static_cast<size_t>(img) * p.HW + pix) * 128) + half * 4;
 #pragma unroll
-                        for (int ch = 0; ch < 8; ++ch) {
-                            const uint32_t* q = v[ch >> 1] + (ch & 1) * 8;
-                            dst[ch] = make_uint4(pack_h2(__uint_as_float(q[0]), __uint_as_float(q[1]), dt),
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const uint32_t* q = v[c4 >> 1] + (c4 & 1) * 8;
+                            dst[c4] = make_uint4(pack_h2(__uint_as_float(q[0]), __uint_as_float(q[1]), dt),
                                                  pack_h2(__uint_as_float(q[2]), __uint_as_float(q[3]), dt),
                                                  pack_h2(__uint_as_float(q[4]), __uint_as_float(q[5]), dt),
                                                  pack_h2(__uint_as_float(q[6]), __uint_as_float(q[7]), dt));
                         }
                     }
+                    // prop half of dBoth: summed over the samples (networks.py:39 repeats prop for every sample)
+                    tmem_ld16(tlane + 64 + half * 32, v[0]);
+                    tmem_ld16(tlane + 64 + half * 32 + 16, v[1]);
+                    tmem_ld_wait16(v[0]);
+                    tmem_ld_wait16(v[1]);
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld16(tlane + 64 + cc * 16, v[cc]);
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) tmem_ld_wait16(v[cc]);
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) acc[i] += __uint_as_float(v[i >> 4][i & 15]);
+                    for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i >> 4][i & 15]);
                 }
                 tc_fence_before();
             }
             if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.d_prop) + (static_cast<size_t>(b) * p.HW + pix) * 128);
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.d_prop) + (static_cast<size_t>(b) * p.HW + pix) * 128) +
+                             half * 4;
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch)
-                    dst[ch] = make_uint4(pack_h2(acc[8 * ch], acc[8 * ch + 1], dt), pack_h2(acc[8 * ch + 2], acc[8 * ch + 3], dt),
-                                         pack_h2(acc[8 * ch + 4], acc[8 * ch + 5], dt), pack_h2(acc[8 * ch + 6], acc[8 * ch + 7], dt));
+                for (int c4 = 0; c4 < 4; ++c4)
+                    dst[c4] = make_uint4(pack_h2(acc[8 * c4], acc[8 * c4 + 1], dt), pack_h2(acc[8 * c4 + 2], acc[8 * c4 + 3], dt),
+                                         pack_h2(acc[8 * c4 + 4], acc[8 * c4 + 5], dt), pack_h2(acc[8 * c4 + 6], acc[8 * c4 + 7], dt));
             }
         }
-        // db2: warp sums -> shared
+        // db2: warp sums of the half-0 warps (4 per group) -> shared
+        if (half == 0) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float v = c < OP ? warp_sum(db2[c < OP ? c : 0]) : 0.f;
-            if (lane == 0) db2_smem[warp * 32 + c] = v;
+            for (int c = 0; c < 32; ++c) {
+                const float v = c < OP ? warp_sum(db2[c < OP ? c : 0]) : 0.f;
+                if (lane == 0) db2_smem[(grp * 4 + (warp & 3)) * 32 + c] = v;
+            }
         }
     }
     // ---------------------------------------------- slab ----------------------------------------------
@@ -344,7 +353,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
     tc_fence_after();
     float* slab = p.partial + static_cast<size_t>(blockIdx.x) * kFinSlab;
     const bool any = blockIdx.x * 2 < p.items;   // a CTA without items never initialised its accumulators
-    if (grp == 0) {
+    if (tid < 128) {
         // lanes = cout of layer 1 (row tid), columns [256, 384) = cin
         const uint32_t tl = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + kColW1;
         for (int cc = 0; cc < 8; ++cc) {
@@ -358,7 +367,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                                          __uint_as_float(v[4 * i + 3]))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else if (grp == 1) {
+    } else if (tid >= 256 && tid < 384) {
         const int row = tid & 127;
         const uint32_t tl = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         uint32_t v[16];
@@ -381,7 +390,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================================================================
@@ -416,7 +425,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sync + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = tid >> 7;
+    const int grp = tid >> 8;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmde);
@@ -426,7 +435,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
         tma_prefetch_desc(&tmx);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&sync[g].tma_full, 1);
-            mbar_init(&sync[g].req, 128);
+            mbar_init(&sync[g].req, kGroupThreads);
             mbar_init(&sync[g].done, 1);
         }
         fence_barrier_init();
@@ -437,7 +446,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
         load_rows_swizzled(w3t, 0, p.w3t, 64, 64, 0, tid, kBwdThreads);
         load_rows_swizzled(w2t, 0, p.w2t, 64, 64, 0, tid, kBwdThreads);
     }
-    if (warp == 8) tmem_alloc(tmem_ptr, 512);
+    if (warp == 16) tmem_alloc(tmem_ptr, 512);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -499,7 +508,8 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
             }
         }
     } else {
-        const int r = tid & 127;
+        const int r = tid & 127;                 // row of the tile = TMEM lane
+        const int half = (tid >> 7) & 1;         // this thread's 32-column half of the row
         uint8_t* base = gbase + grp * kEmbGroupBytes;
         uint8_t* de = base;
         uint8_t* em = base + kTile;
@@ -522,21 +532,22 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
         // dz = dH * act'(saved output), read from TMEM columns [0,64) of the group, written to tile `dst` (row r);
         // `saved` is the tile that holds the layer's post-activation output
         auto mask_epilogue = [&](const uint8_t* saved, uint8_t* dst, int act) {
-            uint32_t v[4][16];
+            uint32_t v[2][16];
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) tmem_ld16(tlane + cc * 16, v[cc]);
+            for (int cc = 0; cc < 2; ++cc) tmem_ld16(tlane + half * 32 + cc * 16, v[cc]);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) tmem_ld_wait16(v[cc]);
+            for (int cc = 0; cc < 2; ++cc) tmem_ld_wait16(v[cc]);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int ch = half * 4 + c4;
                 const uint4 hv = *reinterpret_cast<const uint4*>(saved + swz(r, ch));
                 const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
                 uint32_t o[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int col = (ch & 1) * 8 + 2 * i;
-                    o[i] = pack_h2(__uint_as_float(v[ch >> 1][col]) * dact(hw[i] & 0xFFFFu, act, p.slope),
-                                   __uint_as_float(v[ch >> 1][col + 1]) * dact(hw[i] >> 16, act, p.slope), dt);
+                    const int col = (c4 & 1) * 8 + 2 * i;
+                    o[i] = pack_h2(__uint_as_float(v[c4 >> 1][col]) * dact(hw[i] & 0xFFFFu, act, p.slope),
+                                   __uint_as_float(v[c4 >> 1][col + 1]) * dact(hw[i] >> 16, act, p.slope), dt);
                 }
                 *reinterpret_cast<uint4*>(dst + swz(r, ch)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -546,7 +557,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
             const int b = item / p.tiles, pix0 = (item - b * p.tiles) * 128;
             const int pix = pix0 + r;
             const bool valid = pix < p.HW;
-            if (r == 0) load_tiles(pix0, b * p.S);
+            if (r == 0 && half == 0) load_tiles(pix0, b * p.S);
             for (int s = 0; s < p.S; ++s) {
                 const int img = b * p.S + s;
                 // ---- (a) dz3 = (d_emb + d_red / S) * act3'(emb), in place over the d_emb tile ----
@@ -556,7 +567,8 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                     const uint4* dr = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.d_red) +
                                                                      (static_cast<size_t>(b) * p.HW + pix) * 128);
 #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) {
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const int ch = half * 4 + c4;
                         uint4* ptr = reinterpret_cast<uint4*>(de + swz(r, ch));
                         const uint4 dv = *ptr;
                         const uint4 ev = *reinterpret_cast<const uint4*>(em + swz(r, ch));
@@ -596,7 +608,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                 // ---- (g) layer-1 weight gradient retired: all five tiles are free ----
                 mbar_wait(&sy.done, done_ph);
                 done_ph ^= 1;
-                if (r == 0 && s + 1 < p.S) load_tiles(pix0, img + 1);
+                if (r == 0 && half == 0 && s + 1 < p.S) load_tiles(pix0, img + 1);
             }
         }
     }
@@ -625,7 +637,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // Sums the per-CTA slabs in a fixed order, multiplies by *scale (1 / loss scale) and scatters into up to 8 output
