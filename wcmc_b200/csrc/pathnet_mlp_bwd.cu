@@ -156,44 +156,62 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
             const uint32_t id_dh = make_idesc_f16(128, 128, 0, 0, p.dtype, p.dtype);      // K-major x K-major
             const uint32_t id_w = make_idesc_f16(128, 128, 1, 1, p.dtype, p.dtype);       // MN-major x MN-major
             const uint32_t id_w64 = make_idesc_f16(128, 64, 1, 1, p.dtype, p.dtype);
-            const uint32_t w1a = smem_u32(w1t), onesa = smem_u32(ones);
+            // Every descriptor is built ONCE: this single thread feeds the tensor pipe for both groups, and with
+            // descriptors rebuilt per MMA it was the bottleneck of the kernel (one warp retires an instruction every
+            // ~14 clocks; ~45 instructions per MMA x 33 MMAs per sample tile = 12 us).
+            const uint64_t w1k0 = kdesc(smem_u32(w1t)), w1k1 = kdesc(smem_u32(w1t) + kTile);
+            const uint64_t ones_mn = mndesc(smem_u32(ones), kTile);
+            const int k2 = p.outc_p >> 4;
             bool first_w2 = true, first_w1 = true;
             long long last = clock64();
-            while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
-                for (int g = 0; g < 2; ++g) {
-                    if (st.step[g] >= st.total[g] || !mbar_try_wait(&sync[g].req, st.req_ph[g])) continue;
-                    st.req_ph[g] ^= 1;
-                    last = clock64();
-                    const uint32_t base = smem_u32(gbase + g * kFinGroupBytes);
-                    const uint32_t ha = base, ea = base + 2 * kTile, zwa = base + 4 * kTile;
-                    const uint32_t dcol = tmem + g * 128;
-                    if ((st.step[g] & 1) == 0) {
-                        // R1: dH = Z2 . W2 (K = outc_p);  dW2^T += H^T . Z2  (K = 128 rows)
-                        mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
-                        st.tma_ph[g] ^= 1;
-                        tc_fence_after();
-                        for (int k = 0; k < (p.outc_p >> 4); ++k)
-                            umma_bf16(dcol, kdesc(zwa) + 2 * k, kdesc(zwa) + 4 + 2 * k, id_dh, k > 0 ? 1u : 0u);
-                        for (int j = 0; j < 8; ++j)
-                            umma_bf16(tmem + kColW2, mndesc(ha, kTile) + j * 128, mndesc(zwa, kTile) + j * 128, id_w64,
-                                      (first_w2 && j == 0) ? 0u : 1u);
-                        first_w2 = false;
-                    } else {
-                        // R2: dBoth = Z1 . W1 (K = 128 channels);  dW1 += Z1^T . [emb | prop];  db1 += Z1^T . 1
-                        tc_fence_after();
-                        for (int c = 0; c < 2; ++c)
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(dcol, kdesc(ha + c * kTile) + 2 * k, kdesc(w1a + c * kTile) + 2 * k, id_dh,
-                                          (c | k) ? 1u : 0u);
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t acc = (first_w1 && j == 0) ? 0u : 1u;
-                            umma_bf16(tmem + kColW1, mndesc(ha, kTile) + j * 128, mndesc(ea, kTile) + j * 128, id_w, acc);
-                            umma_bf16(tmem + kColB1, mndesc(ha, kTile) + j * 128, mndesc(onesa, kTile) + j * 128, id_w64, acc);
-                        }
-                        first_w1 = false;
+            auto serve = [&](const int g) {
+                const uint32_t base = smem_u32(gbase + g * kFinGroupBytes);
+                const uint64_t hk0 = kdesc(base), hk1 = kdesc(base + kTile), zk = kdesc(base + 4 * kTile);
+                const uint64_t h_mn = mndesc(base, kTile), e_mn = mndesc(base + 2 * kTile, kTile),
+                               z_mn = mndesc(base + 4 * kTile, kTile);
+                const uint32_t dcol = tmem + g * 128;
+                if ((st.step[g] & 1) == 0) {
+                    // R1: dH = Z2 . W2 (K = outc_p);  dW2^T += H^T . Z2  (K = 128 rows)
+                    mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
+                    st.tma_ph[g] ^= 1;
+                    tc_fence_after();
+                    umma_bf16(dcol, zk, zk + 4, id_dh, 0u);
+                    if (k2 > 1) umma_bf16(dcol, zk + 2, zk + 6, id_dh, 1u);
+                    umma_bf16(tmem + kColW2, h_mn, z_mn, id_w64, first_w2 ? 0u : 1u);
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) umma_bf16(tmem + kColW2, h_mn + j * 128, z_mn + j * 128, id_w64, 1u);
+                    first_w2 = false;
+                } else {
+                    // R2: dBoth = Z1 . W1 (K = 128 channels);  dW1 += Z1^T . [emb | prop];  db1 += Z1^T . 1
+                    tc_fence_after();
+                    umma_bf16(dcol, hk0, w1k0, id_dh, 0u);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) umma_bf16(dcol, hk0 + 2 * k, w1k0 + 2 * k, id_dh, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(dcol, hk1 + 2 * k, w1k1 + 2 * k, id_dh, 1u);
+                    const uint32_t acc0 = first_w1 ? 0u : 1u;
+                    umma_bf16(tmem + kColW1, h_mn, e_mn, id_w, acc0);
+                    umma_bf16(tmem + kColB1, h_mn, ones_mn, id_w64, acc0);
+#pragma unroll
+                    for (int j = 1; j < 8; ++j) {
+                        umma_bf16(tmem + kColW1, h_mn + j * 128, e_mn + j * 128, id_w, 1u);
+                        umma_bf16(tmem + kColB1, h_mn + j * 128, ones_mn + j * 128, id_w64, 1u);
                     }
-                    umma_commit(&sync[g].done);
-                    ++st.step[g];
+                    first_w1 = false;
+                }
+                umma_commit(&sync[g].done);
+                ++st.step[g];
+            };
+            while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
+                if (st.step[0] < st.total[0] && mbar_try_wait(&sync[0].req, st.req_ph[0])) {
+                    st.req_ph[0] ^= 1;
+                    last = clock64();
+                    serve(0);
+                }
+                if (st.step[1] < st.total[1] && mbar_try_wait(&sync[1].req, st.req_ph[1])) {
+                    st.req_ph[1] ^= 1;
+                    last = clock64();
+                    serve(1);
                 }
                 if (clock64() - last > 8000000000LL) issuer_trap("pathnet_final_bwd");
             }
@@ -466,43 +484,63 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
             }
             const uint32_t id_dh = make_idesc_f16(128, 64, 0, 0, p.dtype, p.dtype);
             const uint32_t id_w = make_idesc_f16(128, 64, 1, 1, p.dtype, p.dtype);
-            const uint32_t onesa = smem_u32(ones);
+            const uint64_t ones_mn = mndesc(smem_u32(ones), kTile);
+            const uint64_t w3k = kdesc(smem_u32(w3t)), w2k = kdesc(smem_u32(w2t));
             bool first[3] = {true, true, true};
             int kind[2] = {0, 0};
             long long last = clock64();
-            while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
-                for (int g = 0; g < 2; ++g) {
-                    if (st.step[g] >= st.total[g] || !mbar_try_wait(&sync[g].req, st.req_ph[g])) continue;
-                    st.req_ph[g] ^= 1;
-                    last = clock64();
-                    const uint32_t base = smem_u32(gbase + g * kEmbGroupBytes);
-                    const uint32_t de = base, em = base + kTile, h2 = base + 2 * kTile, h1 = base + 3 * kTile,
-                                   xa = base + 4 * kTile;
-                    const uint32_t dcol = tmem + g * 64;
-                    const int k3 = kind[g];
-                    // request 0: Z3 in DE, input h2, weights W3;  1: Z2 in EM, input h1, weights W2;  2: Z1 in DE, input x
-                    const uint32_t za = k3 == 1 ? em : de;
-                    const uint32_t ia = k3 == 0 ? h2 : (k3 == 1 ? h1 : xa);
-                    if (k3 == 0) {
-                        mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
-                        st.tma_ph[g] ^= 1;
-                    }
+            // one request: Z tile `z` (K-major for the data gradient with weights `wk`, MN-major for the weight
+            // gradient against the layer input `in_mn`), accumulators of layer block `blk`
+            auto layer = [&](uint32_t dcol, uint32_t z, uint64_t in_mn, uint64_t wk, bool dgrad, int blk) {
+                const uint64_t zk = kdesc(z), z_mn = mndesc(z, kTile);   // A = (Z tile, the tile after it): rows 64.. unused
+                if (dgrad) {
+                    umma_bf16(dcol, zk, wk, id_dh, 0u);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) umma_bf16(dcol, zk + 2 * k, wk + 2 * k, id_dh, 1u);
+                }
+                const uint32_t wcol = tmem + 128 + blk * 128;
+                const uint32_t acc0 = first[blk] ? 0u : 1u;
+                umma_bf16(wcol, z_mn, in_mn, id_w, acc0);
+                umma_bf16(wcol + 64, z_mn, ones_mn, id_w, acc0);
+#pragma unroll
+                for (int j = 1; j < 8; ++j) {
+                    umma_bf16(wcol, z_mn + j * 128, in_mn + j * 128, id_w, 1u);
+                    umma_bf16(wcol + 64, z_mn + j * 128, ones_mn + j * 128, id_w, 1u);
+                }
+                first[blk] = false;
+            };
+            auto serve = [&](const int g) {
+                const uint32_t base = smem_u32(gbase + g * kEmbGroupBytes);
+                const uint32_t de = base, em = base + kTile;
+                const uint32_t dcol = tmem + g * 64;
+                const int k3 = kind[g];
+                // request 0: Z3 in DE, input h2, weights W3;  1: Z2 in EM, input h1, weights W2;  2: Z1 in DE, input x
+                if (k3 == 0) {
+                    mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
+                    st.tma_ph[g] ^= 1;
                     tc_fence_after();
-                    if (k3 < 2) {
-                        const uint32_t wa = smem_u32(k3 == 0 ? w3t : w2t);
-                        for (int k = 0; k < 4; ++k) umma_bf16(dcol, kdesc(za) + 2 * k, kdesc(wa) + 2 * k, id_dh, k > 0 ? 1u : 0u);
-                    }
-                    const uint32_t wcol = tmem + 128 + k3 * 128;
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t acc = (first[k3] && j == 0) ? 0u : 1u;
-                        // A = (Z tile, whatever tile follows it): rows 64..127 of the product are never read
-                        umma_bf16(wcol, mndesc(za, kTile) + j * 128, mndesc(ia, kTile) + j * 128, id_w, acc);
-                        umma_bf16(wcol + 64, mndesc(za, kTile) + j * 128, mndesc(onesa, kTile) + j * 128, id_w, acc);
-                    }
-                    first[k3] = false;
-                    umma_commit(&sync[g].done);
-                    kind[g] = k3 == 2 ? 0 : k3 + 1;
-                    ++st.step[g];
+                    layer(dcol, de, mndesc(base + 2 * kTile, kTile), w3k, true, 0);
+                } else if (k3 == 1) {
+                    tc_fence_after();
+                    layer(dcol, em, mndesc(base + 3 * kTile, kTile), w2k, true, 1);
+                } else {
+                    tc_fence_after();
+                    layer(dcol, de, mndesc(base + 4 * kTile, kTile), w2k, false, 2);
+                }
+                umma_commit(&sync[g].done);
+                kind[g] = k3 == 2 ? 0 : k3 + 1;
+                ++st.step[g];
+            };
+            while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
+                if (st.step[0] < st.total[0] && mbar_try_wait(&sync[0].req, st.req_ph[0])) {
+                    st.req_ph[0] ^= 1;
+                    last = clock64();
+                    serve(0);
+                }
+                if (st.step[1] < st.total[1] && mbar_try_wait(&sync[1].req, st.req_ph[1])) {
+                    st.req_ph[1] ^= 1;
+                    last = clock64();
+                    serve(1);
                 }
                 if (clock64() - last > 8000000000LL) issuer_trap("pathnet_embed_bwd");
             }
