@@ -105,6 +105,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking poll (try_wait may suspend the thread for a hardware time slice before it answers "not yet":
+// a thread that polls SEVERAL barriers must use this one, or a ready barrier waits behind an idle one).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a pipeline bug must never hang the GPU box.  After ~4 s of spinning the
 // kernel traps (the launch then reports an error through the C ABI).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -203,12 +203,12 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                 ++st.step[g];
             };
             while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
-                if (st.step[0] < st.total[0] && mbar_try_wait(&sync[0].req, st.req_ph[0])) {
+                if (st.step[0] < st.total[0] && mbar_test_wait(&sync[0].req, st.req_ph[0])) {
                     st.req_ph[0] ^= 1;
                     last = clock64();
                     serve(0);
                 }
-                if (st.step[1] < st.total[1] && mbar_try_wait(&sync[1].req, st.req_ph[1])) {
+                if (st.step[1] < st.total[1] && mbar_test_wait(&sync[1].req, st.req_ph[1])) {
                     st.req_ph[1] ^= 1;
                     last = clock64();
                     serve(1);
@@ -532,12 +532,12 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                 ++st.step[g];
             };
             while (st.step[0] < st.total[0] || st.step[1] < st.total[1]) {
-                if (st.step[0] < st.total[0] && mbar_try_wait(&sync[0].req, st.req_ph[0])) {
+                if (st.step[0] < st.total[0] && mbar_test_wait(&sync[0].req, st.req_ph[0])) {
                     st.req_ph[0] ^= 1;
                     last = clock64();
                     serve(0);
                 }
-                if (st.step[1] < st.total[1] && mbar_try_wait(&sync[1].req, st.req_ph[1])) {
+                if (st.step[1] < st.total[1] && mbar_test_wait(&sync[1].req, st.req_ph[1])) {
                     st.req_ph[1] ^= 1;
                     last = clock64();
                     serve(1);
