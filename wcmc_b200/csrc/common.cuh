@@ -91,6 +91,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// Adds `bytes` to the transaction count of the current phase WITHOUT arriving (a phase whose loads are issued
+// in several pieces: the last piece arrives with mbar_expect_tx).
+__device__ __forceinline__ void mbar_add_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -171,9 +171,8 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                                z_mn = mndesc(base + 4 * kTile, kTile);
                 const uint32_t dcol = tmem + g * 128;
                 if ((st.step[g] & 1) == 0) {
-                    // R1: dH = Z2 . W2 (K = outc_p);  dW2^T += H^T . Z2  (K = 128 rows)
-                    mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
-                    st.tma_ph[g] ^= 1;
+                    // R1: dH = Z2 . W2 (K = outc_p);  dW2^T += H^T . Z2  (K = 128 rows).  The group posts the request
+                    // only after its TMA tiles have landed: this thread serves both groups and must never block.
                     tc_fence_after();
                     umma_bf16(dcol, zk, zk + 4, id_dh, 0u);
                     if (k2 > 1) umma_bf16(dcol, zk + 2, zk + 6, id_dh, 1u);
@@ -264,6 +263,16 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                         }
                         db2[c] += z[c];
                     }
+                    if (s + 1 < p.S) {   // pull the next sample's lines towards L2 while this one is processed
+#pragma unroll
+                        for (int c = 0; c < OP; ++c) {
+                            if (c < p.outc && valid && lane == 0) {
+                                const size_t o2 = o + static_cast<size_t>(p.outc) * p.HW + static_cast<size_t>(c) * p.HW;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.g + o2));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.out + o2));
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < OP / 8; ++q) {
                         *reinterpret_cast<uint4*>(zw + swz(r, q)) =
@@ -271,12 +280,12 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
                                            pack_h2(z[8 * q + 4], z[8 * q + 5], dt), pack_h2(z[8 * q + 6], z[8 * q + 7], dt));
                     }
                 }
+                mbar_wait(&sy.tma_full, tma_ph);   // the request below promises the issuer that the tiles are there
+                tma_ph ^= 1;
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(&sy.req);
                 // ---- (c) dz1 = dH * act1'(h), in place over the h tiles ----
-                mbar_wait(&sy.tma_full, tma_ph);   // acquire the TMA writes for the generic reads below
-                tma_ph ^= 1;
                 mbar_wait(&sy.done, done_ph);
                 done_ph ^= 1;
                 tc_fence_after();
@@ -515,9 +524,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                 const uint32_t dcol = tmem + g * 64;
                 const int k3 = kind[g];
                 // request 0: Z3 in DE, input h2, weights W3;  1: Z2 in EM, input h1, weights W2;  2: Z1 in DE, input x
-                if (k3 == 0) {
-                    mbar_wait(&sync[g].tma_full, st.tma_ph[g]);
-                    st.tma_ph[g] ^= 1;
+                if (k3 == 0) {   // (the group waited for its TMA tiles before posting the request)
                     tc_fence_after();
                     layer(dcol, de, mndesc(base + 2 * kTile, kTile), w3k, true, 0);
                 } else if (k3 == 1) {
@@ -559,13 +566,21 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
         const int dt = p.dtype;
         uint32_t tma_ph = 0, done_ph = 0;
 
-        auto load_tiles = [&](int pix0, int img) {
-            mbar_expect_tx(&sy.tma_full, 5 * kTile);
-            tma_load_3d(de, &tmde, &sy.tma_full, 0, pix0, img);
-            tma_load_3d(em, &tmem_map, &sy.tma_full, 0, pix0, img);
-            tma_load_3d(h2, &tmh2, &sy.tma_full, 0, pix0, img);
-            tma_load_3d(h1, &tmh1, &sy.tma_full, 0, pix0, img);
-            tma_load_3d(xt, &tmx, &sy.tma_full, 0, pix0, img);
+        // The five tiles of a sample are requested in two pieces, each as soon as its buffers are dead: h2 (last read
+        // by every thread's layer-2 mask pass) and emb (holds dz2, last read by the layer-2 MMAs) once the layer-2
+        // request has retired; h1, d_emb and x after the layer-1 MMAs.  Only the last piece arrives on the barrier,
+        // so the phase completes when all five tiles have landed.
+        auto load_piece = [&](int piece, int pix0, int img) {
+            if (piece == 0) {
+                mbar_add_tx(&sy.tma_full, 2 * kTile);
+                tma_load_3d(h2, &tmh2, &sy.tma_full, 0, pix0, img);
+                tma_load_3d(em, &tmem_map, &sy.tma_full, 0, pix0, img);
+            } else {
+                mbar_expect_tx(&sy.tma_full, 3 * kTile);
+                tma_load_3d(h1, &tmh1, &sy.tma_full, 0, pix0, img);
+                tma_load_3d(de, &tmde, &sy.tma_full, 0, pix0, img);
+                tma_load_3d(xt, &tmx, &sy.tma_full, 0, pix0, img);
+            }
         };
         // dz = dH * act'(saved output), read from TMEM columns [0,64) of the group, written to tile `dst` (row r);
         // `saved` is the tile that holds the layer's post-activation output
@@ -595,7 +610,10 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
             const int b = item / p.tiles, pix0 = (item - b * p.tiles) * 128;
             const int pix = pix0 + r;
             const bool valid = pix < p.HW;
-            if (r == 0 && half == 0) load_tiles(pix0, b * p.S);
+            if (r == 0 && half == 0) {
+                load_piece(0, pix0, b * p.S);
+                load_piece(1, pix0, b * p.S);
+            }
             for (int s = 0; s < p.S; ++s) {
                 const int img = b * p.S + s;
                 // ---- (a) dz3 = (d_emb + d_red / S) * act3'(emb), in place over the d_emb tile ----
@@ -639,6 +657,8 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                 mbar_wait(&sy.done, done_ph);
                 done_ph ^= 1;
                 tc_fence_after();
+                // the layer-2 request was posted by all 256 threads after their pass over h2 and has retired
+                if (r == 0 && half == 0 && s + 1 < p.S) load_piece(0, pix0, img + 1);
                 mask_epilogue(h1, de, p.act1);
                 fence_proxy_async();
                 tc_fence_before();
@@ -646,7 +666,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
                 // ---- (g) layer-1 weight gradient retired: all five tiles are free ----
                 mbar_wait(&sy.done, done_ph);
                 done_ph ^= 1;
-                if (r == 0 && half == 0 && s + 1 < p.S) load_tiles(pix0, img + 1);
+                if (r == 0 && half == 0 && s + 1 < p.S) load_piece(1, pix0, img + 1);
             }
         }
     }
