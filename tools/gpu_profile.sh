@@ -22,6 +22,6 @@ gzip -f $O/launches.csv
 cap conv_layers conv_igemm -c 24 -- python tools/conv_bench.py fwd 1
 cap wgrad_layers conv_wgrad_kernel -c 8 -- python tools/conv_bench.py wgrad 1
 cap kernel_apply kernel_apply -c 12 -- python tools/ka_bench.py 1
-cap misc "pathnet|fmse|adam_clip|wgrad_reduce_batch" -s 12 -c 12 -- env WCMC_BRANCH_STREAMS=0 $BENCH
+cap misc "pathnet|fmse|adam_clip|wgrad_reduce_batch|slab_reduce" -s 14 -c 14 -- env WCMC_BRANCH_STREAMS=0 $BENCH
 cap allpairs allpairs_kernel -c 2 -- python tools/loss_sweep.py 1
 du -sh $O; ls -la $O
