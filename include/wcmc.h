@@ -235,6 +235,24 @@ int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff, const void
                            int outc, int outc_p, int dtype, int act1, int act2, float slope, void* h,
                            float* out, int B, int S, int HW, void* stream);
 
+/* ---- batched weight normalisation (torch._weight_norm over dim 0 for every convolution of a network in one
+ * launch; sbmc.modules.ConvChain's `weight_norm=True` default, kept by networks.py:18-24) ----------------------
+ * forward (backward = 0): w[r,:] = g[r] * v[r,:] / ||v[r,:]||, norm[r] = ||v[r,:]|| saved.
+ * backward (backward = 1): dg[r] = <dw[r,:], v[r,:]> / norm[r];  dv = (g/norm) (dw - v <dw,v> / norm^2).
+ * All tensors fp32, row-major (rows = output channels, cols = cin*k*k).                                       */
+#define WCMC_WN_BATCH_MAX 32
+typedef struct {
+    const float* v;
+    const float* g;
+    float* w;          /* forward output */
+    float* norm;       /* forward output, backward input */
+    const float* dw;   /* backward input */
+    float* dv;         /* backward outputs */
+    float* dg;
+    int rows, cols;
+} wcmc_wn_desc;
+int wcmc_weight_norm_batch(const wcmc_wn_desc* host_descs, int n, int backward, void* stream);
+
 /* ---- K8 / K9: the backward passes of the two MLPs, each ONE tensor-core kernel + a slab reduction
  * (autograd of networks.py:29-42; replaces the 1x1-conv dgrad / wgrad / bias / activation launches) ----
  * Gradients between kernels stay 16-bit and loss-scaled: *gscale multiplies the incoming fp32 gradient,

@@ -638,3 +638,22 @@ def test_fused_mlp_backward_vs_generic_path(backend, oracle, size, batch, spp, o
     # every tensor separately (a wrong bias / small weight block would hide in the global norm)
     for k, e in per.items():
         assert e < 5e-2, "%s: fused vs generic rel-L2 %.3e" % (k, e)
+
+
+def test_batched_weight_norm_vs_torch(backend):
+    """ops.BatchedWeightNormFn (one launch for all layers, each direction) against torch._weight_norm + autograd."""
+    from wcmc_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [(64, 36, 1, 1), (64, 64, 3, 3), (512, 512, 3, 3), (3, 128, 1, 1), (128, 192, 3, 3)]
+    vs = [torch.randn(s, device="cuda", generator=g).requires_grad_(True) for s in shapes]
+    gs = [(torch.rand(s[0], 1, 1, 1, device="cuda", generator=g) + 0.5).requires_grad_(True) for s in shapes]
+    flat = [t for pair in zip(vs, gs) for t in pair]
+    ws = ops.BatchedWeightNormFn.apply(*flat)
+    ref = [torch._weight_norm(v, gg, 0) for v, gg in zip(vs, gs)]
+    ups = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    for w, r in zip(ws, ref):
+        assert rel(w, r) < 1e-6
+    got = torch.autograd.grad([(w * u).sum() for w, u in zip(ws, ups)], flat)
+    want = torch.autograd.grad([(r * u).sum() for r, u in zip(ref, ups)], flat)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel(a, b) < 1e-5

@@ -49,10 +49,41 @@ def _make_conv(cin, cout, ksize, padding, gain_of, weight_norm):
     return conv
 
 
+_WN_OVERRIDE = None   # {id(conv): effective weight} while batched_weight_norm() is active
+
+
 def _effective_weight(conv):
+    if _WN_OVERRIDE is not None and id(conv) in _WN_OVERRIDE:
+        return _WN_OVERRIDE[id(conv)]
     if hasattr(conv, "weight_g"):
         return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
     return conv.weight
+
+
+class batched_weight_norm:
+    """Context manager: the effective weights of every weight-normalised convolution under `module` come from ONE
+    launch (ops.BatchedWeightNormFn) instead of one torch._weight_norm kernel per layer and direction; the `spec()`
+    calls made inside the context pick them up."""
+
+    def __init__(self, module):
+        self.convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and hasattr(m, "weight_g")]
+
+    def __enter__(self):
+        global _WN_OVERRIDE
+        self.prev = _WN_OVERRIDE
+        if self.convs and self.convs[0].weight_v.is_cuda:
+            flat = []
+            for c in self.convs:
+                flat += [c.weight_v, c.weight_g]
+            ws = ops.BatchedWeightNormFn.apply(*flat)
+            _WN_OVERRIDE = dict(self.prev or {})
+            _WN_OVERRIDE.update({id(c): w for c, w in zip(self.convs, ws)})
+        return self
+
+    def __exit__(self, *exc):
+        global _WN_OVERRIDE
+        _WN_OVERRIDE = self.prev
+        return False
 
 
 class _ConvAct(nn.Module):

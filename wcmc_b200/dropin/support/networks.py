@@ -30,8 +30,9 @@ class PathNet(nn.Module):
         paths = samples["paths"]
         if paths.shape[-2] % 4 or paths.shape[-1] % 4:
             raise ValueError("PathNet: spatial size %s must be divisible by 4" % (tuple(paths.shape[-2:]),))
-        e_layers, e_params = self.embedding.spec()
-        u_spec, u_params = self.propagation.spec()
-        f_layers, f_params = self.final.spec()
+        with ops.batched_weight_norm(self):   # all 20 layers' g * v / ||v|| in one launch (and one in backward)
+            e_layers, e_params = self.embedding.spec()
+            u_spec, u_params = self.propagation.spec()
+            f_layers, f_params = self.final.spec()
         spec = wops.PathNetSpec(embedding=e_layers, unet=u_spec, final=f_layers)
         return wops.PathNetFn.apply(paths, spec, *(e_params + u_params + f_params))

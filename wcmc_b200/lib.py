@@ -26,6 +26,12 @@ class PackDesc(ctypes.Structure):
                 ("cin_p", c_int)]
 
 
+class WnDesc(ctypes.Structure):
+    """wcmc_wn_desc of include/wcmc.h"""
+    _fields_ = [("v", c_void_p), ("g", c_void_p), ("w", c_void_p), ("norm", c_void_p), ("dw", c_void_p),
+                ("dv", c_void_p), ("dg", c_void_p), ("rows", c_int), ("cols", c_int)]
+
+
 class WgradReduceDesc(ctypes.Structure):
     """wcmc_wgrad_reduce_desc of include/wcmc.h"""
     _fields_ = [("ws", c_void_p), ("dw", c_void_p), ("scale", c_void_p), ("nsplit", c_int), ("cout", c_int),
@@ -82,6 +88,7 @@ SIGNATURES = {
                                + [c_void_p] * 6 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "wcmc_pathnet_embed_bwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float]
                                + [c_void_p] * 6 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "wcmc_weight_norm_batch": (c_int, [ctypes.POINTER(WnDesc), c_int, c_int, c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
@@ -608,6 +615,46 @@ def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc,
          prop.shape[-1], prop_coff, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), outc, outc_p,
          _dt(emb), acts[0], acts[1], float(slope), _p(hfin), out.data_ptr(), b, s, hw, _stream())
     return out
+
+
+# ---- batched weight normalisation ------------------------------------------------------------------
+def weight_norm_batch_fwd(vs, gs):
+    """vs[i] (cout, ...) / gs[i] (cout, 1, ...) fp32 -> (ws, norms): torch._weight_norm(v, g, 0) for every layer, one launch."""
+    lib = init(vs[0].device)
+    n = len(vs)
+    descs = (WnDesc * n)()
+    ws, norms = [], []
+    for i, (v, g) in enumerate(zip(vs, gs)):
+        assert v.dtype == torch.float32 and v.is_contiguous() and g.dtype == torch.float32 and g.is_contiguous()
+        rows = v.shape[0]
+        assert g.numel() == rows
+        w = torch.empty_like(v)
+        nrm = torch.empty(rows, dtype=torch.float32, device=v.device)
+        descs[i] = WnDesc(v.data_ptr(), g.data_ptr(), w.data_ptr(), nrm.data_ptr(), 0, 0, 0, rows, v.numel() // rows)
+        ws.append(w)
+        norms.append(nrm)
+    _run(lib.wcmc_weight_norm_batch, "weight_norm_fwd", sum(v.numel() for v in vs) * 8.0, descs, n, 0, _stream())
+    return ws, norms
+
+
+def weight_norm_batch_bwd(dws, vs, gs, norms):
+    """-> (dvs, dgs) for every layer, one launch."""
+    lib = init(vs[0].device)
+    n = len(vs)
+    descs = (WnDesc * n)()
+    dvs, dgs, keep = [], [], []
+    for i, (dw, v, g, nrm) in enumerate(zip(dws, vs, gs, norms)):
+        if dw.dtype != torch.float32 or not dw.is_contiguous():
+            dw = dw.float().contiguous()
+        keep.append(dw)
+        rows = v.shape[0]
+        dv, dg = torch.empty_like(v), torch.empty_like(g)
+        descs[i] = WnDesc(v.data_ptr(), g.data_ptr(), 0, nrm.data_ptr(), dw.data_ptr(), dv.data_ptr(), dg.data_ptr(), rows,
+                          v.numel() // rows)
+        dvs.append(dv)
+        dgs.append(dg)
+    _run(lib.wcmc_weight_norm_batch, "weight_norm_bwd", sum(v.numel() for v in vs) * 12.0, descs, n, 1, _stream())
+    return dvs, dgs
 
 
 # ---- K8/K9: fused PathNet MLP backward passes -------------------------------------------------------

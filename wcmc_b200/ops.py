@@ -149,6 +149,31 @@ def _grad_nhwc(g, c_fill, scale=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# weight normalisation of every convolution of a network in one launch per direction
+# ------------------------------------------------------------------------------------------------
+class BatchedWeightNormFn(torch.autograd.Function):
+    """(v0, g0, v1, g1, ...) -> (w0, w1, ...) with w = g * v / ||v|| over all dims but 0 (torch._weight_norm(v, g, 0))."""
+
+    @staticmethod
+    def forward(ctx, *vg):
+        vs = [t.detach().float().contiguous() for t in vg[0::2]]
+        gs = [t.detach().float().contiguous() for t in vg[1::2]]
+        ws, norms = lib.weight_norm_batch_fwd(vs, gs)
+        ctx.saved = (vs, gs, norms)
+        return tuple(ws)
+
+    @staticmethod
+    def backward(ctx, *dws):
+        vs, gs, norms = ctx.saved
+        dws = [torch.zeros_like(v) if d is None else d for d, v in zip(dws, vs)]
+        dvs, dgs = lib.weight_norm_batch_bwd(dws, vs, gs, norms)
+        out = []
+        for dv, dg in zip(dvs, dgs):
+            out += [dv, dg]
+        return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
 # ConvChain
 # ------------------------------------------------------------------------------------------------
 class ConvChainFn(torch.autograd.Function):
