@@ -712,24 +712,35 @@ struct SlabReduceParams {
     int nseg;
     SlabSeg seg[8];
 };
+// 64 output elements per CTA, 4 threads per element (each sums every 4th slab with 4 loads in flight), fixed-order
+// combine through shared memory.  (The first version -- 32 CTAs, one thread per element walking all 148 slabs --
+// took 196 us per call: 8 k threads cannot cover 12 MB of latency-bound strided reads.)
 __global__ void __launch_bounds__(256) slab_reduce_kernel(const SlabReduceParams p) {
+    __shared__ float red[4][64];
     const float sc = p.scale != nullptr ? __ldg(p.scale) : 1.f;
+    const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
     for (int s = 0; s < p.nseg; ++s) {
         const SlabSeg& sg = p.seg[s];
         const int n = sg.rows * sg.cols_dst;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const int row = i / sg.cols_dst, col = i - row * sg.cols_dst;
-            const float* src = p.partial + sg.off + row * sg.cols_src + col;
+        for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {
+            const int i = base + e;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int k = 0;
-            for (; k + 4 <= p.nslabs; k += 4) {
-                a0 += __ldg(src + static_cast<size_t>(k) * p.slab);
-                a1 += __ldg(src + static_cast<size_t>(k + 1) * p.slab);
-                a2 += __ldg(src + static_cast<size_t>(k + 2) * p.slab);
-                a3 += __ldg(src + static_cast<size_t>(k + 3) * p.slab);
+            if (i < n) {
+                const int row = i / sg.cols_dst, col = i - row * sg.cols_dst;
+                const float* src = p.partial + sg.off + row * sg.cols_src + col;
+                int k = q;
+                for (; k + 12 < p.nslabs; k += 16) {
+                    a0 += __ldg(src + static_cast<size_t>(k) * p.slab);
+                    a1 += __ldg(src + static_cast<size_t>(k + 4) * p.slab);
+                    a2 += __ldg(src + static_cast<size_t>(k + 8) * p.slab);
+                    a3 += __ldg(src + static_cast<size_t>(k + 12) * p.slab);
+                }
+                for (; k < p.nslabs; k += 4) a0 += __ldg(src + static_cast<size_t>(k) * p.slab);
             }
-            for (; k < p.nslabs; ++k) a0 += __ldg(src + static_cast<size_t>(k) * p.slab);
-            sg.dst[i] = ((a0 + a1) + (a2 + a3)) * sc;
+            red[q][e] = (a0 + a1) + (a2 + a3);
+            __syncthreads();
+            if (q == 0 && i < n) sg.dst[i] = ((red[0][e] + red[1][e]) + (red[2][e] + red[3][e])) * sc;
+            __syncthreads();
         }
     }
 }
@@ -803,7 +814,7 @@ extern "C" int wcmc_pathnet_final_bwd(const float* g, const float* out, const fl
     r.seg[1] = SlabSeg{db1, 128 * 128, 1, 128, 128};
     r.seg[2] = SlabSeg{dw2, 128 * 128 + 128, outc, 128, 128};
     r.seg[3] = SlabSeg{db2, 128 * 128 + 128 + 32 * 128, 1, 32, outc};
-    slab_reduce_kernel<<<32, 256, 0, stream>>>(r);
+    slab_reduce_kernel<<<296, 256, 0, stream>>>(r);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -854,7 +865,7 @@ extern "C" int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, cons
     r.seg[3] = SlabSeg{db2, blk + 64 * 64, 1, 64, 64};
     r.seg[4] = SlabSeg{dw1, 2 * blk, 64, 64, cin};
     r.seg[5] = SlabSeg{db1, 2 * blk + 64 * 64, 1, 64, 64};
-    slab_reduce_kernel<<<32, 256, 0, stream>>>(r);
+    slab_reduce_kernel<<<296, 256, 0, stream>>>(r);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
