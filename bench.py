@@ -169,6 +169,21 @@ def bench_720p(args, KPCN, make_batch):
                         "whole frame in one pass (no tiling)"}
 
 
+def _leave(world):
+    """End of a rank under torchrun.  The gradient all-reduce is captured INSIDE the step's CUDA graph; tearing such a
+    communicator down (dist.destroy_process_group, or the interpreter's own exit with the graph still alive) hung
+    for minutes after the result line had been printed (2-GPU run of round 1, profiles/r01final_multi2.txt).
+    Every collective of the run has completed by now (the timed regions end with a barrier + synchronize), so the
+    ranks leave without the teardown."""
+    if world <= 1:
+        return
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -302,8 +317,7 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
     pk, pk_src = peaks()
     frame = bench_720p(args, KPCN, make_batch) if (world == 1 and not args.no_720p) else None
@@ -356,9 +370,8 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "2 timed steps of batch 2 (same 128x128, 8 spp patches) after 1 warm-up; "
                                           "%.1f s/step" % dt}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _leave(world)
 
 
 if __name__ == "__main__":
