@@ -179,3 +179,51 @@ def test_pre_interface_step_matches_reference(golden_n4, oracle, tag):
         _close(v, g["losses"]["m_" + k], rtol=1e-4, atol=1e-7)
     # parameters of the frozen models must not move; gradients are compared where the reference has them
     _check_models(models, g, [n for n in models if float(g["grad_abs_sums"][n].min()) >= 0])
+
+
+# ---- preprocessing of raw sample buffers, restatement vs the reference's own methods ----
+@pytest.fixture(scope="module")
+def golden_n3():
+    import os
+    import numpy as np
+    from tests.conftest import ROOT
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_golden_n3.npz"))
+
+
+@pytest.fixture(scope="module")
+def prep():
+    import importlib.util
+    import os
+    from tests.conftest import ROOT
+    spec = importlib.util.spec_from_file_location("oracle_preprocess_ref", os.path.join(ROOT, "oracle", "preprocess_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_preprocess_matches_reference(golden_n3, prep, tag):
+    import numpy as np
+    raw = golden_n3["raw_" + tag]
+    with np.errstate(all="ignore"):
+        san = prep.sanitize(raw)
+        assert np.isfinite(san).all() and san.max() <= np.float32(1.0e38)
+        kp = prep.preprocess_kpcn(san)
+        ll = prep.preprocess_llpm(san)
+    want_k, want_l = golden_n3["kpcn_" + tag], golden_n3["llpm_" + tag]
+    assert kp.shape == want_k.shape and kp.shape[2] == 44 and ll.shape == want_l.shape and ll.shape[3] == 37
+    # tag "a" carries inf / NaN / 3e38 outliers: the reference's own output has NaN there (inf / inf), same places
+    np.testing.assert_allclose(kp, want_k, rtol=2e-5, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(ll, want_l, rtol=1e-6, atol=1e-7, equal_nan=True)
+    if tag == "b":
+        assert np.isfinite(kp).all()
+    np.testing.assert_allclose(prep.gradients(kp[..., :3]), golden_n3["grad_" + tag], rtol=0, atol=0, equal_nan=True)
+    # the batch tensors: channel bookkeeping of datasets.py:1078-1110
+    t = prep.kpcn_batch_tensors(kp, ll)
+    h, w, s = raw.shape[:3]
+    assert t["kpcn_diffuse_in"].shape == (35, h, w) and t["kpcn_specular_in"].shape == (35, h, w)
+    assert t["paths"].shape == (s, 36, h, w) and t["kpcn_albedo"].shape == (3, h, w)
+    np.testing.assert_array_equal(t["kpcn_diffuse_in"][:3], t["kpcn_diffuse_buffer"])
+    np.testing.assert_array_equal(t["kpcn_specular_in"][:3], t["kpcn_specular_buffer"])
+    np.testing.assert_array_equal(t["kpcn_diffuse_in"][10:34], t["kpcn_specular_in"][10:34])   # shared normal/depth/albedo
+    np.testing.assert_allclose(t["kpcn_diffuse_in"][34], ll[..., 0].mean(2), rtol=1e-6, equal_nan=True)
