@@ -279,6 +279,15 @@ int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, const float* in
                            float* dw3, float* db3, float* dw2, float* db2, float* dw1, float* db1, int B,
                            int S, int HW, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- preprocessing of raw OptaGen sample buffers (DenoiseDataset._preprocess_kpcn /
+ * _preprocess_llpm, /root/reference/support/datasets.py:487-582, :301-361, NaN clamp :621-624 folded in) ----
+ * raw: (H,W,S,104) fp32, S <= 8.  out44: (H,W,44) fp32 in the reference's channel order; out37: (H*W*S,37) fp32.
+ * Written after round 1's GPU budget was spent: compiled, not yet validated on a GPU, not on the product path.   */
+size_t wcmc_preprocess_kpcn_workspace(int H, int W);
+int wcmc_preprocess_kpcn(const float* raw, int H, int W, int S, float* out44, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int wcmc_preprocess_llpm(const float* raw, long nrows, float* out37, void* stream);
+
 /* ---- K12: clip_grad_value_ + Adam for all parameter tensors in one launch
  * (/root/reference/support/interfaces.py:261 clip, :269-271 three optimiser steps; Adam with torch's
  * defaults as constructed at /root/reference/train_kpcn.py:277) -----------------------------------

@@ -89,6 +89,9 @@ SIGNATURES = {
     "wcmc_pathnet_embed_bwd": (c_int, [c_void_p] * 4 + [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_float]
                                + [c_void_p] * 6 + [c_int] * 3 + [c_void_p, c_size_t, c_void_p]),
     "wcmc_weight_norm_batch": (c_int, [ctypes.POINTER(WnDesc), c_int, c_int, c_void_p]),
+    "wcmc_preprocess_kpcn_workspace": (c_size_t, [c_int, c_int]),
+    "wcmc_preprocess_kpcn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "wcmc_preprocess_llpm": (c_int, [c_void_p, ctypes.c_long, c_void_p, c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
@@ -614,6 +617,32 @@ def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc,
     _run(lib.wcmc_pathnet_final_fwd, "pathnet_final_fwd", work, emb.data_ptr(), ecs, emb_coff, prop.data_ptr(),
          prop.shape[-1], prop_coff, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), outc, outc_p,
          _dt(emb), acts[0], acts[1], float(slope), _p(hfin), out.data_ptr(), b, s, hw, _stream())
+    return out
+
+
+# ---- preprocessing of raw sample buffers (not yet validated on a GPU) ----------------
+def preprocess_kpcn(raw):
+    """raw (H,W,S,104) fp32 cuda -> (H,W,44) fp32: DenoiseDataset._preprocess_kpcn (datasets.py:487-582)."""
+    lib = init(raw.device)
+    assert raw.dtype == torch.float32 and raw.is_contiguous() and raw.dim() == 4 and raw.shape[3] == 104
+    h, w, s, _ = raw.shape
+    out = torch.empty((h, w, 44), dtype=torch.float32, device=raw.device)
+    need = lib.wcmc_preprocess_kpcn_workspace(h, w)
+    ws = torch.empty(need, dtype=torch.uint8, device=raw.device)
+    LAUNCHES["count"] += 1
+    _run(lib.wcmc_preprocess_kpcn, "preprocess_kpcn", raw.numel() * 4.0 * 0.3 + out.numel() * 4.0, raw.data_ptr(), h, w, s,
+         out.data_ptr(), ws.data_ptr(), need, _stream())
+    return out
+
+
+def preprocess_llpm(raw):
+    """raw (H,W,S,104) fp32 cuda -> (H,W,S,37) fp32: DenoiseDataset._preprocess_llpm (datasets.py:301-361)."""
+    lib = init(raw.device)
+    assert raw.dtype == torch.float32 and raw.is_contiguous() and raw.dim() == 4 and raw.shape[3] == 104
+    h, w, s, _ = raw.shape
+    out = torch.empty((h, w, s, 37), dtype=torch.float32, device=raw.device)
+    _run(lib.wcmc_preprocess_llpm, "preprocess_llpm", h * w * s * (176.0 + 148.0), raw.data_ptr(), h * w * s,
+         out.data_ptr(), _stream())
     return out
 
 
