@@ -142,3 +142,25 @@ def test_tile_protocol_matches_reference_rule():
     assert torch.equal(one, rad)
     np_rad, _ = inf.to_numpy_hwc(rad, None)
     assert np_rad.shape == (192, 256, 3)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: the oracle port on the host cores, one JSON line with the base contract's keys;
+    under torchrun only rank 0 works, the other ranks exit 0 silently."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "KPCN+WCMC train patches/s" and line["unit"] == "patches/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env["RANK"], env["WORLD_SIZE"], env["LOCAL_RANK"] = "1", "2", "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
