@@ -87,6 +87,35 @@ def test_conv_tilings_agree(backend, mt, nt):
     assert torch.equal(base, alt)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,pad,f32", [(1, 44, 44, 100, 100, 5, 0, False),    # 9 regions: a dead second region
+                                                         (1, 16, 16, 64, 64, 3, 1, False),      # a single region
+                                                         (4, 72, 72, 100, 441, 5, 0, True),     # 4 n tiles, fp32 logits
+                                                         (8, 64, 64, 192, 64, 3, 1, False)])
+def test_conv_pair_launch_is_bit_identical(backend, n, h, w, cin, cout, k, pad, f32):
+    """CTA-pair launches (cluster of 2, tcgen05 cta_group::2, flags bit 20) against single-CTA launches (bit 21), with
+    a kernel row of taps per weight stage and with one tap per stage (bit 22): the same MMAs per output element in the
+    same K order, so forward, data gradient (+ fused ReLU mask) are bit-identical and the fused bias gradient agrees
+    up to the order of its atomics (the product path picks the launch shape per layer; tools/pair_check.py times it)."""
+    lib = backend.lib
+    PAIR, SINGLE, TAPS = 1 << 20, 1 << 21, 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(100 * k + cin)
+    dt = _act_dtype()
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    x = lib.nchw_to_nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype=dt)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.03
+    wf, wd, bp = lib.pack_weights(wt, torch.randn(cout, device="cuda", generator=g), want_bias=True, dtype=dt)
+    dy = lib.nchw_to_nhwc(torch.randn(n, cout, ho, wo, device="cuda", generator=g), dtype=dt)
+    od = torch.float32 if f32 else None
+    base = lib.conv2d(x, wf, bp, k, pad, act=0 if f32 else 1, out_dtype=od, flags=SINGLE | TAPS)
+    cs0 = torch.zeros(lib.pad16(cin), device="cuda")
+    dbase = lib.conv2d(dy, wd, None, k, k - 1 - pad, act=0, mask=x, flags=SINGLE | TAPS, colsum=cs0)
+    for flags in (SINGLE, PAIR, PAIR | TAPS):
+        assert torch.equal(lib.conv2d(x, wf, bp, k, pad, act=0 if f32 else 1, out_dtype=od, flags=flags), base), flags
+        cs = torch.zeros(lib.pad16(cin), device="cuda")
+        assert torch.equal(lib.conv2d(dy, wd, None, k, k - 1 - pad, act=0, mask=x, flags=flags, colsum=cs), dbase), flags
+        assert rel(cs, cs0) < 1e-4, flags
+
+
 @pytest.mark.parametrize("k,c,shape", [(21, 3, (2, 37, 45)), (21, 3, (8, 92, 92)), (5, 1, (1, 9, 70)), (3, 4, (2, 8, 32))])
 def test_kernel_apply_vs_oracle(backend, oracle, k, c, shape):
     lib = backend.lib
