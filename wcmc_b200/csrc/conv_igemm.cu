@@ -494,6 +494,20 @@ static int g_conv_pair = 1;
 int wcmc_conv_set_pair(int v) { g_conv_pair = v ? 1 : 0; return 0; }
 static int g_conv_row_stages = 1;
 int wcmc_conv_set_row_stages(int v) { g_conv_row_stages = v ? 1 : 0; return 0; }
+// measurement knobs of the launch-shape model (defaults = the values measured in round 1):
+//   "conv_pair_min_clk"  single-CTA MMA clocks above which a layer is launched on CTA pairs (20000)
+//   "conv_item_clk"      fixed per-item cost of the M-tiles-per-region model (1000)
+//   "conv_plane_slots"   halo ring depth for k > 1 layers (0 = 2 slots; 3 or 4 trade weight stages for a deeper halo
+//                        prefetch -- untested idea for the short 3x3 U-Net layers, which are latency-bound per item)
+static int g_conv_pair_min_clk = 20000, g_conv_item_clk = 1000, g_conv_plane_slots = 0;
+int wcmc_conv_set_model(int which, int v) {
+    if (v < 0) return -1;
+    if (which == 0) g_conv_pair_min_clk = v;
+    else if (which == 1) g_conv_item_clk = v;
+    else if (which == 2 && (v == 0 || (v >= 2 && v <= kMaxPlaneSlots))) g_conv_plane_slots = v;
+    else return -1;
+    return 0;
+}
 
 template <bool PAIR, int TPS>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams& p, int grid, int smem_bytes,
@@ -579,12 +593,12 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
         // MMA clocks of the single-CTA launch: below ~20k (about 10 us) the kernel is launch / epilogue bound
         const long items1 = static_cast<long>(N) * ((Wo + 8 * mt - 1) / (8 * mt)) * ry16 * p.n_tiles;
         const long clk1 = ((items1 + sms - 1) / sms) * mt * mmas_per_tile * (p.nt / 2);
-        pair = items1 >= sms && clk1 >= 20000;
+        pair = items1 >= sms && clk1 >= g_conv_pair_min_clk;
     }
     if (flags & (1 << 20)) pair = true;
     if (flags & (1 << 21)) pair = false;
     if (pair) {
-        const long tile_clk = mmas_per_tile * (p.nt / 2), fixed_clk = 1000;
+        const long tile_clk = mmas_per_tile * (p.nt / 2), fixed_clk = g_conv_item_clk;
         long best = -1;
         for (int m = 1; m <= 2; ++m) {
             const long regions = static_cast<long>(N) * ((Wo + 8 * m - 1) / (8 * m)) * ry16;
@@ -634,7 +648,10 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.tap_stride = (((pair ? p.nt / 2 : p.nt) * 128 + 1023) / 1024) * 1024;
     // Two halo slots are enough when a chunk carries k*k taps of MMAs (the next plane loads during a whole
     // chunk); 1x1 convolutions have one tap per region and are HBM-bound: give them a deeper plane ring.
-    p.plane_slots = (ksize == 1) ? kMaxPlaneSlots : 2;
+    p.plane_slots = (ksize == 1) ? kMaxPlaneSlots : (g_conv_plane_slots ? g_conv_plane_slots : 2);
+    if (ksize > 1 && p.plane_slots > 2 &&
+        (kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride) / p.tap_stride < 4)
+        p.plane_slots = 2;   // the deeper halo ring must leave room for a useful weight ring
     const int b_room = kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride;
     int tps = 1;
     if (g_conv_row_stages && !(flags & (1 << 22)) && ksize > 1 && b_room / (ksize * p.tap_stride) >= 3) tps = ksize;
