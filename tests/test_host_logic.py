@@ -164,3 +164,23 @@ def test_bench_reference_arm_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_preprocess_batch_tensor_bookkeeping_matches_oracle():
+    """wcmc_b200.preprocess.kpcn_batch_tensors (pure slicing / permutes, runs on any device) against the oracle's
+    restatement of datasets.py:1078-1110 on the reference-generated buffers."""
+    import numpy as np
+    from wcmc_b200 import preprocess
+    spec = importlib.util.spec_from_file_location("oracle_preprocess_ref", os.path.join(ROOT, "oracle", "preprocess_ref.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden_n3.npz"))
+    kp, ll = g["kpcn_b"], g["llpm_b"]
+    want = ref.kpcn_batch_tensors(kp, ll)
+    got = preprocess.kpcn_batch_tensors(torch.from_numpy(kp), torch.from_numpy(ll))
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert got[k].is_contiguous() and tuple(got[k].shape) == want[k].shape, k
+        np.testing.assert_allclose(got[k].numpy(), want[k], rtol=1e-6, atol=1e-7, err_msg=k)
+    no_paths = preprocess.kpcn_batch_tensors(torch.from_numpy(kp))
+    assert "paths" not in no_paths and tuple(no_paths["kpcn_diffuse_in"].shape) == (34,) + kp.shape[:2]
