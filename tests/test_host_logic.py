@@ -3,6 +3,7 @@ eligibility rules, the synthetic batch contract, crop_like, and the all-pairs or
 import importlib.util
 import os
 
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -184,3 +185,38 @@ def test_preprocess_batch_tensor_bookkeeping_matches_oracle():
         np.testing.assert_allclose(got[k].numpy(), want[k], rtol=1e-6, atol=1e-7, err_msg=k)
     no_paths = preprocess.kpcn_batch_tensors(torch.from_numpy(kp))
     assert "paths" not in no_paths and tuple(no_paths["kpcn_diffuse_in"].shape) == (34,) + kp.shape[:2]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_preprocess_kernel_arithmetic_on_host(tag):
+    """The per-element functions the N3 CUDA kernels call (wcmc_b200/csrc/preprocess_math.cuh, __host__ __device__)
+    compiled for the host (tests/native/preprocess_host_check.cu) against the vectors the REFERENCE's own
+    _preprocess_kpcn / _preprocess_llpm produced -- channel indices, formulas, the NaN / inf clamp, the depth
+    normalisation and the finite differences are checked here; only the launch mechanics are left for the GPU."""
+    import ctypes
+    import shutil
+    import subprocess
+    import numpy as np
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    so = os.path.join(ROOT, "build", "preprocess_host_check.so")
+    src = os.path.join(ROOT, "tests", "native", "preprocess_host_check.cu")
+    hdr = os.path.join(ROOT, "wcmc_b200", "csrc", "preprocess_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.run(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets", "-o", so,
+                        src], check=True, capture_output=True)
+    lib = ctypes.CDLL(so)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden_n3.npz"))
+    raw = np.ascontiguousarray(g["raw_" + tag], dtype=np.float32)      # un-sanitised: inf / NaN / 3e38 outliers in "a"
+    h, w, s, _ = raw.shape
+    fp = ctypes.POINTER(ctypes.c_float)
+    ll = np.empty((h, w, s, 37), np.float32)
+    lib.host_preprocess_llpm(raw.ctypes.data_as(fp), ctypes.c_long(h * w * s), ll.ctypes.data_as(fp))
+    np.testing.assert_allclose(ll, g["llpm_" + tag], rtol=2e-6, atol=1e-7)
+    kp = np.empty((h, w, 44), np.float32)
+    ws = np.empty((h * w, 18), np.float32)
+    lib.host_preprocess_kpcn(raw.ctypes.data_as(fp), h, w, s, ws.ctypes.data_as(fp), kp.ctypes.data_as(fp))
+    want = g["kpcn_" + tag]
+    assert np.array_equal(np.isnan(kp), np.isnan(want))     # NaN exactly where the reference has it (overflowed variance)
+    np.testing.assert_allclose(kp, want, rtol=3e-5, atol=2e-6, equal_nan=True)
