@@ -169,6 +169,57 @@ def bench_720p(args, KPCN, make_batch):
                         "whole frame in one pass (no tiling)"}
 
 
+def summarize_kernels(prof, steps, pk, pk_src):
+    """prof = {C-ABI call: (calls, total ms, total algorithmic work)} of the eager timed pass (lib.profile_stop()).
+    -> (roofline of the dominant kernel, roofline_more, per-call table).  Pure host logic (tests/test_host_logic.py).
+    Dominant kernel: conv_igemm_kernel<1,5> -- the 5x5, 100-channel KPCN layers (forward + data gradient) on CTA pairs,
+    the largest entry of the ncu launch list together with conv_wgrad_kernel
+    (profiles/r01z_ncu_launch_shares_step.txt); the other instantiations / kernels go to roofline_more."""
+    total_ms = sum(v[1] for v in prof.values()) or 1.0
+    n_c, ms_c, fl_c = prof.get("conv2d_k5", (0, 0.0, 0.0))
+    ms_c = ms_c or 1.0
+    achieved = fl_c / (ms_c * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    more = []
+    for name, label, bound in (
+            ("conv2d_k3", "conv_igemm_kernel<*,3> (3x3 U-Net layers of PathNet, forward + data gradient)", "tensor"),
+            ("conv2d_wgrad_k5", "conv_wgrad_kernel (5x5 layers)", "tensor"),
+            ("conv2d_wgrad_k3", "conv_wgrad_kernel (3x3 layers)", "tensor"),
+            ("kernel_apply_fwd", "kernel_apply_fwd_kernel (8 x 92^2 pixels per launch)", "hbm"),
+            ("kernel_apply_bwd", "kernel_apply_bwd_kernel", "hbm"),
+            ("pathnet_embed_fwd", "pathnet_embed_fwd_kernel", "hbm"),
+            ("pathnet_final_fwd", "pathnet_final_fwd_kernel", "hbm"),
+            ("pathnet_final_bwd", "pathnet_final_bwd_kernel + slab_reduce_kernel", "hbm"),
+            ("pathnet_embed_bwd", "pathnet_embed_bwd_kernel + slab_reduce_kernel", "hbm")):
+        cnt, ms, work = prof.get(name, (0, 0.0, 0.0))
+        if cnt and ms > 0 and work > 0:
+            pkv = peak if bound == "tensor" else pk["hbm_gbs"]
+            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            more.append({"kernel": label, "bound": bound, "achieved": round(ach, 1), "peak": pkv,
+                         "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(ach / pkv, 4),
+                         "ms_per_step": round(ms / steps, 4)})
+    kernels = {k: {"calls_per_step": v[0] // steps, "ms_per_step": round(v[1] / steps, 4),
+                   "share_of_kernel_time": round(v[1] / total_ms, 4)} for k, v in sorted(prof.items())}
+    units = {"tflops": 1e12, "gbs": 1e9}
+    for name, v in prof.items():
+        key = "tflops" if name.startswith("conv2d") else ("gbs" if v[2] > 0 else None)
+        if key and v[1] > 0:
+            kernels[name][key] = round(v[2] / (v[1] * 1e-3) / units[key], 1)
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["conv_igemm_k5_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"kernel": "conv_igemm_kernel<1,5> (5x5 100-channel KPCN layers, forward + data gradient, tcgen05 "
+                          "cta_group::2)",
+                "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": pk_src + " (sustained)",
+                "launches_per_step": n_c // steps,
+                "algorithmic_tflop_per_launch": round(fl_c / max(n_c, 1) / 1e12, 4),
+                "share_of_step_kernel_time": round(ms_c / total_ms, 4)}
+    return roofline, more, kernels
+
+
 def _leave(world):
     """End of a rank under torchrun.  The gradient all-reduce is captured INSIDE the step's CUDA graph; tearing such a
     communicator down (dist.destroy_process_group, or the interpreter's own exit with the graph still alive) hung
@@ -321,44 +372,7 @@ def main():
         return
     pk, pk_src = peaks()
     frame = bench_720p(args, KPCN, make_batch) if (world == 1 and not args.no_720p) else None
-    total_ms = sum(v[1] for v in prof.values()) or 1.0
-    # dominant kernel: conv_igemm_kernel<1,5> -- the 5x5, 100-channel KPCN layers (forward + data gradient) on CTA
-    # pairs, the largest entry of the ncu launch list together with conv_wgrad_kernel
-    # (profiles/r01z_ncu_launch_shares_step.txt).  The other instantiations / kernels follow under "roofline_more".
-    n_c, ms_c, fl_c = prof.get("conv2d_k5", (0, 0.0, 0.0))
-    ms_c = ms_c or 1.0
-    achieved = fl_c / (ms_c * 1e-3) / 1e12
-    peak = pk["bf16_tflops_sustained"]
-    more = []
-    for name, label, bound in (
-            ("conv2d_k3", "conv_igemm_kernel<*,3> (3x3 U-Net layers of PathNet, forward + data gradient)", "tensor"),
-            ("conv2d_wgrad_k5", "conv_wgrad_kernel (5x5 layers)", "tensor"),
-            ("conv2d_wgrad_k3", "conv_wgrad_kernel (3x3 layers)", "tensor"),
-            ("kernel_apply_fwd", "kernel_apply_fwd_kernel (8 x 92^2 pixels per launch)", "hbm"),
-            ("kernel_apply_bwd", "kernel_apply_bwd_kernel", "hbm"),
-            ("pathnet_embed_fwd", "pathnet_embed_fwd_kernel", "hbm"),
-            ("pathnet_final_fwd", "pathnet_final_fwd_kernel", "hbm"),
-            ("pathnet_final_bwd", "pathnet_final_bwd_kernel + slab_reduce_kernel", "hbm"),
-            ("pathnet_embed_bwd", "pathnet_embed_bwd_kernel + slab_reduce_kernel", "hbm")):
-        cnt, ms, work = prof.get(name, (0, 0.0, 0.0))
-        if cnt and ms > 0 and work > 0:
-            pkv = peak if bound == "tensor" else pk["hbm_gbs"]
-            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
-            more.append({"kernel": label, "bound": bound, "achieved": round(ach, 1), "peak": pkv,
-                         "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(ach / pkv, 4),
-                         "ms_per_step": round(ms / args.steps, 4)})
-    kernels = {k: {"calls_per_step": v[0] // args.steps, "ms_per_step": round(v[1] / args.steps, 4),
-                   "share_of_kernel_time": round(v[1] / total_ms, 4)} for k, v in sorted(prof.items())}
-    units = {"tflops": 1e12, "gbs": 1e9}
-    for name, v in prof.items():
-        key = "tflops" if name.startswith("conv2d") else ("gbs" if v[2] > 0 else None)
-        if key and v[1] > 0:
-            kernels[name][key] = round(v[2] / (v[1] * 1e-3) / units[key], 1)
-    traffic = None
-    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["conv_igemm_k5_bytes_per_launch"]
-    except Exception:  # noqa: BLE001
-        pass
+    roofline, more, kernels = summarize_kernels(prof, args.steps, pk, pk_src)
     line = {
         "metric": METRIC, "value": BATCH * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -373,13 +387,7 @@ def main():
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"kernel": "conv_igemm_kernel<1,5> (5x5 100-channel KPCN layers, forward + data gradient, tcgen05 "
-                               "cta_group::2)",
-                     "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": pk_src + " (sustained)",
-                     "launches_per_step": n_c // args.steps,
-                     "algorithmic_tflop_per_launch": round(fl_c / max(n_c, 1) / 1e12, 4),
-                     "share_of_step_kernel_time": round(ms_c / total_ms, 4)},
+        "roofline": roofline,
         "roofline_more": more,
         "kernels": kernels,
     }

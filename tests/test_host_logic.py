@@ -220,3 +220,36 @@ def test_preprocess_kernel_arithmetic_on_host(tag):
     want = g["kpcn_" + tag]
     assert np.array_equal(np.isnan(kp), np.isnan(want))     # NaN exactly where the reference has it (overflowed variance)
     np.testing.assert_allclose(kp, want, rtol=3e-5, atol=2e-6, equal_nan=True)
+
+
+def test_bench_kernel_summary_from_profile():
+    """bench.summarize_kernels: the `roofline` / `roofline_more` / `kernels` entries of the bench line from a profile
+    of the eager timed pass.  Fed with the per-call table of the final round-1 bench (profiles/r01final_bench.json)."""
+    import json
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r01final_bench.json")).read().strip().splitlines()[-1])
+    steps = 10
+    prof = {}
+    for name, v in d["kernels"].items():   # (calls, total ms, total work) as lib.profile_stop() returns them
+        ms = v["ms_per_step"] * steps
+        rate = v.get("tflops", 0.0) * 1e12 if "tflops" in v else v.get("gbs", 0.0) * 1e9
+        prof[name] = (v["calls_per_step"] * steps, ms, rate * ms * 1e-3)
+    pk = {"hbm_gbs": 6456.2, "bf16_tflops": 1699.4, "bf16_tflops_sustained": 1433.8}
+    roofline, more, kernels = bench.summarize_kernels(prof, steps, pk, "measured")
+    json.dumps({"roofline": roofline, "roofline_more": more, "kernels": kernels})     # serialisable
+    assert roofline["bound"] == "tensor" and roofline["unit"] == "TFLOP/s" and roofline["peak"] == 1433.8
+    assert abs(roofline["achieved"] - d["kernels"]["conv2d_k5"]["tflops"]) < 1.0
+    assert abs(roofline["frac"] - roofline["achieved"] / 1433.8) < 1e-3 and 0.6 < roofline["frac"] < 0.75
+    assert roofline["launches_per_step"] == 36 and roofline["traffic"] and roofline["traffic"] > 1e6
+    by = {m["kernel"]: m for m in more}
+    ka = by["kernel_apply_fwd_kernel (8 x 92^2 pixels per launch)"]
+    assert ka["bound"] == "hbm" and ka["peak"] == 6456.2 and ka["unit"] == "GB/s"
+    assert abs(by["conv_wgrad_kernel (5x5 layers)"]["achieved"] - d["kernels"]["conv2d_wgrad_k5"]["tflops"]) < 1.0
+    assert abs(by["conv_wgrad_kernel (3x3 layers)"]["achieved"] - d["kernels"]["conv2d_wgrad_k3"]["tflops"]) < 1.0
+    assert all(0.0 < m["frac"] < 1.0 for m in more) and len(more) == 9
+    assert set(kernels) == set(d["kernels"]) and abs(sum(k["share_of_kernel_time"] for k in kernels.values()) - 1.0) < 0.01
+    # an empty profile (no conv launches) must not divide by zero
+    r0, m0, k0 = bench.summarize_kernels({}, steps, pk, "fallback")
+    assert r0["achieved"] == 0.0 and m0 == [] and k0 == {}
