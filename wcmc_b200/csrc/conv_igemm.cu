@@ -18,11 +18,14 @@
 // Every tap's A operand is then just a shifted window of that halo: the UMMA shared-memory
 // descriptor starts at pixel (ky, kx+8t) of the halo and uses the halo row pitch as its
 // stride-byte-offset, so the k*k-fold re-read of the activations never leaves the SM.
-// Weights stream through a 4-stage TMA ring.  Accumulators live in TMEM (double buffered:
-// the epilogue of one region overlaps the MMAs of the next).
+// Weights stream through a TMA ring whose stages carry one tap or a whole kernel row of taps (TPS).  Accumulators
+// live in TMEM (double buffered: the epilogue of one region overlaps the MMAs of the next).
 //
-// Warp roles (224 threads): w0 halo producer | w1 weight producer | w2 TMEM alloc + MMA
-// issuer | w3..w6 epilogue (TMEM -> regs -> bias/act/mask -> global).
+// Warp roles (352 threads): w0 halo producer | w1 weight producer | w2 TMEM alloc + MMA issuer | w3..w10 epilogue
+// (TMEM -> regs -> bias / act / mask / column sums -> global).
+//
+// PAIR = true: the kernel runs as clusters of two CTAs on tcgen05 cta_group::2 (M = 256) -- see decode_item below and
+// DESIGN.md section 5 for why (the shared-memory operand feed, not the tensor pipe, bounds the single-CTA kernel).
 #include "common.cuh"
 
 namespace wcmc {
