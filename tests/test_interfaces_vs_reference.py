@@ -1,0 +1,165 @@
+"""CPU: the drop-in step orchestration (wcmc_b200/dropin/support/interfaces.py) against the REFERENCE's own classes
+(/root/reference/support/interfaces.py: KPCNInterface :80-333, KPCNRefInterface :526-585, KPCNPreInterface :588-750),
+both driven with the same stand-in torch modules (the CUDA kernels are not involved): same losses, same gradients, same
+parameters after the Adam step, same train / eval modes, same validate_batch outputs.  Needs the reference checkout
+(present where the CPU tests run; skipped on the GPU box)."""
+import importlib.util
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+REF = "/root/reference/support/interfaces.py"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not present")
+
+from tests.test_ddp_gloo import _TinyKPCN, _TinyPathNet  # noqa: E402
+
+
+class _TinyManifLoss(torch.nn.Module):
+    """Stand-in for FeatureMSE (a CUDA kernel in the product): same call contract, any channel count."""
+
+    def forward(self, p_buffer, ref):
+        return (p_buffer.mean(1).mean(1, keepdim=True) - ref.mean(1, keepdim=True)).pow(2).mean() + 0.1 * p_buffer.pow(2).mean()
+
+
+@pytest.fixture(scope="module")
+def both():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import _install_stubs
+    _install_stubs()                      # matplotlib.pyplot.imsave -> no-op (interfaces.py:130-137 writes PNGs)
+    from wcmc_b200 import dropin
+    dropin.install()
+    import support.interfaces as ours
+    spec = importlib.util.spec_from_file_location("wcmc_reference_interfaces", REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from support.losses import RelativeMSE
+    return types.SimpleNamespace(ours=ours, ref=ref, RelativeMSE=RelativeMSE)
+
+
+def _models(n_in, llpm, outc=3):
+    torch.manual_seed(0)
+    m = {"dncnn": _TinyKPCN(n_in)}
+    if llpm:
+        m["backbone_diffuse"] = _TinyPathNet(36, outc)
+        m["backbone_specular"] = _TinyPathNet(36, outc)
+    return m
+
+
+def _loss_funcs(both, manif):
+    lf = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+          "l_test": both.RelativeMSE()}
+    if manif:
+        lf["l_manif"] = _TinyManifLoss()
+    return lf
+
+
+def _run(cls, models, lf, batch, **kw):
+    optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-3) for k, m in models.items()}
+    itf = cls(models, optims, lf, types.SimpleNamespace(model_name="t"), **kw)
+    itf.to_train_mode()
+    modes = {k: m.training for k, m in models.items()}
+    itf.preprocess(batch)
+    itf.train_batch(batch)
+    losses = {k: v.clone() for k, v in itf.m_losses.items()}
+    grads = {k: [None if p.grad is None else p.grad.clone() for p in m.parameters()] for k, m in models.items()}
+    params = {k: [p.detach().clone() for p in m.parameters()] for k, m in models.items()}
+    itf.to_eval_mode()
+    with torch.no_grad():
+        rad, pb = itf.validate_batch(batch)
+    return dict(losses=losses, grads=grads, params=params, modes=modes, rad=rad, pb=pb, m_val=itf.m_losses["m_val"].clone(),
+                summary=itf.get_epoch_summary("eval", 1.0))
+
+
+def _same(a, b):
+    assert list(a["losses"]) == list(b["losses"])          # same keys in the same order
+    for k in a["losses"]:
+        torch.testing.assert_close(a["losses"][k], b["losses"][k], rtol=1e-6, atol=1e-8, msg=k)
+    assert a["modes"] == b["modes"]
+    for name in a["params"]:
+        for x, y in zip(a["params"][name], b["params"][name]):
+            torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-8)
+        for x, y in zip(a["grads"][name], b["grads"][name]):
+            assert (x is None) == (y is None), name
+            if x is not None:
+                torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(a["rad"], b["rad"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(a["m_val"], b["m_val"], rtol=1e-6, atol=1e-8)
+    assert abs(a["summary"] - b["summary"]) < 1e-7
+    if a["pb"] is None:
+        assert b["pb"] is None
+    else:
+        assert sorted(a["pb"]) == sorted(b["pb"])
+        for k in a["pb"]:
+            torch.testing.assert_close(a["pb"][k], b["pb"][k], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("cfg", [dict(use_llpm_buf=True, manif_learn=True, disentanglement_option="m11r11"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentanglement_option="m10r01"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentanglement_option="m11r01"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentanglement_option="m10r11"),
+                                 dict(use_llpm_buf=True, manif_learn=False),
+                                 dict(use_llpm_buf=False, manif_learn=False),
+                                 dict(use_llpm_buf=False, manif_learn=False, train_branches=False)],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+def test_kpcn_interface_matches_reference_class(both, cfg):
+    from wcmc_b200.synth import make_batch
+    llpm = cfg["use_llpm_buf"]
+    outc = 4
+    half = cfg.get("disentanglement_option", "m11r11") in ("m10r01", "m11r01")
+    n_in = 34 + (1 + (outc // 2 if half else outc) + 1 if llpm else 0)
+    batch = make_batch(batch=2, spp=2, size=24, seed=3, paths=llpm)
+    kw = dict(cfg, w_manif=0.1)
+    ref = _run(both.ref.KPCNInterface, _models(n_in, llpm, outc), _loss_funcs(both, cfg["manif_learn"]), batch, **kw)
+    ours = _run(both.ours.KPCNInterface, _models(n_in, llpm, outc), _loss_funcs(both, cfg["manif_learn"]), batch, **kw)
+    _same(ours, ref)
+
+
+def test_ref_interface_matches_reference_class(both):
+    from wcmc_b200.synth import make_batch
+    batch = make_batch(batch=2, spp=2, size=24, seed=4, paths=False)
+    ref = _run(both.ref.KPCNRefInterface, _models(37, False), _loss_funcs(both, False), batch)
+    ours = _run(both.ours.KPCNRefInterface, _models(37, False), _loss_funcs(both, False), batch)
+    _same(ours, ref)
+
+
+@pytest.mark.parametrize("manif_learn", [True, False])
+def test_pre_interface_matches_reference_class(both, manif_learn):
+    from wcmc_b200.synth import make_batch
+    batch = make_batch(batch=2, spp=2, size=24, seed=5, paths=True)
+    ref = _run(both.ref.KPCNPreInterface, _models(39, True), _loss_funcs(both, True), batch, manif_learn=manif_learn)
+    ours = _run(both.ours.KPCNPreInterface, _models(39, True), _loss_funcs(both, True), batch, manif_learn=manif_learn)
+    _same(ours, ref)
+    frozen = ["dncnn"] if manif_learn else ["backbone_diffuse", "backbone_specular"]
+    fresh = _models(39, True)
+    for k in frozen:    # the stage's frozen side keeps its initial weights in both implementations
+        for p0, p1 in zip(fresh[k].parameters(), ours["params"][k]):
+            assert torch.equal(p0.detach(), p1)
+
+
+def test_error_behaviour_matches_reference(both):
+    """Constructor assertions and the non-finite-loss exception (interfaces.py:84-95, :255-257)."""
+    lf = _loss_funcs(both, False)
+    for mod in (both.ref, both.ours):
+        with pytest.raises(AssertionError):
+            mod.KPCNInterface({"backbone_diffuse": _TinyPathNet(36, 3)}, {}, lf, None)          # no 'dncnn'
+        with pytest.raises(AssertionError):
+            mod.KPCNInterface({"dncnn": _TinyKPCN(34)}, {}, lf, None, manif_learn=True)         # no backbones
+        with pytest.raises(AssertionError):
+            mod.KPCNInterface({"dncnn": _TinyKPCN(34)}, {}, {"l_recon": lf["l_recon"], "l_test": lf["l_test"]}, None)
+        with pytest.raises(AssertionError):
+            mod.KPCNRefInterface({"dncnn": _TinyKPCN(37)}, {}, lf, None, use_llpm_buf=True)
+    from wcmc_b200.synth import make_batch
+    batch = make_batch(batch=1, spp=2, size=24, seed=6, paths=False)
+    batch["target_diffuse"] = batch["target_diffuse"].clone()
+    batch["target_diffuse"][0, 0, 12, 12] = float("nan")
+    for mod in (both.ref, both.ours):
+        models = _models(34, False)
+        optims = {"optim_dncnn": torch.optim.Adam(models["dncnn"].parameters(), lr=1e-3)}
+        itf = mod.KPCNInterface(models, optims, lf, types.SimpleNamespace(model_name="t"))
+        itf.to_train_mode()
+        itf.preprocess(batch)
+        with pytest.raises(RuntimeError, match="Non-finite loss at train time"):
+            itf.train_batch(batch)
