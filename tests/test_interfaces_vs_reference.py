@@ -163,3 +163,65 @@ def test_error_behaviour_matches_reference(both):
         itf.preprocess(batch)
         with pytest.raises(RuntimeError, match="Non-finite loss at train time"):
             itf.train_batch(batch)
+
+
+def test_train_kpcn_imports_unchanged_against_the_dropin():
+    """`import train_kpcn` (the reference's training script, unmodified) resolves every hot-path import to the drop-in
+    packages (train_kpcn.py:19-33: PathNet, the three losses, KPCNInterface / KPCNRefInterface / KPCNPreInterface,
+    sbmc.KPCN, ttools crop_like) while datasets / utils fall through to the reference checkout.  Own process: the
+    script's imports must not leak into the other tests."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, types
+for name in ("visdom", "kornia"):
+    sys.modules[name] = types.ModuleType(name)
+mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); plt.imsave = lambda *a, **k: None
+mpl.pyplot = plt; sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, %r)
+from wcmc_b200 import dropin
+dropin.install()
+import train_kpcn as T
+import support.interfaces as I, support.networks as N, support.losses as L, sbmc
+drop = dropin.__file__.rsplit("/", 1)[0]
+for obj in (T.KPCNInterface, T.KPCNRefInterface, T.KPCNPreInterface, T.PathNet, T.FeatureMSE, T.GlobalRelativeSimilarityLoss,
+            T.RelativeMSE, T.KPCN, T.crop_like):
+    mod = sys.modules[obj.__module__]
+    assert mod.__file__.startswith(drop), (obj, mod.__file__)
+assert T.MSDenoiseDataset.__module__ == "support.datasets" and sys.modules["support.datasets"].__file__.startswith("/root/reference")
+assert T.BasicArgumentParser.__module__ == "support.utils"
+assert issubclass(T.KPCNRefInterface, T.KPCNInterface) and issubclass(T.KPCNPreInterface, T.KPCNInterface)
+assert callable(T.train_epoch_kpcn) and callable(T.validate_kpcn) and callable(T.train)
+print("OK")
+''' % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-500:], r.stderr[-2000:])
+
+
+def test_dropin_utils_match_reference_utils():
+    """support/utils.py of the drop-in shadows the reference's: same CLI flags on BasicArgumentParser (utils.py:70-100),
+    same tone mappers (:44-67), same crop rule (:24-42)."""
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("wcmc_reference_utils", "/root/reference/support/utils.py")
+    ru = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ru)
+    from wcmc_b200 import dropin
+    dropin.install()
+    import support.utils as du
+
+    def flags(parser):
+        return {a.dest: (tuple(a.option_strings), a.default, getattr(a, "type", None), type(a).__name__)
+                for a in parser._actions}
+    assert flags(du.BasicArgumentParser()) == flags(ru.BasicArgumentParser())
+    g = np.random.default_rng(0)
+    c = g.random((5, 7, 3)).astype(np.float32) * 4
+    np.testing.assert_allclose(du.ToneMap(c), ru.ToneMap(c), rtol=1e-6)
+    np.testing.assert_allclose(du.ToneMap(c, 2.5), ru.ToneMap(c, 2.5), rtol=1e-6)
+    np.testing.assert_allclose(du.LinearToSrgb(c), ru.LinearToSrgb(c))
+    b = (g.random((2, 3, 5, 7)).astype(np.float32) - 0.2) * 4
+    np.testing.assert_allclose(du.ToneMapBatch(b), ru.ToneMapBatch(b), rtol=1e-6)
+    assert not np.shares_memory(du.ToneMap(c), c)       # the reference copies, too
+    for shape, tgt in (((1, 1, 128, 128), (1, 1, 92, 92)), ((2, 3, 7, 9), (2, 3, 4, 4)), ((1, 2, 5, 5), (1, 2, 5, 5))):
+        src = torch.arange(float(np.prod(shape))).reshape(shape)
+        assert torch.equal(du.crop_like(src, torch.empty(tgt)), ru.crop_like(src, torch.empty(tgt)))

@@ -24,3 +24,32 @@ class BasicArgumentParser(argparse.ArgumentParser):
         add("--num_samples", type=int, default=8, help="number of samples to display")
         add("--save", type=str, default="./weights", help="directory to save the model")
         add("--overfit", action="store_true", help="launch the overfitting test")
+
+
+# ---- display helpers the reference's own (fall-through) modules import from `support.utils` -------------------
+# support/datasets.py:12 does `from support.utils import ToneMap, LinearToSrgb`; with this drop-in first on sys.path
+# that import lands here, so the three numpy tone mappers of utils.py:44-67 are provided as well (host-side display
+# code, never on the hot path).
+def _luminance_scale(c, channel_axis, limit):
+    import numpy as np
+    r, g, b = (np.take(c, i, axis=channel_axis) for i in range(3))
+    return 1.0 + (0.2126 * r + 0.7152 * g + 0.0722 * b) / limit
+
+
+def ToneMap(c, limit=1.5):
+    """(W,H,3) linear radiance -> Reinhard-style compression by the pixel's luminance (utils.py:44-51)."""
+    import numpy as np
+    return c / np.expand_dims(_luminance_scale(c, 2, limit), 2)
+
+
+def LinearToSrgb(c):
+    """Gamma 2.2 + clip to [0,1] (utils.py:53-56)."""
+    import numpy as np
+    return np.clip(c ** (1.0 / 2.2), 0.0, 1.0)
+
+
+def ToneMapBatch(c):
+    """(B,3,W,H): ToneMap with limit 1.5, negative values clipped, then LinearToSrgb (utils.py:58-67)."""
+    import numpy as np
+    col = np.clip(c / np.expand_dims(_luminance_scale(c, 1, 1.5), 1), 0, None)
+    return LinearToSrgb(col)
