@@ -225,3 +225,28 @@ def test_dropin_utils_match_reference_utils():
     for shape, tgt in (((1, 1, 128, 128), (1, 1, 92, 92)), ((2, 3, 7, 9), (2, 3, 4, 4)), ((1, 2, 5, 5), (1, 2, 5, 5))):
         src = torch.arange(float(np.prod(shape))).reshape(shape)
         assert torch.equal(du.crop_like(src, torch.empty(tgt)), ru.crop_like(src, torch.empty(tgt)))
+
+
+def test_image_metrics_match_reference_losses():
+    """RelativeMSE / SMAPE / TonemappedMSE / TonemappedRelativeMSE of the drop-in against the reference's own
+    classes (support/losses.py:245-320), values and gradients (pure torch on any device)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import _install_stubs
+    _install_stubs()
+    spec = importlib.util.spec_from_file_location("wcmc_reference_losses", "/root/reference/support/losses.py")
+    rl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rl)
+    from wcmc_b200 import dropin
+    dropin.install()
+    import support.losses as dl
+    g = torch.Generator().manual_seed(2)
+    im = (torch.rand(2, 3, 9, 11, generator=g) * 4 - 0.5)
+    ref = torch.rand(2, 3, 9, 11, generator=g) * 4
+    for name in ("RelativeMSE", "SMAPE", "TonemappedMSE", "TonemappedRelativeMSE"):
+        a = im.clone().requires_grad_(True)
+        b = im.clone().requires_grad_(True)
+        la, lb = getattr(dl, name)()(a, ref), getattr(rl, name)()(b, ref)
+        torch.testing.assert_close(la, lb, rtol=1e-6, atol=1e-8, msg=name)
+        la.backward()
+        lb.backward()
+        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-9, msg=name)

@@ -160,3 +160,46 @@ class RelativeMSE(torch.nn.Module):
 
     def forward(self, im, ref):
         return 0.5 * torch.mean((im - ref) ** 2 / (ref ** 2 + self.eps))
+
+
+# ---- the remaining image metrics of support/losses.py (used by train_sbmc.py / train_lbmc.py and as test metrics):
+# a handful of elementwise torch ops on (B,3,h,w) images, kept so that `from support.losses import ...` of any
+# reference script resolves against this package -------------------------------------------------------------
+def _tonemap(im):
+    """Reinhard: clamp(im, 0) / (1 + clamp(im, 0))   (losses.py:234-242)."""
+    im = torch.clamp(im, min=0)
+    return im / (1 + im)
+
+
+class SMAPE(torch.nn.Module):
+    """mean(|im - ref| / (eps + |im| + |ref|)), denominator detached   (losses.py:267-284)."""
+
+    def __init__(self, eps=1e-2):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, im, ref):
+        return (torch.abs(im - ref) / (self.eps + im.detach().abs() + ref.detach().abs())).mean()
+
+
+class TonemappedMSE(torch.nn.Module):
+    """0.5 * mean((T(im) - T(ref))^2)   (losses.py:287-302)."""
+
+    def __init__(self, eps=1e-2):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, im, ref):
+        return 0.5 * torch.mean((_tonemap(im) - _tonemap(ref)) ** 2)
+
+
+class TonemappedRelativeMSE(torch.nn.Module):
+    """RelativeMSE on Reinhard-tonemapped images   (losses.py:305-320)."""
+
+    def __init__(self, eps=1e-2):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, im, ref):
+        im, ref = _tonemap(im), _tonemap(ref)
+        return 0.5 * torch.mean((im - ref) ** 2 / (ref ** 2 + self.eps))
