@@ -250,3 +250,74 @@ def test_image_metrics_match_reference_losses():
         la.backward()
         lb.backward()
         torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-9, msg=name)
+
+
+@pytest.mark.parametrize("flags", ["--train_branches",
+                                   "--use_llpm_buf --manif_learn --manif_loss FMSE --train_branches --pnet_out_size 3",
+                                   "--use_llpm_buf --manif_learn --manif_loss GRS --train_branches --pnet_out_size 4 "
+                                   "--disentangle m10r01",
+                                   "--kpcn_ref --train_branches",
+                                   "--kpcn_pre --use_llpm_buf --manif_learn --manif_loss FMSE --train_branches"])
+def test_train_kpcn_init_model_against_the_dropin(flags, tmp_path):
+    """The reference's own `train_kpcn.init_model` (train_kpcn.py:194-338, unmodified) builds its models, optimisers,
+    losses and interface from the drop-in packages: constructor signatures, `str(model)`, parameters(), state_dict
+    round trip through the checkpoint layout of train_kpcn.train (:108-121).  `.cuda()` is made a no-op (no GPU here;
+    nothing is run forward)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, types, os
+for name in ("visdom", "kornia"):
+    sys.modules[name] = types.ModuleType(name)
+mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); plt.imsave = lambda *a, **k: None
+mpl.pyplot = plt; sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, %r)
+from wcmc_b200 import dropin
+dropin.install()
+import torch
+torch.nn.Module.cuda = lambda self, *a, **k: self
+torch.cuda.device_count = lambda: 1
+import train_kpcn as T
+p = T.BasicArgumentParser()
+# the flags train_kpcn.py adds under __main__ (train_kpcn.py:386-427)
+p.add_argument('--desc', type=str, default="t"); p.add_argument('--lr_dncnn', type=float, default=1e-4)
+p.add_argument('--lr_pnet', type=float, nargs='+', default=[0.0001]); p.add_argument('--lr_ckpt', action='store_true')
+p.add_argument('--best_err', type=float); p.add_argument('--pnet_out_size', type=int, nargs='+', default=[3])
+p.add_argument('--manif_loss', type=str); p.add_argument('--train_branches', action='store_true')
+p.add_argument('--use_llpm_buf', action='store_true'); p.add_argument('--manif_learn', action='store_true')
+p.add_argument('--w_manif', type=float, nargs='+', default=[0.1]); p.add_argument('--disentangle', type=str, default='m11r11')
+p.add_argument('--single_gpu', action='store_true'); p.add_argument('--device_id', type=int, default=0)
+p.add_argument('--kpcn_ref', action='store_true'); p.add_argument('--kpcn_pre', action='store_true')
+p.add_argument('--not_save', action='store_true'); p.add_argument('--local', action='store_true')
+args = p.parse_args(%r.split() + ["--single_gpu", "--save", %r, "--model_name", "m"])
+llpm = args.use_llpm_buf
+ds = types.SimpleNamespace(dncnn_in_size=34 + (3 + 2 if llpm else 0), pnet_in_size=36 if llpm else 0, pnet_out_size=3)
+interfaces, params = T.init_model({"train": ds}, args)
+assert len(interfaces) == 1
+itf = interfaces[0]
+want = "KPCNRefInterface" if args.kpcn_ref else ("KPCNPreInterface" if args.kpcn_pre else "KPCNInterface")
+assert type(itf).__name__ == want and type(itf).__module__ == "support.interfaces"
+assert set(itf.models) == ({"dncnn", "backbone_diffuse", "backbone_specular"} if llpm else {"dncnn"})
+assert all("optim_" + k in itf.optims for k in itf.models)
+n_first = next(itf.models["dncnn"].parameters()).shape[1]
+half = args.disentangle in ("m10r01", "m11r01")
+exp = 34 + 3 if args.kpcn_ref else (34 + 1 + (args.pnet_out_size[0] // 2 if half else args.pnet_out_size[0]) + 1 if llpm else 34)
+assert n_first == exp, (n_first, exp)
+itf.to_train_mode()
+# the checkpoint train_kpcn.train() writes, and the way init_model reads it back
+state = {"model": str(itf.models["dncnn"]), "optims": itf.optims, "best_err": itf.best_err}
+for name in itf.models:
+    state["state_dict_" + name] = itf.models[name].state_dict()
+fn = os.path.join(args.save, "latest_m.pth")
+torch.save(state, fn)
+ck = torch.load(fn, weights_only=False)
+for name in itf.models:
+    itf.models[name].load_state_dict(ck["state_dict_" + name])
+    ck["optims"]["optim_" + name].state_dict()
+if llpm:
+    assert str(itf.models["backbone_diffuse"]) == "PathNet i36in64o%%d" %% args.pnet_out_size[0]
+print("OK")
+''' % (root, flags, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-800:], r.stderr[-2500:])
