@@ -321,3 +321,49 @@ print("OK")
 ''' % (root, flags, str(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-800:], r.stderr[-2500:])
+
+
+def test_train_kpcn_train_loop_drives_the_dropin_interface(tmp_path):
+    """The reference's own `train_kpcn.train` (train_kpcn.py:87-160: epoch loop, checkpoint dicts, validation, best-error
+    bookkeeping) driving the drop-in KPCNInterface for one epoch.  Stand-in torch models replace the CUDA-backed ones
+    (no GPU here) and Tensor.cuda is a no-op; what is checked is the interface contract the loop relies on."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, types, os
+for name in ("visdom", "kornia"):
+    sys.modules[name] = types.ModuleType(name)
+mpl = types.ModuleType("matplotlib"); plt = types.ModuleType("matplotlib.pyplot"); plt.imsave = lambda *a, **k: None
+mpl.pyplot = plt; sys.modules["matplotlib"] = mpl; sys.modules["matplotlib.pyplot"] = plt
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, %r)
+from wcmc_b200 import dropin
+dropin.install()
+import torch
+torch.Tensor.cuda = lambda self, *a, **k: self
+import train_kpcn as T
+from tests.test_ddp_gloo import _TinyKPCN, _TinyPathNet
+from tests.test_interfaces_vs_reference import _TinyManifLoss
+from wcmc_b200.synth import make_batch
+torch.manual_seed(0)
+models = {"dncnn": _TinyKPCN(39), "backbone_diffuse": _TinyPathNet(36, 3), "backbone_specular": _TinyPathNet(36, 3)}
+optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-3) for k, m in models.items()}
+lf = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(), "l_test": T.RelativeMSE(),
+      "l_manif": _TinyManifLoss()}
+args = types.SimpleNamespace(desc="t", start_epoch=0, num_epoch=2, model_name="m", visual=False, val_epoch=1, not_save=False,
+                             save=%r)
+itf = T.KPCNInterface(models, optims, lf, args, use_llpm_buf=True, manif_learn=True, w_manif=0.1, train_branches=True)
+loaders = {"train": [make_batch(batch=2, spp=2, size=24, seed=s) for s in (1, 2)],
+           "val": [make_batch(batch=2, spp=2, size=24, seed=3)]}
+w0 = [p.detach().clone() for p in models["dncnn"].parameters()]
+T.train([itf], loaders, {"data_device": 0}, args)
+assert itf.iters == 4 and itf.best_err < 1e10
+assert any(not torch.equal(a, b) for a, b in zip(w0, models["dncnn"].parameters()))
+for fn in ("latest_m.pth", "m.pth"):
+    ck = torch.load(os.path.join(args.save, fn), weights_only=False)
+    assert ck["start_epoch"] in (1, 2) and ck["model"] == str(models["dncnn"]) and "state_dict_backbone_specular" in ck
+    assert abs(ck["best_err"] - itf.best_err) < 1e-12 or fn == "latest_m.pth"
+print("OK")
+''' % (root, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-1500:], r.stderr[-2500:])
