@@ -8,6 +8,7 @@ children only HOLD the parameters (and torch's weight-norm reparametrisation); t
 called.  CUDA only - there is no CPU fallback.
 """
 import math
+import threading
 
 import torch
 import torch.nn as nn
@@ -49,12 +50,14 @@ def _make_conv(cin, cout, ksize, padding, gain_of, weight_norm):
     return conv
 
 
-_WN_OVERRIDE = None   # {id(conv): effective weight} while batched_weight_norm() is active
+_WN = threading.local()   # .override = {id(conv): effective weight} while batched_weight_norm() is active (per thread:
+                          # nn.DataParallel runs one replica per Python thread)
 
 
 def _effective_weight(conv):
-    if _WN_OVERRIDE is not None and id(conv) in _WN_OVERRIDE:
-        return _WN_OVERRIDE[id(conv)]
+    override = getattr(_WN, "override", None)
+    if override is not None and id(conv) in override:
+        return override[id(conv)]
     if hasattr(conv, "weight_g"):
         return torch._weight_norm(conv.weight_v, conv.weight_g, 0)
     return conv.weight
@@ -69,20 +72,19 @@ class batched_weight_norm:
         self.convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and hasattr(m, "weight_g")]
 
     def __enter__(self):
-        global _WN_OVERRIDE
-        self.prev = _WN_OVERRIDE
+        self.prev = getattr(_WN, "override", None)
         if self.convs and self.convs[0].weight_v.is_cuda:
             flat = []
             for c in self.convs:
                 flat += [c.weight_v, c.weight_g]
             ws = ops.BatchedWeightNormFn.apply(*flat)
-            _WN_OVERRIDE = dict(self.prev or {})
-            _WN_OVERRIDE.update({id(c): w for c, w in zip(self.convs, ws)})
+            merged = dict(self.prev or {})
+            merged.update({id(c): w for c, w in zip(self.convs, ws)})
+            _WN.override = merged
         return self
 
     def __exit__(self, *exc):
-        global _WN_OVERRIDE
-        _WN_OVERRIDE = self.prev
+        _WN.override = self.prev
         return False
 
 
