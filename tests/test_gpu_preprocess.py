@@ -1,16 +1,20 @@
 """GPU parity of the N3 preprocessing kernels (wcmc_b200/preprocess.py) against the reference-generated vectors.
 
-GATED: the kernels were written after round 1's GPU budget was spent and have never run on a GPU; they are not on the
-product path.  Run with WCMC_UNVALIDATED=1 (first thing in round 2), then drop the gate."""
+The kernels were written after round 1's GPU budget was spent: their per-element arithmetic is checked on the CPU
+(tests/test_host_logic.py::test_preprocess_kernel_arithmetic_on_host) but they had never been launched when the round
+closed, and nothing on the product path calls them.  Until a GPU run has been seen green the tests are non-strict
+xfail -- they RUN (this file is the last GPU file of the suite), a pass is reported as XPASS, a failure cannot turn the
+tier red.  WCMC_UNVALIDATED=1 makes them ordinary tests (tools/round2_first.sh); drop the marker once green."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("WCMC_UNVALIDATED") != "1",
-                                 reason="N3 kernels not yet validated on a GPU (set WCMC_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
+if os.environ.get("WCMC_UNVALIDATED") != "1":
+    pytestmark.append(pytest.mark.xfail(reason="first GPU run of the N3 preprocessing kernels (never launched in round 1)",
+                                        strict=False))
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
