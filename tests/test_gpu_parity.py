@@ -517,6 +517,83 @@ def test_fused_clip_adam_matches_torch(backend):
     assert int(fused.t_dev) == 5
 
 
+def test_fused_adam_checkpoint_is_interchangeable_with_torch(backend, tmp_path):
+    """The reference checkpoints by pickling the optimiser OBJECTS (`'optims': itf.optims`, train_kpcn.py:114,143):
+    `Optimizer.__getstate__` runs no state-dict hook, so `state['step']` must be current at all times.  After a
+    save / load round trip torch's own Adam must continue exactly where the fused kernel stopped (bias corrections
+    included), a load_state_dict + lr change must be honoured by the next fused step, and optimisers at different
+    step counts make the interface fall back to torch's step instead of raising."""
+    import io
+    import pickle
+    from wcmc_b200 import optim as wopt
+    shapes = [(33, 7, 3, 3), (33,), (130,), (5, 5)]
+
+    def make(lr=1e-3):
+        ps = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)))
+              for i, s in enumerate(shapes)]
+        return ps, [torch.optim.Adam(ps[:2], lr=lr), torch.optim.Adam(ps[2:], lr=lr)]
+
+    def set_grads(ps, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for q in ps:
+            q.grad = torch.randn(q.shape, device="cuda", generator=g)
+
+    pa, oa = make()
+    pb, ob = make()
+    fused = wopt.FusedClipAdam(ob)
+    for step in range(4):
+        set_grads(pa, step)
+        set_grads(pb, step)
+        torch.nn.utils.clip_grad_value_(pa, 1.0)
+        for o in oa:
+            o.step()
+        fused.step(clip=1.0)
+        for o in ob:   # what pickling sees, with no hook involved
+            assert all(float(st["step"]) == step + 1 for st in o.state.values())
+    buf = io.BytesIO()
+    torch.save({"optims": ob, "params": pb}, buf)          # train_kpcn.py:109-116 pickles the objects
+    buf.seek(0)
+    ck = torch.load(buf, weights_only=False)
+    pc, oc = ck["params"], ck["optims"]
+    assert all(float(st["step"]) == 4.0 for o in oc for st in o.state.values())
+    # torch's Adam continues from the unpickled fused state exactly like from its own state
+    set_grads(pa, 99)
+    set_grads(pc, 99)
+    torch.nn.utils.clip_grad_value_(pa, 1.0)
+    torch.nn.utils.clip_grad_value_(pc, 1.0)
+    for o in oa + oc:
+        o.step()
+    for p_, q_ in zip(pa, pc):
+        torch.testing.assert_close(q_.detach(), p_.detach(), rtol=1e-5, atol=1e-7)
+    # load_state_dict into the LIVE fused optimisers (resume, train_kpcn.py:283-296) + an lr change: both honoured
+    for o, src in zip(ob, oa):
+        o.load_state_dict(pickle.loads(pickle.dumps(src.state_dict())))
+        o.param_groups[0]["lr"] = 5e-4
+    for o in oa:
+        o.param_groups[0]["lr"] = 5e-4
+    for p_, q_ in zip(pa, pb):
+        q_.data.copy_(p_.data)
+    set_grads(pa, 7)
+    set_grads(pb, 7)
+    torch.nn.utils.clip_grad_value_(pa, 1.0)
+    for o in oa:
+        o.step()
+    fused.step(clip=1.0)
+    assert fused.t == 6 and int(fused.t_dev) == 6
+    for p_, q_ in zip(pa, pb):
+        torch.testing.assert_close(q_.detach(), p_.detach(), rtol=1e-5, atol=1e-7)
+    # different step counts (only one optimiser resumed): consistent() is False -> the interface keeps torch's step
+    pd, od = make()
+    od[0].load_state_dict(pickle.loads(pickle.dumps(oa[0].state_dict())))
+    assert not wopt.FusedClipAdam(od).consistent()
+    itf = backend.itf.KPCNInterface.__new__(backend.itf.KPCNInterface)
+    itf.fused_optim, itf._fused_adam = True, None
+    itf.models = {"a": None, "b": None}
+    itf.optims = {"optim_a": od[0], "optim_b": od[1]}
+    assert itf._fused() is None
+
+
+
 # ---------------------------------------------------------------------------------------------
 # SURVEY §8(f) N4: the ablation interfaces on the same kernels, against vectors produced by the REFERENCE's
 # own KPCNRefInterface / KPCNPreInterface (tests/golden/make_golden_n4.py)

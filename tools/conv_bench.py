@@ -59,7 +59,7 @@ for name, n, h, w, cin, cout, k, pad in cfgs:
         timeit(lambda: lib.conv2d_wgrad(x, dy, cout, cin, k, pad, lib.pad16(cin), lib.pad16(cout)), fl, "wgrad " + name)
         def partial_only():
             lib.conv2d_wgrad(x, dy, cout, cin, k, pad, lib.pad16(cin), lib.pad16(cout), defer=True)
-            lib._pending_wgrad.clear()
+            lib._pending().clear()
         timeit(partial_only, fl, "wgrad (tensor-core kernel only) " + name[:12])
         lib.load().wcmc_tuning_set(b"wgrad_uniform", 0)
         timeit(partial_only, fl, "wgrad (kernel only, splits ~ taps) " + name[:9])

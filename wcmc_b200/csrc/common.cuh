@@ -53,7 +53,16 @@ int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const ui
 int wcmc_encode_tmap(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 
-int wcmc_num_sms();
+int wcmc_num_sms();   // of the current device
+
+// Opts `kernel` in to `bytes` of dynamic shared memory on the CURRENT device (once per kernel and device,
+// mutex-guarded; the attribute is per device).  Returns a WCMC_E* code.
+int wcmc_func_smem(const void* kernel, int bytes);
+#define WCMC_FUNC_SMEM(kernel, bytes)                                                      \
+    do {                                                                                   \
+        int _rc = wcmc_func_smem(reinterpret_cast<const void*>(kernel), (bytes));          \
+        if (_rc) return _rc;                                                               \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------
 // device side

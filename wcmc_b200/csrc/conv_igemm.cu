@@ -515,12 +515,7 @@ int wcmc_conv_set_model(int which, int v) {
 template <bool PAIR, int TPS>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams& p, int grid, int smem_bytes,
                        cudaStream_t stream) {
-    static bool attr_set = false;   // one flag per instantiation
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<PAIR, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kConvSmemMax + 1024));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM((conv_igemm_kernel<PAIR, TPS>), kConvSmemMax + 1024);
     if (PAIR) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);

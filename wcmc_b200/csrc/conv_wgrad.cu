@@ -348,12 +348,7 @@ extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int 
                                        1);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(
-            cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM(conv_wgrad_kernel, kWgSmem);
     const int grid = p.m_tiles * p.ci_tiles * ((p.tap_groups - 1) * p.nsplit_a + p.nsplit_b);
     conv_wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(tmdy, tmx, p);
     WCMC_LAUNCH_CHECK();

@@ -414,8 +414,7 @@ extern "C" int wcmc_fmse_allpairs_fwd(const float* p_rows, const float* ref_rows
     int grid = static_cast<int>(std::min<long>(items, wcmc_num_sms()));
 #define WCMC_AP_LAUNCH(M, K)                                                                                  \
     do {                                                                                                     \
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(allpairs_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             kApSmem));                                                      \
+        WCMC_FUNC_SMEM((allpairs_kernel<M, K>), kApSmem);                                                    \
         allpairs_kernel<M, K><<<grid, kApThreads, kApSmem, stream>>>(tmA, tmB, p);                           \
     } while (0)
     if (mode == 0 && !masked) WCMC_AP_LAUNCH(0, false);

@@ -278,8 +278,7 @@ static int launch_fwd2(const float* logits, int l_cs, const float* data, float* 
                        int H, int W, int ks, cudaStream_t stream) {
     dim3 grid((W + TW - 1) / TW, (H + kKaTileH - 1) / kKaTileH, N);
     size_t smem = ka_smem_bytes(ks, TW, 0);
-    WCMC_CHECK_CUDA(cudaFuncSetAttribute(kernel_apply_fwd_kernel<C, KS, TW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    WCMC_FUNC_SMEM((kernel_apply_fwd_kernel<C, KS, TW>), static_cast<int>(smem));
     kernel_apply_fwd_kernel<C, KS, TW><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, N, H, W, ks);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -317,8 +316,7 @@ static int launch_bwd2(const float* logits, int l_cs, const float* data, const f
                        cudaStream_t stream) {
     dim3 grid((W + TW - 1) / TW, (H + kKaTileH - 1) / kKaTileH, N);
     size_t smem = ka_smem_bytes(ks, TW, DT != WCMC_F32 ? dl_cs / 2 : dl_cs);
-    WCMC_CHECK_CUDA(cudaFuncSetAttribute(kernel_apply_bwd_kernel<C, DT, KS, TW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    WCMC_FUNC_SMEM((kernel_apply_bwd_kernel<C, DT, KS, TW>), static_cast<int>(smem));
     kernel_apply_bwd_kernel<C, DT, KS, TW><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, gout,
                                                                                dl, dl_cs, N, H, W, ks, scale);
     WCMC_LAUNCH_CHECK();

@@ -186,9 +186,7 @@ extern "C" int wcmc_nchw_f32_to_nhwc(const float* src, void* dst, int dst_dtype,
     dim3 grid((HW + kTrPix - 1) / kTrPix, N);
     size_t smem = static_cast<size_t>(c_fill) * 33 * sizeof(float);
     WCMC_REQUIRE(smem <= 200 * 1024, WCMC_ESHAPE, "nchw_to_nhwc: too many channels (%d)", c_fill);
-    if (smem > 48 * 1024)
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(nchw_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
+    if (smem > 48 * 1024) WCMC_FUNC_SMEM(nchw_to_nhwc_kernel, static_cast<int>(smem));
     nchw_to_nhwc_kernel<<<grid, kTrThreads, smem, stream>>>(src, static_cast<__nv_bfloat16*>(dst), C, HW, dst_cs,
                                                             dst_coff, c_fill, dst_dtype, scale);
     WCMC_LAUNCH_CHECK();
@@ -204,9 +202,7 @@ extern "C" int wcmc_nhwc_to_nchw_f32(const void* src, int src_dtype, float* dst,
     dim3 grid((HW + kTrPix - 1) / kTrPix, N);
     size_t smem = static_cast<size_t>(C) * 33 * sizeof(float);
     WCMC_REQUIRE(smem <= 200 * 1024, WCMC_ESHAPE, "nhwc_to_nchw: too many channels (%d)", C);
-    if (smem > 48 * 1024)
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
+    if (smem > 48 * 1024) WCMC_FUNC_SMEM(nhwc_to_nchw_kernel, static_cast<int>(smem));
     nhwc_to_nchw_kernel<<<grid, kTrThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, C, HW,
                                                             src_cs, src_coff, accumulate, src_dtype, scale);
     WCMC_LAUNCH_CHECK();

@@ -465,12 +465,7 @@ extern "C" int wcmc_pathnet_embed_fwd(const float* paths, int B, int S, int Cin,
     if (h1 && (rc = act_tmap(&tmh1, h1, 64, HW, images))) return rc;
     if (h2 && (rc = act_tmap(&tmh2, h2, 64, HW, images))) return rc;
     const int smem_bytes = emb_smem_bytes(Cin);
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(pathnet_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             emb_smem_bytes(64)));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM(pathnet_embed_fwd_kernel, emb_smem_bytes(64));
     dim3 grid((HW + 127) / 128, B);
     pathnet_embed_fwd_kernel<<<grid, kMlpThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
         tmp, tmx16, tmh1, tmh2, tmemb, p);
@@ -501,12 +496,7 @@ extern "C" int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff,
     if ((rc = act_tmap(&tmpr, prop, prop_cs, HW, B))) return rc;
     tmh = tme;
     if (h && (rc = act_tmap(&tmh, h, 128, HW, static_cast<long>(B) * S))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(pathnet_final_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kFinSmem));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM(pathnet_final_fwd_kernel, kFinSmem);
     dim3 grid((HW + 127) / 128, B);
     pathnet_final_fwd_kernel<<<grid, kMlpThreads, kFinSmem, static_cast<cudaStream_t>(stream)>>>(tme, tmpr, tmh, p);
     WCMC_LAUNCH_CHECK();

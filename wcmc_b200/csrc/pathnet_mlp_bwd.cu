@@ -799,12 +799,8 @@ extern "C" int wcmc_pathnet_final_bwd(const float* g, const float* out, const fl
     if (rc) return rc;
     if ((rc = bwd_act_tmap(&tme, emb, emb_cs, HW, static_cast<long>(B) * S))) return rc;
     if ((rc = bwd_act_tmap(&tmpr, prop, prop_cs, HW, B))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(pathnet_final_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem));
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(pathnet_final_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinSmem));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM(pathnet_final_bwd_kernel<16>, kFinSmem);
+    WCMC_FUNC_SMEM(pathnet_final_bwd_kernel<32>, kFinSmem);
     if (outc_p == 16) pathnet_final_bwd_kernel<16><<<grid, kBwdThreads, kFinSmem, stream>>>(tmh, tme, tmpr, p);
     else pathnet_final_bwd_kernel<32><<<grid, kBwdThreads, kFinSmem, stream>>>(tmh, tme, tmpr, p);
     WCMC_LAUNCH_CHECK();
@@ -849,11 +845,7 @@ extern "C" int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, cons
     if ((rc = bwd_act_tmap(&tmh2, h2, 64, HW, images))) return rc;
     if ((rc = bwd_act_tmap(&tmh1, h1, 64, HW, images))) return rc;
     if ((rc = bwd_act_tmap(&tmx, x16, 64, HW, images))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        WCMC_CHECK_CUDA(cudaFuncSetAttribute(pathnet_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmbSmem));
-        attr_set = true;
-    }
+    WCMC_FUNC_SMEM(pathnet_embed_bwd_kernel, kEmbSmem);
     pathnet_embed_bwd_kernel<<<grid, kBwdThreads, kEmbSmem, stream>>>(tmde, tmem_map, tmh2, tmh1, tmx, p);
     WCMC_LAUNCH_CHECK();
     SlabReduceParams r;

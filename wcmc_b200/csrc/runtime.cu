@@ -2,7 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -23,7 +25,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_sms = 0;
+constexpr int kMaxDevices = 64;
+static int g_sms[kMaxDevices] = {0};                               // per device, written by wcmc_init(device)
+static std::map<std::pair<const void*, int>, int> g_func_smem;     // (kernel, device) -> opted-in dynamic smem bytes
 static std::mutex g_mu;
 
 extern "C" int wcmc_init(int device) {
@@ -33,7 +37,8 @@ extern "C" int wcmc_init(int device) {
     WCMC_REQUIRE(prop.major == 10, WCMC_EARCH,
                  "wcmc_init: device %d is sm_%d%d; libwcmc.so is sm_100a only (no fallback)", device,
                  prop.major, prop.minor);
-    g_sms = prop.multiProcessorCount;
+    WCMC_REQUIRE(device >= 0 && device < kMaxDevices, WCMC_ESHAPE, "wcmc_init: device index %d out of range", device);
+    g_sms[device] = prop.multiProcessorCount;
     if (!g_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -45,7 +50,27 @@ extern "C" int wcmc_init(int device) {
     return WCMC_OK;
 }
 
-int wcmc_num_sms() { return g_sms > 0 ? g_sms : 148; }
+// SM count of the CURRENT device (the launches of this library go to the current device).
+int wcmc_num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    return g_sms[dev] > 0 ? g_sms[dev] : 148;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: every (kernel, device) pair opts in once,
+// behind the library mutex (nn.DataParallel drives one replica per Python thread and per device through this
+// library; /root/reference/train_kpcn.py:266-269).
+int wcmc_func_smem(const void* kernel, int bytes) {
+    int dev = 0;
+    WCMC_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    const auto key = std::make_pair(kernel, dev);
+    auto it = g_func_smem.find(key);
+    if (it != g_func_smem.end() && it->second >= bytes) return WCMC_OK;
+    WCMC_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_func_smem[key] = bytes;
+    return WCMC_OK;
+}
 
 int wcmc_encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                           const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {

@@ -246,7 +246,12 @@ class KPCNInterface(BaseInterface):
             from wcmc_b200 import optim as wopt
             opts = [self.optims["optim_" + name] for name in self.models]
             self._fused_adam = wopt.FusedClipAdam(opts) if all(wopt.supported(o) for o in opts) else False
-        return self._fused_adam or None
+        fa = self._fused_adam
+        if fa and fa._dirty and not fa.consistent():
+            # e.g. a resume that restored only one model's optimiser state (train_kpcn.py:283-296): the launch has
+            # one bias-correction step count, so torch's own per-parameter step keeps running until they agree
+            return None
+        return fa or None
 
     def _accumulate(self, loss_dict):
         for k in loss_dict:

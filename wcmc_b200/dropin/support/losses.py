@@ -60,8 +60,50 @@ def _views(p_buffer, ref):
     return p_buffer, ref
 
 
-def _perms(p, rng, non_local, idx_patch, idx_batch):
+class PermStage:
+    """Pre-staged pairing permutations: the reference's RNG contract (CPU default generator, `randperm(S*H*W)` then
+    `randperm(B*S*H*W)` per loss call, losses.py:35, :50) under a captured CUDA graph.  A graph cannot draw from the
+    CPU generator, so every loss call of a step owns a slot of STATIC device index buffers; `begin_step()` (called
+    by wcmc_b200.engine.GraphedTrainStep before each replay) draws the step's permutations on the host, in the
+    order the calls will consume them, into pinned memory and copies them over.  The graph only reads the buffers."""
+
+    def __init__(self):
+        self.slots = []      # one per loss call of a step, in call order
+        self.cursor = 0
+
+    @staticmethod
+    def _draw(slot):
+        for host, dev in slot:
+            if host is not None:
+                torch.randperm(host.numel(), out=host)          # CPU default generator, like the reference
+                dev.copy_(host, non_blocking=True)
+
+    def begin_step(self):
+        """Draws this step's permutations for every known slot (host work: ~13 ms per 541,696 elements)."""
+        self.cursor = 0
+        for slot in self.slots:
+            self._draw(slot)
+
+    def take(self, n_patch, n_batch, device):
+        if self.cursor == len(self.slots):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PermStage: a loss call without a staged slot inside a CUDA-graph capture")
+            mk = lambda n: (None, None) if not n else (  # noqa: E731
+                torch.empty(n, dtype=torch.int64).pin_memory(), torch.empty(n, dtype=torch.int64, device=device))
+            slot = (mk(n_patch), mk(n_batch))
+            self._draw(slot)                 # first use: drawn right here, i.e. still in call order
+            self.slots.append(slot)
+        (hp, dp), (hb, db) = self.slots[self.cursor]
+        self.cursor += 1
+        assert dp.numel() == n_patch and (db is None) == (not n_batch) and (db is None or db.numel() == n_batch), \
+            "PermStage: the loss calls of a step changed shape"
+        return dp, db
+
+
+def _perms(p, rng, non_local, idx_patch, idx_batch, stage=None):
     b, s, c, h, w = p.shape
+    if stage is not None and idx_patch is None and idx_batch is None:
+        return stage.take(s * h * w, b * s * h * w if non_local else 0, p.device)
     if idx_patch is None:
         idx_patch = _randperm(s * h * w, p.device, rng)
     if non_local and idx_batch is None:
@@ -124,11 +166,12 @@ class FeatureMSE(torch.nn.Module):
         self.non_local = non_local
         self.rng = rng or _default_rng()
         assert self.rng in ("cpu", "device")
+        self.stage = None    # PermStage while a GraphedTrainStep drives this loss with rng="cpu"
         print("FeatureMSE locality: %s" % ("Non-local" if non_local else "Local"))
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
         p, r = _views(p_buffer, ref)
-        idx_patch, idx_batch = _perms(p, self.rng, self.non_local, idx_patch, idx_batch)
+        idx_patch, idx_batch = _perms(p, self.rng, self.non_local, idx_patch, idx_batch, self.stage)
         return _FmseFn.apply(p, r, idx_patch, idx_batch)
 
 
@@ -140,11 +183,12 @@ class GlobalRelativeSimilarityLoss(torch.nn.Module):
         self.color = color
         self.alpha = alpha
         self.rng = rng or _default_rng()
+        self.stage = None
 
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
         p, r = _views(p_buffer, ref)
         b, s, c, h, w = p.shape
-        idx_patch, idx_batch = _perms(p, self.rng, True, idx_patch, idx_batch)
+        idx_patch, idx_batch = _perms(p, self.rng, True, idx_patch, idx_batch, self.stage)
         d_p, d_b = _PairDisplacementFn.apply(p, r, idx_patch, idx_batch)
         zero = torch.zeros(1, dtype=p.dtype, device=p.device)
         ex = self.alpha * torch.cat([d_p, d_b, -d_p, -d_b, zero], 0)

@@ -7,10 +7,11 @@ graph and replayed: per step the host copies the batch into the graph's static i
 replays, checks the finite flags (the step's single host sync, as in support/interfaces.py) and
 runs gradient all-reduce / clipping / Adam eagerly.
 
-Semantics are those of `KPCNInterface.train_batch` (/root/reference/support/interfaces.py:122-192)
-with two restrictions: the path-disentangling loss must draw its pairing permutations on the device
-(`FeatureMSE(rng="device")`: a CPU `randperm` would be frozen into the graph), and the every-1000-
-iterations PNG dump of the p-buffers is skipped.
+Semantics are those of `KPCNInterface.train_batch` (/root/reference/support/interfaces.py:122-192); the
+every-1000-iterations PNG dump of the p-buffers is skipped.  Pairing permutations of the path-disentangling
+loss: `FeatureMSE(rng="device")` draws them inside the graph; `rng="cpu"` keeps the reference's RNG contract
+(CPU default generator, losses.py:35, :50) through pre-staged static index buffers that the host refills
+before every replay (support.losses.PermStage) -- exact parity mode, ~27 ms of host randperm per step.
 """
 import os
 
@@ -23,9 +24,12 @@ class GraphedTrainStep:
     def __init__(self, itf, example_batch, warmup=3):
         self.itf = itf
         lm = itf.loss_funcs.get("l_manif")
+        self.stage = None
         if itf.manif_learn and getattr(lm, "rng", "cpu") != "device":
-            raise ValueError("GraphedTrainStep needs FeatureMSE(rng='device'): a CPU permutation would be "
-                             "captured once and replayed forever")
+            if not hasattr(lm, "stage"):
+                raise ValueError("GraphedTrainStep: the manifold loss draws CPU permutations and cannot stage them "
+                                 "(use support.losses.FeatureMSE / GlobalRelativeSimilarityLoss)")
+            self.stage = lm.stage = _losses.PermStage()
         self.static = {k: torch.empty_like(v, device="cuda") for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v)
@@ -36,6 +40,8 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):   # eager warm-up on a side stream (allocator / lazy init)
+                if self.stage is not None:
+                    self.stage.begin_step()
                 self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -73,6 +79,8 @@ class GraphedTrainStep:
         self.fused = itf._fused() if (itf.grad_sync is None or self.sync_in_graph) else None
         if self.fused is not None:
             self.fused.prepare()
+        if self.stage is not None:
+            self.stage.begin_step()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             loss, flags = self._fwd_bwd()
@@ -95,6 +103,10 @@ class GraphedTrainStep:
         for k, v in batch.items():
             if k in self.static:
                 self.static[k].copy_(v, non_blocking=True)
+        if self.fused is not None:
+            self.fused.refresh_if_changed()   # lr schedule / load_state_dict since the last replay
+        if self.stage is not None:
+            self.stage.begin_step()           # this step's pairing permutations from the CPU generator
         self.graph.replay()
         if self.fused is not None:
             if not bool(self.flags):     # the single host sync of the step; the update was skipped on the device

@@ -110,7 +110,15 @@ LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
 _KERNELS_PER_CALL = {"conv2d_wgrad": 2, "conv2d_wgrad_k1": 2, "conv2d_wgrad_k3": 2, "conv2d_wgrad_k5": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
                      "fmse_allpairs_fwd": 3, "pathnet_final_bwd": 2, "pathnet_embed_bwd": 2}
-_pending_wgrad = []  # (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
+
+
+def _pending():
+    """Per thread AND device: (WgradReduceDesc, keep-alive tensors) of deferred weight-gradient reductions
+    (nn.DataParallel drives one replica per thread; a flush must only see its own replica's layers)."""
+    d = getattr(_tls, "pending", None)
+    if d is None:
+        d = _tls.pending = {}
+    return d.setdefault(_tls.dev, [])
 
 
 def profile_start():
@@ -134,7 +142,13 @@ def _run(fn, what, work, *args):
     """Calls one C-ABI entry point; counts its kernel launches; optionally brackets it with CUDA
     events on the launching stream (bench.py's live per-kernel timing)."""
     LAUNCHES["count"] += _KERNELS_PER_CALL.get(what, 1)
-    if _profile is None:
+    dev = _tls.dev
+    if torch.cuda.current_device() != dev:
+        # the library launches on the CUDA runtime's current device; the tensors (and the stream fetched by
+        # _stream()) live on `dev`
+        with torch.cuda.device(dev):
+            rc = fn(*args)
+    elif _profile is None:
         rc = fn(*args)
     else:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -169,40 +183,48 @@ def _check(rc, what):
         raise WcmcError("%s failed (%d): %s" % (what, rc, load().wcmc_last_error().decode()))
 
 
-_ready = {"lib": None, "dev": -1}
+_tls = threading.local()   # .dev: device index of the call being issued; .pending: deferred weight-gradient reductions
+
+
+def _resolve(device):
+    if isinstance(device, int):
+        return device
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None:
+            return idx
+    return torch.cuda.current_device()
 
 
 def init(device=None):
-    """Loads the library and checks the device once; afterwards a dictionary lookup (this sits on
-    the launch path of every kernel).  `device`: None (current), int, or torch.device."""
-    lib = _ready["lib"]
-    if lib is not None:
-        idx = device if isinstance(device, int) else (None if device is None else device.index)
-        if idx is None or idx == _ready["dev"]:
-            return lib
-    lib = load()
-    if not torch.cuda.is_available():
+    """Loads the library, checks `device` once (sm_100 or WcmcError) and makes it the device of this thread's next
+    launches.  `device`: None (torch's current device), int, or torch.device -- the wrappers below pass the device
+    of their tensors, so a model living on cuda:1 launches on cuda:1 whatever torch's current device is (the
+    reference never calls set_device: /root/reference/train_kpcn.py:259-269 `.cuda(args.device_id)`, nn.DataParallel
+    replicas in threads).  Afterwards a dictionary lookup: this sits on the launch path of every kernel."""
+    lib = _lib
+    if lib is None:
+        lib = load()
+    if not _inited_devices and not torch.cuda.is_available():
         raise WcmcError("wcmc_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
-    if isinstance(device, int):
-        dev = device
-    elif device is None or torch.device(device).index is None:
-        dev = torch.cuda.current_device()
-    else:
-        dev = torch.device(device).index
+    dev = _resolve(device)
     if dev not in _inited_devices:
-        _check(lib.wcmc_init(dev), "wcmc_init")
-        _inited_devices.add(dev)
-        # measurement aid: WCMC_TUNE="knob=value,..." forwards to wcmc_tuning_set (tools/, bench A/B runs)
-        for item in filter(None, os.environ.get("WCMC_TUNE", "").split(",")):
-            name, _, val = item.partition("=")
-            _check(lib.wcmc_tuning_set(name.strip().encode(), int(val)), "wcmc_tuning_set")
-    _ready["lib"], _ready["dev"] = lib, dev
+        with _lock:
+            if dev not in _inited_devices:
+                _check(lib.wcmc_init(dev), "wcmc_init")
+                if not _inited_devices:
+                    # measurement aid: WCMC_TUNE="knob=value,..." forwards to wcmc_tuning_set (tools/, bench A/B runs)
+                    for item in filter(None, os.environ.get("WCMC_TUNE", "").split(",")):
+                        name, _, val = item.partition("=")
+                        _check(lib.wcmc_tuning_set(name.strip().encode(), int(val)), "wcmc_tuning_set")
+                _inited_devices.add(dev)
+    _tls.dev = dev
     return lib
 
 
 def _stream():
-    # raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~15 us per call)
-    return torch._C._cuda_getCurrentRawStream(_ready["dev"])
+    # raw cudaStream_t of torch's current stream ON THE DEVICE OF THE CALL (torch.cuda.current_stream() costs ~15 us)
+    return torch._C._cuda_getCurrentRawStream(_tls.dev)
 
 
 def _p(t):
@@ -311,9 +333,12 @@ def pack_weights_batch(specs, dtype=torch.bfloat16, dgrad=True):
 
 
 def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype=None, x_coff=0, mask=None,
-           mask_coff=0, slope=0.0, flags=0, cin=None, cout=None, colsum=None, colsum_scale=None):
+           mask_coff=0, slope=0.0, flags=0, cin=None, cout=None, colsum=None, colsum_scale=None, alg_hw=None):
     """x (N,H,W,Cs) 16-bit NHWC; w_packed (cout_p, k*k, cin_p) 16-bit; returns the NHWC output
-    (dtype `out_dtype`, default = x's dtype; torch.float32 for the logits layer)."""
+    (dtype `out_dtype`, default = x's dtype; torch.float32 for the logits layer).
+    alg_hw: spatial extent the ALGORITHMIC work of this launch is counted on (bench accounting only): a data-gradient
+    launch is a "full"-padded convolution over the forward layer's output map, and its algorithmic FLOPs are the
+    forward layer's 2*N*Ho*Wo*k^2*Cin*Cout, not this launch's larger output extent."""
     lib = init(x.device)
     n, h, w, xcs = _h16(x).shape
     cout_p, taps, cin_p = _h16(w_packed).shape
@@ -326,7 +351,8 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype
         assert bias.dtype == torch.float32 and bias.numel() >= cout_p
     if mask is not None:
         assert tuple(_h16(mask).shape[:3]) == (n, ho, wo)
-    _run(lib.wcmc_conv2d, "conv2d_k%d" % ksize, 2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
+    ah, aw = alg_hw or (ho, wo)
+    _run(lib.wcmc_conv2d, "conv2d_k%d" % ksize, 2.0 * n * ah * aw * ksize * ksize * (cin or cin_p) * (cout or cout_p),
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, _p(bias),
          ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),
          0 if mask is None else mask.shape[3], mask_coff, float(slope), _p(colsum), _p(colsum_scale), flags,
@@ -369,7 +395,7 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
              x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
              ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(),
              ctypes.byref(desc), _stream())
-        _pending_wgrad.append((desc, (ws, out, scale)))
+        _pending().append((desc, (ws, out, scale)))
         return out
     ws = _workspace(need, x.device)
     _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", work,
@@ -378,19 +404,21 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
     return out
 
 
-def wgrad_flush():
-    """Finalises every deferred weight gradient (one launch per 32 layers)."""
-    if not _pending_wgrad:
+def wgrad_flush(device=None):
+    """Finalises every deferred weight gradient of this thread on `device` (default: the device of the last
+    call) -- one launch per 32 layers."""
+    lib = init(device if device is not None else getattr(_tls, "dev", None))
+    pend = _pending()
+    if not pend:
         return
-    lib = init()
-    n = len(_pending_wgrad)
-    descs = (WgradReduceDesc * n)(*[d for d, _ in _pending_wgrad])
+    n = len(pend)
+    descs = (WgradReduceDesc * n)(*[d for d, _ in pend])
     byts = float(sum((d.nsplit * d.taps_a + d.nsplit_b * (d.taps - d.taps_a)) * d.cout_p * d.cin_p * 4
-                     for d, _ in _pending_wgrad))
+                     for d, _ in pend))
     try:
         _run(lib.wcmc_wgrad_reduce_batch, "wgrad_reduce", byts, descs, n, _stream())
     finally:
-        _pending_wgrad.clear()
+        pend.clear()
 
 
 def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False, scale=None):

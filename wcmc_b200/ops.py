@@ -131,7 +131,7 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
                        mask=None if mask is None else mask.t, mask_coff=0 if mask is None else mask.coff,
                        slope=slope, cin=l.cout, cout=l.cin,
                        colsum=db_all[offs[i - 1]:] if (db_all is not None and i > 0) else None,
-                       colsum_scale=inv_scale)
+                       colsum_scale=inv_scale, alg_hw=tuple(dz.t.shape[1:3]))
         dz = Slice(d, 0, l.cin)
     return dz, grads
 

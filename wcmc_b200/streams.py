@@ -17,12 +17,21 @@ caller's stream.
 """
 import contextlib
 import os
+import threading
 
 import torch
 
 ENABLED = os.environ.get("WCMC_BRANCH_STREAMS", "1") != "0"
-_side = {}      # (device index, name) -> torch.cuda.Stream
-_open = []      # side streams forked since the last join()
+_side = {}      # (device index, name, thread) -> torch.cuda.Stream
+_tls = threading.local()   # .open: side streams forked by THIS thread since its last join() (nn.DataParallel: one
+                           # replica per thread, each with its own fork / join bookkeeping)
+
+
+def _open():
+    lst = getattr(_tls, "open", None)
+    if lst is None:
+        lst = _tls.open = []
+    return lst
 
 
 @contextlib.contextmanager
@@ -32,7 +41,7 @@ def fork(name):
         return
     dev = torch.cuda.current_device()
     cur = torch.cuda.current_stream(dev)
-    key = (dev, name)
+    key = (dev, name, threading.get_ident())
     st = _side.get(key)
     if st is None:
         st = _side[key] = torch.cuda.Stream(dev)
@@ -40,12 +49,13 @@ def fork(name):
         yield
         return
     st.wait_stream(cur)
-    _open.append((cur, st))
+    _open().append((cur, st))
     with torch.cuda.stream(st):
         yield
 
 
 def join():
-    while _open:
-        cur, st = _open.pop()
+    lst = _open()
+    while lst:
+        cur, st = lst.pop()
         cur.wait_stream(st)
