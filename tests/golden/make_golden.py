@@ -49,6 +49,7 @@ def main():
     from support.interfaces import KPCNInterface
     from sbmc import KPCN
     from wcmc_b200.synth import make_batch
+    from tests import _proj
 
     G = {}
 
@@ -117,6 +118,11 @@ def main():
         rec["grad_abs_sums"] = {k: torch.stack([p.grad.detach().double().abs().sum()
                                                 for p in m.parameters()])
                                 for k, m in models.items()}
+        # per-tensor fingerprints (tests/_proj.py): K sign projections + L2 norm of every gradient (left CLIPPED by
+        # the step, interfaces.py:261) and of every parameter after the Adam step
+        rec["grad_fp"] = {k: _proj.fingerprints([p.grad for p in m.parameters()]) for k, m in models.items()}
+        rec["param_fp"] = {k: _proj.fingerprints(list(m.parameters())) for k, m in models.items()}
+        rec["param_names"] = {k: [n for n, _ in m.named_parameters()] for k, m in models.items()}
         itf.to_eval_mode()
         with torch.no_grad():
             rad, pb = itf.validate_batch(batch)

@@ -23,6 +23,10 @@ def _record(itf, models, batch):
                                              else torch.tensor(-1.0, dtype=torch.float64)) for p in m.parameters()])
                             for k, m in models.items()}
     rec["training"] = {k: bool(m.training) for k, m in models.items()}
+    from tests import _proj   # per-tensor fingerprints, see make_golden.py
+    rec["grad_fp"] = {k: _proj.fingerprints([p.grad for p in m.parameters()]) for k, m in models.items()
+                      if all(p.grad is not None for p in m.parameters())}
+    rec["param_fp"] = {k: _proj.fingerprints(list(m.parameters())) for k, m in models.items()}
     return rec
 
 

@@ -8,6 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from tests._record import record
 from wcmc_b200.synth import make_batch
 
 pytestmark = pytest.mark.gpu
@@ -265,6 +266,12 @@ def test_kpcn_matches_oracle(backend, oracle, size, batch, n_in):
     assert rel(gx_ours, gx_q) < TOL_GRAD_FP32_ORACLE
     print("KPCN grads: vs precision-matched oracle %.2e (worst tensor %.2e), vs fp32 oracle %.2e"
           % (_global_rel(g_ours, g_q), worst, e32))
+    record("test_kpcn_matches_oracle[%d-%d-%d]" % (size, batch, n_in),
+           radiance=rel(out_o["radiance"], out_r["radiance"]), diffuse=rel(out_o["diffuse"], out_r["diffuse"]),
+           specular=rel(out_o["specular"], out_r["specular"]), bound_img=TOL_IMG,
+           grads_vs_precision_matched=_global_rel(g_ours, g_q), worst_tensor_vs_precision_matched=worst,
+           bound_pm=2 * TOL_GRAD, grads_vs_fp32=e32, input_grad_vs_pm=rel(gx_ours, gx_q),
+           input_grad_vs_fp32=rel(gx_ours, gx_ref), bound_fp32_small_case=TOL_GRAD_FP32_ORACLE)
     assert e32 < TOL_GRAD_FP32_ORACLE
     assert rel(gx_ours, gx_ref) < 2 * TOL_GRAD_FP32_ORACLE
 
@@ -300,7 +307,31 @@ def test_pathnet_matches_oracle(backend, oracle, size, batch, spp, outc):
     # checked on the full step below
     _compare_grads(_grads(ours), g_q, TOL_GRAD_FP32_ORACLE)
     print("PathNet grads: vs precision-matched oracle %.2e, vs fp32 oracle %.2e" % (_global_rel(_grads(ours), g_q), e32))
+    record("test_pathnet_matches_oracle[%d-%d-%d-%d]" % (size, batch, spp, outc), p_buffer=rel(po, pr), bound_out=2e-3,
+           grads_vs_precision_matched=_global_rel(_grads(ours), g_q), grads_vs_fp32=e32,
+           bound_small_case=TOL_GRAD_FP32_ORACLE)
     assert e32 < TOL_GRAD_FP32_ORACLE
+
+
+def _fingerprint_check(tag, models, g, grad_bound, names=None):
+    """Per-tensor relative L2 of every gradient / updated parameter against the REFERENCE's own step through the
+    sign-projection fingerprints of the golden fixture (tests/_proj.py); every value is recorded."""
+    from tests import _proj
+    for name, m in models.items():
+        if name not in g.get("grad_fp", {}) or any(p.grad is None for p in m.parameters()):
+            continue
+        pn = [n for n, _ in m.named_parameters()]
+        e_g = _proj.est_rel(_proj.fingerprints([p.grad for p in m.parameters()]), g["grad_fp"][name])
+        e_all = _proj.est_rel_global(_proj.fingerprints([p.grad for p in m.parameters()]), g["grad_fp"][name])
+        e_p = _proj.param_rms_shift_in_lr(m.parameters(), g["param_fp"][name], 1e-4)
+        worst = int(e_g.argmax())
+        record(tag, model=name, grad_rel_all_tensors=e_all, grad_rel_worst_tensor=float(e_g[worst]),
+               worst_tensor=pn[worst], grad_rel_median_tensor=float(e_g.median()),
+               param_rms_shift_in_lr_worst=float(e_p.max()), bound=grad_bound)
+        assert e_all < grad_bound, (name, e_all)
+        # Adam's first step moves every weight by lr * sign(g): an RMS shift of 0.7 lr = 12 % of the signs of the
+        # worst tensor (biases whose gradient is below the 16-bit noise floor)
+        assert float(e_p.max()) < 0.7, (name, float(e_p.max()))
 
 
 def _build(KPCN, PathNet, n_in, llpm, outc):
@@ -337,17 +368,24 @@ def test_train_step_matches_reference_golden(backend, oracle, golden, tag):
     itf.preprocess(batch)
     torch.manual_seed(g["perm_seed"])
     itf.train_batch(batch)
+    record("test_train_step_matches_reference_golden[%s]" % tag, bound_loss=TOL_IMG, bound_manif=TOL_MANIF,
+           **{k: rel(itf.m_losses[k].cpu(), v) for k, v in g["losses"].items()})
     for k, v in g["losses"].items():
         # the raw manifold term amplifies the p-buffer's fp16 storage error (~7e-4) about 4x
         assert rel(itf.m_losses[k].cpu(), v) < (TOL_MANIF if "manif" in k else TOL_IMG), k
     for name, m in models.items():
         gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()]).cpu()
+        record("test_train_step_matches_reference_golden[%s]" % tag, model=name,
+               grad_abs_sums_rel=rel(gs, g["grad_abs_sums"][name]), bound=3e-2)
         assert rel(gs, g["grad_abs_sums"][name]) < 3e-2, name
         # Adam's first step moves every weight by exactly lr * sign(grad): a gradient whose sign differs
         # (|g| below the precision floor) shifts that weight by 2 * lr.  Allow 3 % sign differences.
         for p_, want in zip(m.parameters(), g["param_sums"][name]):
             tol = 1e-4 * (6 * p_.numel() ** 0.5 + 0.03 * p_.numel()) + 1e-3 * abs(float(want))
             assert abs(float(p_.detach().double().sum()) - float(want)) < tol
+    # per-tensor relative L2 against the reference's own gradients (small case: the 16-bit forward flips ~eps of
+    # the ReLU masks, see TOL_GRAD_FP32_ORACLE above; 1e-2 is asserted at the north-star size)
+    _fingerprint_check("test_train_step_matches_reference_golden[%s]" % tag, models, g, TOL_GRAD_FP32_ORACLE)
     itf.to_eval_mode()
     with torch.no_grad():
         rad, _ = itf.validate_batch(batch)
@@ -377,9 +415,15 @@ def test_full_size_wcmc_step_vs_oracle(backend, oracle):
     torch.manual_seed(77)
     loss, _, _ = oracle.ref.kpcn_train_step(ref_models, ref_optims, batch, use_llpm_buf=True, manif_learn=True,
                                             w_manif=0.1)
+    record("test_full_size_wcmc_step_vs_oracle", bound_loss=TOL_IMG, bound_manif=TOL_MANIF,
+           **{k: rel(itf.m_losses["m_" + k], v) for k, v in loss.items()})
     for k, v in loss.items():
         assert rel(itf.m_losses["m_" + k], v) < (TOL_MANIF if "manif" in k else TOL_IMG), k
     for name in models:
+        go_, gr_ = _grads(models[name]), _grads(ref_models[name])
+        per = {k: rel(go_[k], gr_[k]) for k in go_}
+        record("test_full_size_wcmc_step_vs_oracle", model=name, grads_vs_fp32_oracle=_global_rel(go_, gr_),
+               worst_tensor=max(per.values()), worst_tensor_name=max(per, key=per.get), bound=TOL_GRAD)
         # the north-star configuration meets 1e-2 against the plain fp32 oracle
         worst = _compare_grads(_grads(models[name]), _grads(ref_models[name]), tol=TOL_GRAD)
         print(name, "grad rel-L2 vs fp32 oracle", _global_rel(_grads(models[name]), _grads(ref_models[name])),
@@ -391,6 +435,8 @@ def test_full_size_wcmc_step_vs_oracle(backend, oracle):
     with torch.no_grad():
         rad, _ = itf.validate_batch(batch)
         rad_ref, _, relmse_ref = oracle.ref.kpcn_validate(ref_models, batch, use_llpm_buf=True)
+    record("test_full_size_wcmc_step_vs_oracle", val_radiance=rel(rad, rad_ref),
+           val_relmse=rel(itf.m_losses["m_val"], relmse_ref), bound=TOL_IMG)
     assert rel(rad, rad_ref) < TOL_IMG
     assert rel(itf.m_losses["m_val"], relmse_ref) < TOL_IMG
     # size-independent properties: radiance recombination and finite gradients everywhere
@@ -628,6 +674,7 @@ def _check_step_vs_golden(models, itf, g):
         for p_, want in zip(m.parameters(), g["param_sums"][name]):
             tol = 1e-4 * (6 * p_.numel() ** 0.5 + 0.03 * p_.numel()) + 1e-3 * abs(float(want))
             assert abs(float(p_.detach().double().sum()) - float(want)) < tol, name
+    _fingerprint_check("n4_interfaces[%s]" % "+".join(sorted(itf.m_losses)), models, g, TOL_GRAD_FP32_ORACLE)
 
 
 def test_ref_interface_matches_reference_golden(backend, oracle, golden_n4):

@@ -77,6 +77,14 @@ def test_train_step_matches_reference_interface(golden, oracle, tag):
         _close(sums, g["param_sums"][name], rtol=1e-5, atol=1e-5)
         gs = torch.stack([p.grad.detach().double().abs().sum() for p in m.parameters()])
         _close(gs, g["grad_abs_sums"][name], rtol=1e-3, atol=1e-6)
+        # per-tensor relative L2 (sign-projection fingerprints, tests/_proj.py): the restatement reproduces every
+        # gradient tensor and every updated parameter of the reference's own step
+        from tests import _proj
+        e_g = _proj.est_rel(_proj.fingerprints([p.grad for p in m.parameters()]), g["grad_fp"][name])
+        # parameters after the step: zero-initialised biases become -lr * sign(g), so a ~1e-10 gradient whose sign
+        # differs by summation order is a 2 * lr shift -- bounded as an RMS shift in units of lr (< 0.1 % of signs)
+        e_p = _proj.param_rms_shift_in_lr(m.parameters(), g["param_fp"][name], 1e-4)
+        assert float(e_g.max()) < 1e-4 and float(e_p.max()) < 0.06, (name, float(e_g.max()), float(e_p.max()))
     for m in models.values():
         m.eval()
     rad, _, relmse = oracle.ref.kpcn_validate(models, batch, use_llpm_buf=llpm,
