@@ -135,6 +135,28 @@ int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int H, int W, i
                               void* workspace, size_t workspace_bytes, wcmc_wgrad_reduce_desc* desc_out,
                               void* stream);
 int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs, int n, void* stream);
+/* Weight gradients of EVERY layer of a backward pass in one call (round 2; conv_wgrad_group.cu): the SMs are dealt
+ * out to the layers in proportion to their cost, each layer gets a few K-split teams instead of ~21 splits per tap
+ * group, one batched reduction follows.  Same arithmetic and result layout as n wcmc_conv2d_wgrad calls; all layers
+ * share one 16-bit format `dtype`.  host_layers is a HOST array (n <= 64); x / dy / dw / scale are device pointers
+ * that must stay alive until the stream has run the call.  workspace: wcmc_conv2d_wgrad_group_workspace(layers, n)
+ * bytes, 256-byte aligned.                                                                                    */
+typedef struct {
+    const void* x;       /* NHWC 16-bit (N,H,W,x_cs), channels [x_coff, x_coff + cin_p), padded channels zero */
+    const void* dy;      /* NHWC 16-bit (N,Ho,Wo,dy_cs), channels [dy_coff, dy_coff + cout_p) */
+    float* dw;           /* (cout, cin, k, k) fp32 */
+    const float* scale;  /* device float or NULL: multiplies the result */
+    int N, H, W, x_cs, x_coff, cin_p, cin;
+    int dy_cs, dy_coff, cout_p, cout;
+    int ksize, pad, accumulate;
+} wcmc_wgrad_layer;
+size_t wcmc_conv2d_wgrad_group_workspace(const wcmc_wgrad_layer* host_layers, int n);
+int wcmc_conv2d_wgrad_group(const wcmc_wgrad_layer* host_layers, int n, int dtype, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Host-only: the launch plan (K-split teams, CTAs, taps per group, TMEM column stride per layer; any output may be
+ * NULL); returns the number of kernel launches or a negative error.                                        */
+int wcmc_conv2d_wgrad_group_plan(const wcmc_wgrad_layer* host_layers, int n, int* teams_out, int* ctas_out,
+                                 int* tpg_out, int* cstride_out);
 /* db[co] (+)= scale * sum over all pixels of dy[pix][dy_coff+co]   (scale: device float or NULL) */
 int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs, int dy_coff, int cout, float* db,
                    int accumulate, const float* scale, void* stream);

@@ -75,6 +75,87 @@ def test_conv_fwd_dgrad_wgrad_vs_fp64(backend, k, cin, cout, same, act_dtype):
     assert rel(db, dy.double().sum((0, 2, 3))) < 1e-5
 
 
+@pytest.mark.parametrize("act_dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("pack", [1, 0])
+def test_grouped_wgrad_vs_fp64(backend, act_dtype, pack):
+    """wcmc_conv2d_wgrad_group: the weight gradients of a whole backward pass in ONE launch (K-split teams dealt out
+    over the SMs, whole-kernel-row tap groups, 100-channel rows packed at a TMEM column stride of 100) against fp64
+    autograd -- every layer shape of the hot path in one group (KPCN first / mid / last 5x5 valid layers, U-Net 3x3
+    same-padded layers incl. channel slices of a wider tensor, a 1x1 layer), ragged map sizes, `accumulate` and
+    `scale`; the un-packed column layout (knob) must give the same numbers."""
+    lib = backend.lib
+    rt = lib.load()
+    assert rt.wcmc_tuning_set(b"wgrad_group_pack", pack) == 0
+    try:
+        g = torch.Generator(device="cuda").manual_seed(11)
+        cases = [  # n, h, w, cin, cout, k, pad
+            (2, 37, 29, 39, 100, 5, 0), (2, 33, 25, 100, 100, 5, 0), (1, 29, 21, 100, 441, 5, 0),
+            (2, 24, 40, 64, 64, 3, 1), (2, 12, 20, 128, 256, 3, 1), (2, 12, 20, 256, 256, 3, 1),
+            (2, 24, 40, 384, 128, 3, 1), (2, 24, 40, 192, 64, 3, 1), (3, 9, 7, 36, 64, 1, 0), (1, 8, 8, 100, 100, 5, 2)]
+        scale = torch.full((1,), 0.25, device="cuda")
+        want, got, keep = [], [], []
+        for i, (n, h, w, cin, cout, k, pad) in enumerate(cases):
+            x = torch.randn(n, cin, h, w, device="cuda", generator=g).to(act_dtype).float()
+            ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+            dy = torch.randn(n, cout, ho, wo, device="cuda", generator=g).to(act_dtype).float()
+            gw = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, k, k), dy.double(), padding=pad)
+            # operands live in channel slices of wider NHWC tensors for some layers (U-Net concatenation buffers)
+            xoff, doff = (8, 16) if i % 3 == 1 else (0, 0)
+            cin_p, cout_p = lib.pad16(cin), lib.pad16(cout)
+            xw = torch.randn(n, h, w, cin_p + xoff + 8, device="cuda", generator=g).to(act_dtype)
+            dw_ = torch.randn(n, ho, wo, cout_p + doff + 8, device="cuda", generator=g).to(act_dtype)
+            lib.nchw_to_nhwc(x, dst=xw, dst_coff=xoff, c_fill=cin_p, dtype=act_dtype)
+            lib.nchw_to_nhwc(dy, dst=dw_, dst_coff=doff, c_fill=cout_p, dtype=act_dtype)
+            acc = i % 4 == 2
+            out = torch.randn(cout, cin, k, k, device="cuda", generator=g) if acc else None
+            base = out.double().clone() if acc else 0.0
+            sc = scale if i % 2 == 0 else None
+            r = lib.conv2d_wgrad(xw, dw_, cout, cin, k, pad, cin_p, cout_p, x_coff=xoff, dy_coff=doff, out=out,
+                                 accumulate=acc, scale=sc, defer=True)
+            want.append(base + gw * (0.25 if sc is not None else 1.0))
+            got.append(r)
+            keep.append((xw, dw_))
+        lib.wgrad_flush()
+        torch.cuda.synchronize()
+        for c, a, b in zip(cases, got, want):
+            assert rel(a, b) < 2e-5, (c, rel(a, b))
+    finally:
+        rt.wcmc_tuning_set(b"wgrad_group_pack", 1)
+
+
+def test_grouped_wgrad_matches_per_layer_launches_at_full_size(backend):
+    """The grouped launch against the round-1 per-layer kernel on the nine layers of a KPCN branch at the north-star
+    size (B = 8, 128^2): same gradients (fp32 summation order differs), and the plan uses every SM with 2-4 teams."""
+    lib = backend.lib
+    rt = lib.load()
+    from wcmc_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dt = ops.ACT_DTYPE
+    shapes = [(39, 100, 128)] + [(100, 100, 128 - 4 * i) for i in range(1, 8)] + [(100, 441, 96)]
+    layers = []
+    for cin, cout, h in shapes:
+        x = (torch.randn(8, h, h, lib.pad16(cin), device="cuda", generator=g) * 0.5).to(dt)
+        x[..., cin:] = 0
+        dy = (torch.randn(8, h - 4, h - 4, lib.pad16(cout), device="cuda", generator=g) * 0.1).to(dt)
+        dy[..., cout:] = 0
+        layers.append((x, dy, cin, cout))
+    outs = {}
+    for mode in (1, 0):
+        assert rt.wcmc_tuning_set(b"wgrad_group", mode) == 0
+        try:
+            res = [lib.conv2d_wgrad(x, dy, cout, cin, 5, 0, lib.pad16(cin), lib.pad16(cout), defer=True)
+                   for x, dy, cin, cout in layers]
+            lib.wgrad_flush()
+            torch.cuda.synchronize()
+            outs[mode] = res
+        finally:
+            rt.wcmc_tuning_set(b"wgrad_group", 1)
+    for a, b in zip(outs[1], outs[0]):
+        assert rel(a, b) < 1e-5
+    plan, launches = lib.wgrad_group_plan([(8, h, h, cin, cout, 5, 0) for cin, cout, h in shapes])
+    assert launches == 1 and 140 <= sum(p[1] for p in plan) <= 148 and all(1 <= p[0] <= 6 for p in plan)
+
+
 @pytest.mark.parametrize("mt,nt", [(1, 0), (2, 0), (2, 64), (1, 48)])
 def test_conv_tilings_agree(backend, mt, nt):
     lib = backend.lib

@@ -5,7 +5,8 @@ O=gpurun_out/r02a
 mkdir -p $O
 rm -f gpurun_out/parity_records.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $O/pytest.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "grouped_wgrad" > $O/pytest_wgrad.log 2>&1; echo "grouped wgrad pytest exit $?"; tail -15 $O/pytest_wgrad.log
+timeout 1800 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest exit $?"; tail -25 $O/pytest.log
 cp gpurun_out/parity_records.jsonl $O/ 2>/dev/null
 timeout 300 python tests/ablation_relu_flip.py > $O/relu_flip_ablation.txt 2> $O/relu_flip_ablation.err; echo "ablation exit $?"; grep -v Warn $O/relu_flip_ablation.txt | tail -8
 # compute-sanitizer: memcheck on the unit tests of the kernels whose correctness rests on mbarrier / cluster protocols

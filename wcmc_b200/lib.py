@@ -39,6 +39,14 @@ class WgradReduceDesc(ctypes.Structure):
                 ("nsplit_b", c_int), ("taps_a", c_int)]
 
 
+class WgradLayer(ctypes.Structure):
+    """wcmc_wgrad_layer of include/wcmc.h"""
+    _fields_ = [("x", c_void_p), ("dy", c_void_p), ("dw", c_void_p), ("scale", c_void_p), ("N", c_int), ("H", c_int),
+                ("W", c_int), ("x_cs", c_int), ("x_coff", c_int), ("cin_p", c_int), ("cin", c_int), ("dy_cs", c_int),
+                ("dy_coff", c_int), ("cout_p", c_int), ("cout", c_int), ("ksize", c_int), ("pad", c_int),
+                ("accumulate", c_int)]
+
+
 class AdamTensor(ctypes.Structure):
     """wcmc_adam_tensor of include/wcmc.h"""
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", ctypes.c_long),
@@ -64,6 +72,9 @@ SIGNATURES = {
                                   + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, ctypes.POINTER(WgradReduceDesc),
                                                    c_void_p]),
     "wcmc_wgrad_reduce_batch": (c_int, [ctypes.POINTER(WgradReduceDesc), c_int, c_void_p]),
+    "wcmc_conv2d_wgrad_group_workspace": (c_size_t, [ctypes.POINTER(WgradLayer), c_int]),
+    "wcmc_conv2d_wgrad_group": (c_int, [ctypes.POINTER(WgradLayer), c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "wcmc_conv2d_wgrad_group_plan": (c_int, [ctypes.POINTER(WgradLayer), c_int] + [ctypes.POINTER(c_int)] * 4),
     "wcmc_bias_grad": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p, c_int, c_void_p, c_void_p]),
     "wcmc_kernel_apply_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "wcmc_kernel_apply_bwd": (c_int, [c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
@@ -108,7 +119,7 @@ class WcmcError(RuntimeError):
 # ---- bookkeeping for bench.py: kernels launched, and (optionally) per-launch device time -------
 LAUNCHES = {"count": 0}
 _profile = None  # when a list: (name, algorithmic_work, start_event, end_event) per timed call
-_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "conv2d_wgrad_k1": 2, "conv2d_wgrad_k3": 2, "conv2d_wgrad_k5": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
+_KERNELS_PER_CALL = {"conv2d_wgrad": 2, "bias_grad": 2, "fmse_perm_fwd": 2, "adam_clip_step": 2,
                      "fmse_allpairs_fwd": 3, "pathnet_final_bwd": 2, "pathnet_embed_bwd": 2}
 
 
@@ -385,18 +396,15 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
         out = torch.empty((cout, cin, ksize, ksize), dtype=torch.float32, device=x.device)
         accumulate = False
     assert out.is_contiguous() and out.dtype == torch.float32
-    need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
     work = 2.0 * n * ho * wo * ksize * ksize * cin * cout
     if defer:
-        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-        desc = WgradReduceDesc()
-        LAUNCHES["count"] -= 1   # _run counts 2 kernels per conv2d_wgrad call; the reduce comes at the flush
-        _run(lib.wcmc_conv2d_wgrad_partial, "conv2d_wgrad_k%d" % ksize, work,
-             x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
-             ksize, pad, out.data_ptr(), cout, cin, int(accumulate), _p(scale), ws.data_ptr(), ws.numel(),
-             ctypes.byref(desc), _stream())
-        _pending().append((desc, (ws, out, scale)))
+        # nothing is launched now: the layer joins the backward pass's group and wgrad_flush() runs ONE grouped
+        # launch + one reduction for all of them (x, dy, out and scale are kept alive until then)
+        layer = WgradLayer(x.data_ptr(), dy.data_ptr(), out.data_ptr(), _p(scale), n, h, w, xcs, x_coff, cin_p, cin,
+                           dy.shape[3], dy_coff, cout_p, cout, ksize, pad, int(accumulate))
+        _pending().append((layer, (x, dy, out, scale), work, _dt(x)))
         return out
+    need = lib.wcmc_conv2d_wgrad_workspace(n, h, w, cin_p, cout_p, ksize, pad)
     ws = _workspace(need, x.device)
     _run(lib.wcmc_conv2d_wgrad, "conv2d_wgrad", work,
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, dy.data_ptr(), _dt(dy), dy.shape[3], dy_coff, cout_p,
@@ -404,21 +412,56 @@ def conv2d_wgrad(x, dy, cout, cin, ksize, pad, cin_p, cout_p, x_coff=0, dy_coff=
     return out
 
 
+WGRAD_GROUP_MAX = 64
+
+
 def wgrad_flush(device=None):
-    """Finalises every deferred weight gradient of this thread on `device` (default: the device of the last
-    call) -- one launch per 32 layers."""
+    """Runs every deferred weight gradient of this thread on `device` (default: the device of the last call): one
+    grouped tensor-core launch per <= 16 layers (wcmc_conv2d_wgrad_group) + one batched reduction."""
     lib = init(device if device is not None else getattr(_tls, "dev", None))
     pend = _pending()
     if not pend:
         return
-    n = len(pend)
-    descs = (WgradReduceDesc * n)(*[d for d, _ in pend])
-    byts = float(sum((d.nsplit * d.taps_a + d.nsplit_b * (d.taps - d.taps_a)) * d.cout_p * d.cin_p * 4
-                     for d, _ in pend))
     try:
-        _run(lib.wcmc_wgrad_reduce_batch, "wgrad_reduce", byts, descs, n, _stream())
+        for base in range(0, len(pend), WGRAD_GROUP_MAX):
+            part = pend[base:base + WGRAD_GROUP_MAX]
+            n = len(part)
+            layers = (WgradLayer * n)(*[p[0] for p in part])
+            dtype = part[0][3]
+            assert all(p[3] == dtype for p in part), "deferred weight gradients must share one 16-bit format"
+            need = lib.wcmc_conv2d_wgrad_group_workspace(layers, n)
+            if need == 0:
+                raise WcmcError("wgrad_group: %s" % lib.wcmc_last_error().decode())
+            dev = part[0][1][0].device
+            ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            off = (-ws.data_ptr()) % 256
+            # bench accounting: the call is booked per filter size (the 5x5 KPCN stacks and the 3x3 U-Net differ by
+            # a factor of two in achievable rate); a mixed group goes under the size with the most work
+            by_k = {}
+            for p in part:
+                by_k[p[0].ksize] = by_k.get(p[0].ksize, 0.0) + p[2]
+            k_main = max(by_k, key=by_k.get)
+            LAUNCHES["count"] += 1     # grouped kernel + reduction
+            _run(lib.wcmc_conv2d_wgrad_group, "conv2d_wgrad_k%d" % k_main, sum(by_k.values()), layers, n, dtype,
+                 ws.data_ptr() + off, need, _stream())
     finally:
         pend.clear()
+
+
+def wgrad_group_plan(specs):
+    """Host-only view of the grouped launch plan.  specs: [(N, H, W, cin, cout, ksize, pad)] ->
+    [(teams, ctas, taps_per_group, column_stride)] per layer, number of launches."""
+    lib = load()
+    n = len(specs)
+    layers = (WgradLayer * n)()
+    for i, (nb, h, w, cin, cout, k, pad) in enumerate(specs):
+        layers[i] = WgradLayer(1, 1, 1, 0, nb, h, w, pad16(cin), 0, pad16(cin), cin, pad16(cout), 0, pad16(cout), cout, k,
+                               pad, 0)
+    outs = [(c_int * n)() for _ in range(4)]
+    rc = lib.wcmc_conv2d_wgrad_group_plan(layers, n, *outs)
+    if rc < 0:
+        raise WcmcError("wgrad_group_plan failed (%d): %s" % (rc, lib.wcmc_last_error().decode()))
+    return [tuple(o[i] for o in outs) for i in range(n)], rc
 
 
 def bias_grad(dy, cout, dy_coff=0, out=None, accumulate=False, scale=None):
