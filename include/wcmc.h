@@ -331,6 +331,38 @@ int wcmc_adam_chunk(void);
 int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const int* dev_blocks, int nblocks, int* dev_step,
                         const int* dev_ok_flag, float clip, void* stream);
 
+/* ---- K9: p-buffer statistics + concatenation (/root/reference/support/interfaces.py:165-180) ----------------
+ * out (B, Cin+cr+1, HW) = cat[kpcn_in (B,Cin,HW), mean_S p[:, :, c0:c0+cr], var_S(p[:, :, c0:c0+cr]).mean(C) / S]
+ * with p (B,S,C,HW) fp32 contiguous, var unbiased (torch.var).  The backward writes the whole d p (B,S,C,HW):
+ * d p[b,s,c] = grad_out[b, Cin + c - c0] / S inside the channel range, 0 outside (the variance is detached).      */
+int wcmc_pbuffer_concat_fwd(const float* kpcn_in, const float* p, float* out, int B, int S, int C, int c0, int cr,
+                            int Cin, int HW, void* stream);
+int wcmc_pbuffer_concat_bwd(const float* grad_out, float* dp, int B, int S, int C, int c0, int cr, int Cin, int HW,
+                            void* stream);
+
+/* ---- K12: radiance recombination (sbmc.KPCN.forward) and the image losses of the step ----------------------------
+ * radiance = albedo * r_d + exp(r_s) - 1; r_d, r_s, radiance (B,3,h,w) fp32 contiguous; albedo is read through
+ * strides (batch, channel, row; unit x stride) at the crop origin the pointer already includes.                     */
+int wcmc_recombine(const float* albedo, long a_sb, long a_sc, long a_sh, const float* r_d, const float* r_s,
+                   float* radiance, int B, int h, int w, void* stream);
+/* sums4 = { mean|r_d - t_d|, mean|r_s - t_s|, mean|radiance - t_t|, 0.5 mean((radiance - t_t)^2 / (t_t^2 + eps)) }
+ * (nn.L1Loss x3, /root/reference/train_kpcn.py:300-302; RelativeMSE, support/losses.py:255-264) in ONE launch;
+ * a NULL prediction skips its term.  Targets are crop views: host_strides9 = (batch, channel, row) strides of t_d,
+ * t_s, t_t.  sgn_d / sgn_s (optional, (B,3,h,w)) receive sign(pred - target) / n: the L1 gradients.  workspace:
+ * wcmc_image_losses_workspace() bytes that the caller zero-fills ONCE and then keeps (per-CTA partials + a ticket
+ * the launch re-arms); sums are accumulated in a fixed order.                                                        */
+size_t wcmc_image_losses_workspace(void);
+int wcmc_image_losses(const float* r_d, const float* r_s, const float* radiance, const float* t_d, const float* t_s,
+                      const float* t_t, const long* host_strides9, int B, int h, int w, float eps, float* sgn_d,
+                      float* sgn_s, float* sums4, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- device-side pairing permutations for the throughput mode of the loss (the reference draws
+ * torch.randperm on the CPU, /root/reference/support/losses.py:35, :50; the parity mode keeps that) ----
+ * out[i] = pi(i), a keyed Feistel bijection of [0, n) (cycle walking), no sort.  state: 2 x uint64 on the device,
+ * state[0] = draw counter (seed it; the launch advances it by one), state[1] = 0.  salt distinguishes launches
+ * that read the same counter value.                                                                        */
+int wcmc_random_permutation(int64_t* out, long n, unsigned long long* state, unsigned salt, void* stream);
+
 /* ---- K11: all-pairs form of the path-disentangling loss on the tensor cores (EXTENSION: the reference
  * pairs each row with one random partner, /root/reference/support/losses.py:33-61; this is the quantity
  * that estimator samples, BASELINE.json north_star (4) / configs[4]; oracle/allpairs_ref.py) ---------

@@ -96,32 +96,56 @@ struct PackBatch {
     wcmc_pack_desc d[WCMC_PACK_BATCH_MAX];
 };
 
-// blockIdx.y = layer; same element mapping as pack_weights_kernel
-__global__ void pack_weights_batch_kernel(const PackBatch pb, int dtype) {
+// blockIdx.y = layer.  Round 1 gathered every packed element from torch's (cout,cin,k,k) layout with stride-k^2
+// 4-byte reads (398 GB/s, 0.24 ms of every step).  Here a CTA owns one OUTPUT ROW and stages its source through
+// shared memory, so both sides move whole sectors:
+//   blockIdx.x <  cout_p : fwd row co   = w[co][:][:]   one contiguous cin*taps run       -> fwd[co][tap][ci]
+//   blockIdx.x >= cout_p : dgrad row ci = w[:][ci][:]   cout runs of taps floats          -> dgrad[ci][taps-1-tap][co]
+// Rows / columns beyond the logical channel counts are written as zeros (the convolutions rely on it).
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackBatch pb, int dtype) {
+    extern __shared__ float row[];
     const wcmc_pack_desc& L = pb.d[blockIdx.y];
     const int taps = L.ksize * L.ksize;
-    const long total = static_cast<long>(L.cout_p) * taps * L.cin_p;
-    if (L.dst_bias != nullptr && blockIdx.x == 0)
+    const int r = blockIdx.x;
+    if (r >= L.cout_p + L.cin_p) return;
+    if (r == 0 && L.dst_bias != nullptr)
         for (int c = threadIdx.x; c < L.cout_p; c += blockDim.x)
             L.dst_bias[c] = (L.bias != nullptr && c < L.cout) ? L.bias[c] : 0.f;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        if (L.dst_fwd != nullptr) {
-            int ci = static_cast<int>(i % L.cin_p);
-            int tap = static_cast<int>((i / L.cin_p) % taps);
-            int co = static_cast<int>(i / (static_cast<long>(L.cin_p) * taps));
-            float v = (co < L.cout && ci < L.cin) ? L.w[(static_cast<long>(co) * L.cin + ci) * taps + tap] : 0.f;
-            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_fwd)[i] = __float2half_rn(v);
-            else static_cast<__nv_bfloat16*>(L.dst_fwd)[i] = __float2bfloat16_rn(v);
+    if (r < L.cout_p) {
+        if (L.dst_fwd == nullptr) return;
+        const int co = r;
+        const int n = L.cin * taps;
+        if (co < L.cout) {
+            const float* src = L.w + static_cast<long>(co) * n;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = __ldg(src + i);     // [ci][tap]
         }
-        if (L.dst_dgrad != nullptr) {
-            int co = static_cast<int>(i % L.cout_p);
-            int tapf = static_cast<int>((i / L.cout_p) % taps);
-            int ci = static_cast<int>(i / (static_cast<long>(L.cout_p) * taps));
-            int tap = taps - 1 - tapf;
-            float v = (co < L.cout && ci < L.cin) ? L.w[(static_cast<long>(co) * L.cin + ci) * taps + tap] : 0.f;
-            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_dgrad)[i] = __float2half_rn(v);
-            else static_cast<__nv_bfloat16*>(L.dst_dgrad)[i] = __float2bfloat16_rn(v);
+        __syncthreads();
+        const long base = static_cast<long>(co) * taps * L.cin_p;
+        const int total = taps * L.cin_p;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int tap = i / L.cin_p, ci = i - tap * L.cin_p;
+            const float v = (co < L.cout && ci < L.cin) ? row[ci * taps + tap] : 0.f;
+            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_fwd)[base + i] = __float2half_rn(v);
+            else static_cast<__nv_bfloat16*>(L.dst_fwd)[base + i] = __float2bfloat16_rn(v);
+        }
+    } else {
+        if (L.dst_dgrad == nullptr) return;
+        const int ci = r - L.cout_p;
+        if (ci < L.cin) {
+            const int n = L.cout * taps;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int co = i / taps, tap = i - co * taps;
+                row[i] = __ldg(L.w + (static_cast<long>(co) * L.cin + ci) * taps + tap);     // [co][tap]
+            }
+        }
+        __syncthreads();
+        const long base = static_cast<long>(ci) * taps * L.cout_p;
+        const int total = taps * L.cout_p;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int tapf = i / L.cout_p, co = i - tapf * L.cout_p;
+            const float v = (co < L.cout && ci < L.cin) ? row[co * taps + (taps - 1 - tapf)] : 0.f;
+            if (dtype == WCMC_F16) static_cast<__half*>(L.dst_dgrad)[base + i] = __float2half_rn(v);
+            else static_cast<__nv_bfloat16*>(L.dst_dgrad)[base + i] = __float2bfloat16_rn(v);
         }
     }
 }
@@ -230,17 +254,22 @@ extern "C" int wcmc_pack_weights_batch(const wcmc_pack_desc* descs, int n, int d
     for (int base = 0; base < n; base += WCMC_PACK_BATCH_MAX) {
         PackBatch pb;
         const int m = std::min(WCMC_PACK_BATCH_MAX, n - base);
-        long max_total = 0;
+        int max_rows = 0, max_floats = 0;
         for (int i = 0; i < m; ++i) {
             pb.d[i] = descs[base + i];
             const wcmc_pack_desc& L = pb.d[i];
             WCMC_REQUIRE(L.cout > 0 && L.cin > 0 && L.cout_p >= L.cout && L.cin_p >= L.cin && L.ksize > 0 &&
                              L.w != nullptr,
                          WCMC_ESHAPE, "pack_weights_batch: bad layer %d", base + i);
-            max_total = std::max(max_total, static_cast<long>(L.cout_p) * L.cin_p * L.ksize * L.ksize);
+            max_rows = std::max(max_rows, L.cout_p + L.cin_p);
+            max_floats = std::max(max_floats, std::max(L.cout, L.cin) * L.ksize * L.ksize);
         }
-        dim3 grid(static_cast<unsigned>(std::min<long>((max_total + 255) / 256, 148)), m);
-        pack_weights_batch_kernel<<<grid, 256, 0, stream>>>(pb, dtype);
+        WCMC_REQUIRE(max_floats <= 12 * 1024, WCMC_ESHAPE, "pack_weights_batch: a weight row of %d floats does not fit "
+                     "the staging tile", max_floats);
+        const int smem = max_floats * static_cast<int>(sizeof(float));
+        if (smem > 48 * 1024) WCMC_FUNC_SMEM(pack_weights_batch_kernel, smem);
+        dim3 grid(static_cast<unsigned>(max_rows), m);
+        pack_weights_batch_kernel<<<grid, 256, smem, stream>>>(pb, dtype);
         WCMC_LAUNCH_CHECK();
     }
     return WCMC_OK;

@@ -42,6 +42,5 @@ class KPCN(nn.Module):
         with streams.fork("specular"):
             r_s = self._branch(self.specular, data["kpcn_specular_in"], data["kpcn_specular_buffer"])
         streams.join()
-        albedo = crop_like(data["kpcn_albedo"], r_d)
-        radiance = albedo * r_d + torch.exp(r_s) - 1.0
+        radiance = ops.RecombineFn.apply(data["kpcn_albedo"], r_d, r_s)     # albedo * r_d + exp(r_s) - 1, centred crop
         return dict(radiance=radiance, diffuse=r_d, specular=r_s)

@@ -80,16 +80,25 @@ def _half(p_buffers, lo):
     return {k: v[:, :, sl] for k, v in p_buffers.items()}
 
 
-def _with_pbuffer(batch, p_buffers):
+def _with_pbuffer(batch, p_buffers, channels=None):
     """New batch whose KPCN inputs carry [mean_S(p) | var_S(p).mean(C)/S] (interfaces.py:165-180).
     The mean keeps its graph (gradients reach PathNet through the regression branch); the
-    variance channel is detached, as in the reference."""
+    variance channel is detached, as in the reference.  `channels` = (c0, cr): only that channel range of the
+    p-buffers feeds the regression (the `m10r01` / `m11r01` options).  On the GPU the statistics and the
+    concatenation are one launch (K9, ops.PBufferConcatFn); host-logic tests on CPU tensors keep the expression."""
     new = {k: batch[k] for k in ("target_total", "target_diffuse", "target_specular", "kpcn_diffuse_buffer",
                                  "kpcn_specular_buffer", "kpcn_albedo")}
     for name in ("diffuse", "specular"):
         p = p_buffers[name]
+        c0, cr = channels if channels is not None else (0, p.shape[2])
+        kin = batch["kpcn_%s_in" % name]
+        if p.is_cuda and kin.is_cuda:
+            from wcmc_b200 import ops as wops
+            new["kpcn_%s_in" % name] = wops.PBufferConcatFn.apply(kin, p, c0, cr)
+            continue
+        p = p[:, :, c0:c0 + cr]
         var = p.var(1).mean(1, keepdim=True).detach() / p.shape[1]
-        new["kpcn_%s_in" % name] = torch.cat([batch["kpcn_%s_in" % name], p.mean(1), var], 1)
+        new["kpcn_%s_in" % name] = torch.cat([kin, p.mean(1), var], 1)
     return new
 
 
@@ -177,6 +186,11 @@ class KPCNInterface(BaseInterface):
         man = _half(p_buffers, lo=False) if opt in ("m10r01", "m10r11") else p_buffers
         return reg, man
 
+    def _reg_channels(self, p_buffers):
+        """Channel range (c0, cr) of the p-buffers that feeds the regression (the lower half for `*r01`)."""
+        c = p_buffers["diffuse"].shape[2]
+        return (0, c // 2) if self.disentanglement_option in ("m10r01", "m11r01") else (0, c)
+
     # ---- one optimisation step -----------------------------------------------------------------
     def train_batch(self, batch, grad_hook_mode=False):
         out_manif = None
@@ -186,8 +200,8 @@ class KPCNInterface(BaseInterface):
             p_buffers = self._manifold_forward(batch)
             if self.iters % 1000 == 1:
                 self._dump_pbuffers(p_buffers)
-            p_reg, out_manif = self._split(p_buffers)
-            batch = _with_pbuffer(batch, p_reg)
+            _, out_manif = self._split(p_buffers)
+            batch = _with_pbuffer(batch, p_buffers, self._reg_channels(p_buffers))
         self.models["dncnn"].zero_grad()
         out = self._regress_forward(batch)
         loss_dict = self._backward(batch, out, out_manif)
@@ -201,11 +215,12 @@ class KPCNInterface(BaseInterface):
         total, diffuse, specular = out["radiance"], out["diffuse"], out["specular"]
         losses = {}
         tgt_total = crop_like(batch["target_total"], total)
+        fused = self._fused_image_losses(batch, total, diffuse, specular) if self.train_branches else None
         if self.train_branches:
             branch_loss = {}
             for name, pred in (("diffuse", diffuse), ("specular", specular)):
                 tgt = crop_like(batch["target_" + name], pred)
-                loss = self.loss_funcs["l_" + name](pred, tgt)
+                loss = fused["l_" + name] if fused is not None else self.loss_funcs["l_" + name](pred, tgt)
                 if self.manif_learn:
                     l_manif = self.loss_funcs["l_manif"](crop_like(p_buffers[name], pred), tgt)
                     losses["l_manif_" + name] = l_manif.detach()
@@ -219,16 +234,37 @@ class KPCNInterface(BaseInterface):
             # kernels (recorded on different streams) overlap
             torch.autograd.backward([branch_loss["diffuse"], branch_loss["specular"]])
             with torch.no_grad():
-                losses["l_total"] = self.loss_funcs["l_recon"](total, tgt_total).detach()
+                losses["l_total"] = fused["l_total"] if fused is not None else \
+                    self.loss_funcs["l_recon"](total, tgt_total).detach()
         else:
             l_total = self.loss_funcs["l_recon"](total, tgt_total)
             losses["l_total"] = l_total.detach()
             l_total.backward()
         with torch.no_grad():
-            losses["rmse"] = self.loss_funcs["l_test"](total, tgt_total).detach()
+            losses["rmse"] = fused["rmse"] if fused is not None else self.loss_funcs["l_test"](total, tgt_total).detach()
         # keep the reference's key order (l_diffuse, l_specular, l_manif_*, l_total, rmse)
         order = ["l_diffuse", "l_specular", "l_manif_diffuse", "l_manif_specular", "l_total", "rmse"]
         return {k: losses[k] for k in order if k in losses}
+
+    def _fused_image_losses(self, batch, total, diffuse, specular):
+        """K12: the three L1 terms and RelativeMSE of the step in one reduction launch (ops.ImageLossesFn) when the loss
+        objects are the ones train_kpcn.py constructs (nn.L1Loss with mean reduction, :300-302; RelativeMSE) and the
+        images live on the GPU; None otherwise (any other loss object is simply called, as in the reference)."""
+        lf = self.loss_funcs
+        from support.losses import RelativeMSE
+        l1 = [lf.get(k) for k in ("l_diffuse", "l_specular", "l_recon")]
+        if not all(type(f) is nn.L1Loss and f.reduction == "mean" for f in l1) or type(lf.get("l_test")) is not RelativeMSE:
+            return None
+        tgts = [batch["target_diffuse"], batch["target_specular"], batch["target_total"]]
+        preds = [diffuse, specular, total]
+        if not all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3 for t in tgts + preds):
+            return None
+        if any(t.stride(3) != 1 for t in tgts) or any(p.shape != preds[0].shape for p in preds):
+            return None
+        from wcmc_b200 import ops as wops
+        l_d, l_s, l_t, rmse = wops.ImageLossesFn.apply(diffuse, specular, total.detach(), tgts[0], tgts[1], tgts[2],
+                                                       float(lf["l_test"].eps))
+        return {"l_diffuse": l_d, "l_specular": l_s, "l_total": l_t.detach(), "rmse": rmse.detach()}
 
     def _assert_finite(self, loss_dict):
         keys = list(loss_dict)
@@ -282,9 +318,10 @@ class KPCNInterface(BaseInterface):
         if self.use_llpm_buf:
             p_buffers = self._manifold_forward(batch)
             assert p_buffers["diffuse"].shape[2] >= 2
+            channels = self._reg_channels(p_buffers)
+            batch = _with_pbuffer(batch, p_buffers, channels)
             if self.disentanglement_option in ("m10r01", "m11r01"):
                 p_buffers = _half(p_buffers, lo=True)
-            batch = _with_pbuffer(batch, p_buffers)
         out = self._regress_forward(batch)
         tgt_total = crop_like(batch["target_total"], out["radiance"])
         l_total = self.loss_funcs["l_test"](out["radiance"], tgt_total)

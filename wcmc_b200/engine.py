@@ -58,9 +58,9 @@ class GraphedTrainStep:
                 itf.models["backbone_diffuse"].zero_grad()
                 itf.models["backbone_specular"].zero_grad()
                 p_buffers = itf._manifold_forward(batch)
-                p_reg, out_manif = itf._split(p_buffers)
+                _, out_manif = itf._split(p_buffers)
                 from support.interfaces import _with_pbuffer
-                batch = _with_pbuffer(batch, p_reg)
+                batch = _with_pbuffer(batch, p_buffers, itf._reg_channels(p_buffers))
             itf.models["dncnn"].zero_grad()
             out = itf._regress_forward(batch)
             loss = itf._backward(batch, out, out_manif)

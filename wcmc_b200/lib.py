@@ -103,6 +103,13 @@ SIGNATURES = {
     "wcmc_preprocess_kpcn_workspace": (c_size_t, [c_int, c_int]),
     "wcmc_preprocess_kpcn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "wcmc_preprocess_llpm": (c_int, [c_void_p, ctypes.c_long, c_void_p, c_void_p]),
+    "wcmc_pbuffer_concat_fwd": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    "wcmc_pbuffer_concat_bwd": (c_int, [c_void_p] * 2 + [c_int] * 7 + [c_void_p]),
+    "wcmc_recombine": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "wcmc_image_losses_workspace": (c_size_t, []),
+    "wcmc_image_losses": (c_int, [c_void_p] * 6 + [ctypes.POINTER(c_long), c_int, c_int, c_int, c_float] + [c_void_p] * 4
+                          + [c_size_t, c_void_p]),
+    "wcmc_random_permutation": (c_int, [c_void_p, c_long, c_void_p, ctypes.c_uint, c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
@@ -647,6 +654,98 @@ def fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batc
          inv_patch.data_ptr(), _p(inv_batch), w_patch.data_ptr(), _p(w_batch), _p(scale), float(coef_patch),
          float(coef_batch), b, s, c, h, w, dp.data_ptr(), _stream())
     return dp
+
+
+# ---- K9 / K12: step glue ------------------------------------------------------------------------------------
+def pbuffer_concat_fwd(kpcn_in, p, c0, cr):
+    """kpcn_in (B,Cin,H,W), p (B,S,C,H,W) fp32 contiguous -> (B, Cin+cr+1, H, W) = cat[kpcn_in, mean_S p[:, :, c0:c0+cr],
+    var_S(.).mean(C)/S]   (support/interfaces.py:165-180)."""
+    lib = init(p.device)
+    b, s, c, h, w = p.shape
+    cin = kpcn_in.shape[1]
+    assert kpcn_in.dtype == torch.float32 and kpcn_in.is_contiguous() and tuple(kpcn_in.shape) == (b, cin, h, w)
+    assert p.dtype == torch.float32 and p.is_contiguous()
+    out = torch.empty((b, cin + cr + 1, h, w), dtype=torch.float32, device=p.device)
+    _run(lib.wcmc_pbuffer_concat_fwd, "pbuffer_concat_fwd", (kpcn_in.numel() + out.numel() + b * s * cr * h * w) * 4.0,
+         kpcn_in.data_ptr(), p.data_ptr(), out.data_ptr(), b, s, c, c0, cr, cin, h * w, _stream())
+    return out
+
+
+def pbuffer_concat_bwd(grad_out, shape, c0, cr, cin):
+    """grad_out (B, Cin+cr+1, H, W) -> d p (B,S,C,H,W) (zeros outside the channel range)."""
+    lib = init(grad_out.device)
+    b, s, c, h, w = shape
+    grad_out = grad_out.contiguous()
+    assert grad_out.dtype == torch.float32 and tuple(grad_out.shape) == (b, cin + cr + 1, h, w)
+    dp = torch.empty(shape, dtype=torch.float32, device=grad_out.device)
+    _run(lib.wcmc_pbuffer_concat_bwd, "pbuffer_concat_bwd", (dp.numel() + b * cr * h * w) * 4.0, grad_out.data_ptr(),
+         dp.data_ptr(), b, s, c, c0, cr, cin, h * w, _stream())
+    return dp
+
+
+def _crop_view(t, h, w):
+    """Centred (h, w) crop of a (B,3,H,W) fp32 tensor as (data_ptr at the crop origin, batch / channel / row strides)."""
+    assert t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3 and t.stride(3) == 1
+    dh, dw = t.shape[2] - h, t.shape[3] - w
+    assert dh >= 0 and dw >= 0
+    y0, x0 = max(dh // 2, 0), max(dw // 2, 0)
+    return t.data_ptr() + 4 * (y0 * t.stride(2) + x0), t.stride(0), t.stride(1), t.stride(2)
+
+
+def recombine(albedo, r_d, r_s):
+    """radiance = crop(albedo) * r_d + exp(r_s) - 1; albedo (B,3,H,W) any size >= r_d's (centred crop)."""
+    lib = init(r_d.device)
+    b, _, h, w = r_d.shape
+    assert r_d.dtype == torch.float32 and r_d.is_contiguous() and r_s.dtype == torch.float32 and r_s.is_contiguous()
+    ptr, sb, sc, sh = _crop_view(albedo, h, w)
+    out = torch.empty_like(r_d)
+    _run(lib.wcmc_recombine, "recombine", r_d.numel() * 16.0, ptr, sb, sc, sh, r_d.data_ptr(), r_s.data_ptr(),
+         out.data_ptr(), b, h, w, _stream())
+    return out
+
+
+_loss_ws = {}
+
+
+def image_losses(r_d, t_d, r_s, t_s, rad, t_t, eps, want_signs):
+    """-> (sums (4,) = [L1 diffuse, L1 specular, L1 total, RelMSE total], sgn_d, sgn_s).  Predictions (B,3,h,w) fp32
+    contiguous or None; targets full-size (B,3,H,W) tensors read through a centred crop."""
+    ref = next(t for t in (r_d, r_s, rad) if t is not None)
+    lib = init(ref.device)
+    b, _, h, w = ref.shape
+    key = (ref.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        ws = _loss_ws[key] = torch.zeros(lib.wcmc_image_losses_workspace(), dtype=torch.uint8, device=ref.device)
+    ptrs, strides = [], []
+    for pred, tgt in ((r_d, t_d), (r_s, t_s), (rad, t_t)):
+        if pred is None:
+            ptrs.append(0)
+            strides += [0, 0, 0]
+            continue
+        assert pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == (b, 3, h, w)
+        ptr, sb, sc, sh = _crop_view(tgt, h, w)
+        ptrs.append(ptr)
+        strides += [sb, sc, sh]
+    sums = torch.empty(4, dtype=torch.float32, device=ref.device)
+    sgn_d = torch.empty_like(r_d) if (want_signs and r_d is not None) else None
+    sgn_s = torch.empty_like(r_s) if (want_signs and r_s is not None) else None
+    _run(lib.wcmc_image_losses, "image_losses", ref.numel() * 4.0 * 8, _p(r_d), _p(r_s), _p(rad), ptrs[0], ptrs[1], ptrs[2],
+         (c_long * 9)(*strides), b, h, w, float(eps), _p(sgn_d), _p(sgn_s), sums.data_ptr(), ws.data_ptr(), ws.numel(),
+         _stream())
+    return sums, sgn_d, sgn_s
+
+
+def random_permutation(n, state, salt=0, out=None):
+    """-> int64 (n,) pseudo-random permutation of [0, n) (keyed Feistel network, no sort).  state: int64 (2,) device
+    tensor [draw counter, 0]; every call advances the counter on the device (CUDA-graph replays draw anew)."""
+    lib = init(state.device)
+    assert state.dtype == torch.int64 and state.numel() == 2 and state.is_contiguous()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=state.device)
+    _run(lib.wcmc_random_permutation, "random_permutation", n * 8.0, out.data_ptr(), n, state.data_ptr(), int(salt) & 0xFFFFFFFF,
+         _stream())
+    return out
 
 
 # ---- K6/K7: fused PathNet MLPs ----------------------------------------------------------------------

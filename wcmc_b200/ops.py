@@ -498,3 +498,68 @@ class PathNetFn(torch.autograd.Function):
         lib.wgrad_flush()
         ctx.saved = None
         return (None, None) + tuple(g_emb) + tuple(g_unet) + tuple(g_fin)
+
+
+# ------------------------------------------------------------------------------------------------
+# K9 / K12: step glue (support/interfaces.py:165-180, :206-251; sbmc.KPCN.forward's recombination)
+# ------------------------------------------------------------------------------------------------
+class PBufferConcatFn(torch.autograd.Function):
+    """cat[kpcn_in, mean_S(p[:, :, c0:c0+cr]), var_S(.).mean(C, keepdim) / S] in one launch; the variance channel is
+    detached as in the reference, the mean carries the gradient back to the path-embedding network."""
+
+    @staticmethod
+    def forward(ctx, kpcn_in, p, c0, cr):
+        kin = kpcn_in.detach().contiguous().float()
+        pc = p.detach().contiguous().float()
+        ctx.meta = (tuple(pc.shape), c0, cr, kin.shape[1])
+        return lib.pbuffer_concat_fwd(kin, pc, c0, cr)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, c0, cr, cin = ctx.meta
+        g = g.contiguous().float()
+        dp = lib.pbuffer_concat_bwd(g, shape, c0, cr, cin) if ctx.needs_input_grad[1] else None
+        return (g[:, :cin] if ctx.needs_input_grad[0] else None), dp, None, None
+
+
+class RecombineFn(torch.autograd.Function):
+    """radiance = crop_like(albedo, r_d) * r_d + exp(r_s) - 1 (sbmc.KPCN.forward) in one launch."""
+
+    @staticmethod
+    def forward(ctx, albedo, r_d, r_s):
+        rd, rs = r_d.detach().contiguous().float(), r_s.detach().contiguous().float()
+        alb = albedo.detach().float()
+        if alb.stride(3) != 1:
+            alb = alb.contiguous()
+        ctx.save_for_backward(alb, rs)
+        return lib.recombine(alb, rd, rs)
+
+    @staticmethod
+    def backward(ctx, g):
+        alb, rs = ctx.saved_tensors
+        h, w = rs.shape[-2:]
+        y0, x0 = max((alb.shape[-2] - h) // 2, 0), max((alb.shape[-1] - w) // 2, 0)
+        a = alb[..., y0:y0 + h, x0:x0 + w]
+        return None, g * a, g * torch.exp(rs)
+
+
+class ImageLossesFn(torch.autograd.Function):
+    """(L1(r_d, t_d), L1(r_s, t_s), L1(radiance, t_t), RelativeMSE(radiance, t_t)) in one reduction launch; targets are
+    the full-size tensors (centred crop inside the kernel).  Gradients flow to r_d and r_s only: the step takes the
+    recombined image's losses under no_grad (support/interfaces.py:240-249)."""
+
+    @staticmethod
+    def forward(ctx, r_d, r_s, rad, t_d, t_s, t_t, eps):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        fix = lambda t: None if t is None else t.detach().contiguous().float()   # noqa: E731
+        sums, sgn_d, sgn_s = lib.image_losses(fix(r_d), t_d, fix(r_s), t_s, fix(rad), t_t, eps, need)
+        ctx.sgn = (sgn_d, sgn_s)
+        return sums[0], sums[1], sums[2], sums[3]
+
+    @staticmethod
+    def backward(ctx, g_d, g_s, g_t, g_r):
+        sgn_d, sgn_s = ctx.sgn
+        ctx.sgn = None
+        gd = sgn_d * g_d if (sgn_d is not None and g_d is not None) else None
+        gs = sgn_s * g_s if (sgn_s is not None and g_s is not None) else None
+        return gd, gs, None, None, None, None, None
