@@ -156,11 +156,21 @@ def bench_720p(args, KPCN, make_batch):
     streams.ENABLED = streams_on
     ms_plain = timed(resident, n)          # the number reported: no per-launch events, two streams
     e2e()
-    ms_e2e = timed(e2e, n)
+    ms_latency = timed(e2e, n)             # one frame, strictly sequential: copy in, denoise, copy out
+    # steady state of a frame SEQUENCE: transfers of neighbouring frames overlap the compute (inference.denoise_stream)
+    outs = [torch.empty((1, 3, 720, 1280), dtype=torch.float32).pin_memory() for _ in range(2)]
+    inference.denoise_stream(net, [host] * 2, outs)
+    torch.cuda.synchronize()
+    nseq = max(6, n)
+    ms_e2e = timed(lambda: inference.denoise_stream(net, [host] * nseq, outs), 1) / nseq
     n_c, ms_c, fl_c = prof.get("conv2d_k5", (0, 1.0, 0.0))
     n_k, ms_k, by_k = prof.get("kernel_apply_fwd", (0, 1.0, 0.0))
     flops = fl_c / n
     return {"ms_per_frame": round(ms_plain, 3), "e2e_ms_per_frame": round(ms_e2e, 3),
+            "e2e_single_frame_latency_ms": round(ms_latency, 3),
+            "e2e_note": "e2e_ms_per_frame: %d-frame sequence from pinned host memory, H2D / D2H of neighbouring frames "
+                        "overlapped with the compute on copy streams, every byte of every frame moved inside the timed "
+                        "region; e2e_single_frame_latency_ms: one frame, copy in -> denoise -> copy out, no overlap" % nseq,
             "h2d_bytes_per_frame": sum(v.numel() * 4 for v in host.values()), "d2h_bytes_per_frame": out_host.numel() * 4,
             "conv_tflop_per_frame": round(flops / 1e12, 3), "conv_tflops": round(fl_c / (ms_c * 1e-3) / 1e12, 1),
             "conv_ms": round(ms_c / n, 3), "kernel_apply_ms": round(ms_k / n, 3),
@@ -192,6 +202,40 @@ def mlp_flops_per_step(batch, spp, size, outc):
     fused K6-K9 kernels report in bytes: per sample-pixel 2*(36*64 + 64*64 + 64*64) + 2*(128*128 + 128*outc)."""
     per = 2.0 * (36 * 64 + 64 * 64 + 64 * 64) + 2.0 * (128 * 128 + 128 * outc)
     return 2 * 3 * per * batch * spp * size * size
+
+
+def bench_preprocess(pk):
+    """GPU preprocessing of a raw 1280x720, 4-spp OptaGen sample buffer (H,W,S,104) -> the 44-channel
+    KPCN buffer and the 37-channel path descriptors, against the HBM roofline.  Algorithmic bytes: every raw float is
+    read once (416 B per sample) by each of the two kernels' consumers -- kpcn reads the 13 raw channels it needs per
+    sample (two 28-byte runs = 4 sectors of 32 B) and writes 176 B per pixel; llpm reads one 176-byte run and writes
+    148 B per sample."""
+    import torch
+    from wcmc_b200 import preprocess
+    h, w, s = 720, 1280, 4
+    g = torch.Generator(device="cuda").manual_seed(3)
+    raw = torch.rand(h, w, s, 104, device="cuda", generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn):
+        fn()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[2]
+    ms_k = timed(lambda: preprocess.preprocess_kpcn(raw))
+    ms_l = timed(lambda: preprocess.preprocess_llpm(raw))
+    by_k = h * w * (s * 128.0 + 176.0 + 2 * 72.0)      # 4 sectors per sample + the 44-channel pixel + 18 workspace floats twice
+    by_l = h * w * s * (176.0 + 148.0)
+    return {"workload": "raw (720,1280,4,104) fp32 -> (720,1280,44) + (720,1280,4,37), L2 flushed between repetitions",
+            "kpcn_ms": round(ms_k, 4), "kpcn_gbs": round(by_k / ms_k / 1e6, 1), "kpcn_frac_of_hbm": round(by_k / ms_k / 1e6 / pk["hbm_gbs"], 4),
+            "llpm_ms": round(ms_l, 4), "llpm_gbs": round(by_l / ms_l / 1e6, 1), "llpm_frac_of_hbm": round(by_l / ms_l / 1e6 / pk["hbm_gbs"], 4)}
 
 
 def summarize_kernels(prof, steps, pk, pk_src, window_s=0.0):
@@ -267,19 +311,27 @@ def step_roofline(prof, steps, ms_step, window_s, pk, batch, world):
             "peak_kind": "sustained" if sustained else "burst", "timed_window_s": round(window_s, 3)}
 
 
-def _leave(world):
-    """End of a rank under torchrun.  The gradient all-reduce is captured INSIDE the step's CUDA graph; tearing such a
-    communicator down (dist.destroy_process_group, or the interpreter's own exit with the graph still alive) hung
-    for minutes after the result line had been printed (2-GPU run of round 1, profiles/r01final_multi2.txt).
-    Every collective of the run has completed by now (the timed regions end with a barrier + synchronize), so the
-    ranks leave without the teardown."""
+def _leave(world, graphed=None):
+    """End of a rank under torchrun: the captured step graph (it holds NCCL kernels of the in-graph gradient
+    all-reduce) is released BEFORE the communicator is destroyed -- destroying the process group with the graph still
+    alive is what hung for minutes in round 1 (profiles/r01final_multi2.txt).  A watchdog bounds the teardown anyway:
+    every collective of the run has completed by now (the timed regions end with a barrier + synchronize)."""
     if world <= 1:
         return
     import torch
+    import torch.distributed as dist
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+    t = threading.Timer(30.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    if graphed is not None:
+        graphed.release()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 def main():
@@ -345,7 +397,7 @@ def main():
                   "l_test": RelativeMSE(), "l_manif": l_manif}
     itf = KPCNInterface(models, optims, loss_funcs, types.SimpleNamespace(model_name="bench"), use_llpm_buf=True,
                         manif_learn=True, w_manif=0.1, train_branches=True, disentanglement_option="m11r11")
-    sync = ddp.GradAllReduce()
+    sync = ddp.GradAllReduce(overlap=os.environ.get("WCMC_DDP_OVERLAP", "1") != "0")
     if world > 1:
         itf.grad_sync = sync
     host = {k: v.pin_memory() for k, v in make_batch(batch=batch_per_gpu, spp=SPP, size=SIZE, seed=1234 + rank).items()}
@@ -354,6 +406,7 @@ def main():
     itf.to_train_mode()
 
     use_graph = not args.no_graph   # rng="cpu" replays too: staged permutations (support.losses.PermStage)
+    graphed = None
     if use_graph:
         from wcmc_b200.engine import GraphedTrainStep
         graphed = GraphedTrainStep(itf, dev)
@@ -431,7 +484,7 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
 
     if rank != 0:
-        _leave(world)
+        _leave(world, graphed)
         return
     pk, pk_src = peaks()
     frame = bench_720p(args, KPCN, make_batch) if (world == 1 and not args.no_720p) else None
@@ -449,7 +502,10 @@ def main():
                    "l2": "inputs_exceed_l2 (%.0f MB of step inputs + %.0f MB of saved activations > 126 MB L2)"
                          % (h2d_bytes / 1e6, 700.0),
                    "precision": "fp16 operands (loss-scaled gradients), fp32 accumulate / master weights / losses",
-                   "perm_rng": args.perm_rng, "cuda_graph": bool(use_graph), "branch_streams": bool(streams.ENABLED)},
+                   "perm_rng": args.perm_rng, "cuda_graph": bool(use_graph), "branch_streams": bool(streams.ENABLED),
+                   "grad_exchange": (None if world == 1 else ("nccl all-reduce in the step graph; dncnn's half overlapped "
+                                     "with the path-embedding networks' backward" if sync.early is not None else
+                                     "nccl all-reduce in the step graph, after both backward passes"))},
         "e2e": {"value": batch_per_gpu * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -461,13 +517,14 @@ def main():
     }
     if frame is not None:
         line["denoise_720p"] = frame
+        line["preprocess_n3"] = bench_preprocess(pk)
     if world == 1 and not args.no_cpu_baseline:
         val, threads, dt = cpu_reference_steps(2, 1, 2)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "2 timed steps of batch 2 (same 128x128, 8 spp patches) after 1 warm-up; "
                                           "%.1f s/step" % dt}
     print(json.dumps(line), flush=True)
-    _leave(world)
+    _leave(world, graphed)
 
 
 if __name__ == "__main__":

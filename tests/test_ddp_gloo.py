@@ -114,6 +114,37 @@ def _worker(rank, world, port, out_dir):
     gathered = [torch.empty_like(w1) for _ in range(world)]
     dist.all_gather(gathered, w1)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged after one step"
+    # ---- the overlapping exchange: backward cut at the p-buffers, dncnn's all-reduce started asynchronously while the
+    # path-embedding networks still back-propagate (KPCNInterface._run_backward + GradAllReduce.early) ----
+    itf.grad_sync = None
+    itf.preprocess(batch)
+    torch.manual_seed(9 + rank)
+    itf.train_batch(batch, grad_hook_mode=True)
+    g_local2 = _flat(models, grad=True).clone()
+    g_all2 = [torch.empty_like(g_local2) for _ in range(world)]
+    dist.all_gather(g_all2, g_local2)
+    calls = {"early": 0}
+
+    class Rec(ddp.GradAllReduce):
+        def early(self, ms):
+            calls["early"] += 1
+            assert list(ms) == ["dncnn"]
+            super().early(ms)
+
+        def __call__(self, ms):
+            super().__call__(ms)
+            seen["g2"] = _flat(ms, grad=True).clone()
+    itf.grad_sync = Rec()
+    itf.preprocess(batch)
+    torch.manual_seed(9 + rank)
+    itf.train_batch(batch)
+    assert calls["early"] == 1, "the overlapped path was not taken"
+    torch.testing.assert_close(seen["g2"], torch.stack(g_all2).mean(0), rtol=1e-6, atol=1e-9)
+    assert itf.grad_sync.bytes_last == g_local2.numel() * 4
+    w2 = _flat(models)
+    gathered = [torch.empty_like(w2) for _ in range(world)]
+    dist.all_gather(gathered, w2)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged after the overlapped step"
     # expected update: Adam on clip(mean gradient)
     torch.save({"w0": w0, "w1": w1, "g": seen["g"]}, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()

@@ -138,12 +138,15 @@ image_losses_kernel(const float* __restrict__ rd, const float* __restrict__ rs, 
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x < kLossSums) {       // the last CTA sums the partials in CTA order: deterministic
+    // the last CTA to finish sums the per-CTA partials: warp k takes sum k, lane-strided in a fixed order, then the
+    // fixed shuffle tree -- the result does not depend on which CTA came last
+    if (warp < kLossSums) {
         float v = 0.f;
-        for (unsigned j = 0; j < gridDim.x; ++j) v += __ldcg(partial + j * kLossSums + threadIdx.x);
-        sums[threadIdx.x] = v * inv_n * (threadIdx.x == 3 ? 0.5f : 1.0f);
-        if (threadIdx.x == 0) *ticket = 0u;
+        for (unsigned j = lane; j < gridDim.x; j += 32) v += __ldcg(partial + j * kLossSums + warp);
+        v = wcmc::warp_sum(v);
+        if (lane == 0) sums[warp] = v * inv_n * (warp == 3 ? 0.5f : 1.0f);
     }
+    if (threadIdx.x == 0) *ticket = 0u;
 }
 
 }  // namespace
@@ -197,7 +200,7 @@ extern "C" int wcmc_image_losses(const float* r_d, const float* r_s, const float
     WCMC_REQUIRE(workspace && workspace_bytes >= wcmc_image_losses_workspace(), WCMC_EWORKSPACE,
                  "image_losses: workspace too small");
     const long n = static_cast<long>(B) * 3 * h * w;
-    const int grid = static_cast<int>(std::min<long>((n + kGlueThreads - 1) / kGlueThreads, 4L * 148));
+    const int grid = static_cast<int>(std::min<long>((n + 4 * kGlueThreads - 1) / (4 * kGlueThreads), 2L * 148));
     CropView td{t_d, strides9[0], strides9[1], strides9[2]}, ts{t_s, strides9[3], strides9[4], strides9[5]},
         tt{t_t, strides9[6], strides9[7], strides9[8]};
     float* partial = static_cast<float*>(workspace);

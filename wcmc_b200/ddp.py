@@ -15,25 +15,56 @@ import torch.distributed as dist
 
 class GradAllReduce:
     """Callable(models) for KPCNInterface.grad_sync.  Works with any initialised process group
-    (nccl on GPUs, gloo in the CPU tests)."""
+    (nccl on GPUs, gloo in the CPU tests).
 
-    def __init__(self, group=None):
+    Overlap: `early(models)` may be called DURING the backward pass for models whose gradients are already complete
+    (the interface calls it for `dncnn` once the KPCN part of the traversal is done, while the two path-embedding
+    networks still back-propagate): it starts an asynchronous all-reduce of those gradients on the process group's
+    own stream.  `__call__` then only reduces what is left and waits for the early part -- under a CUDA-graph
+    capture the whole pattern becomes a fork / join inside the graph.  Every rank issues the same collectives in
+    the same order."""
+
+    def __init__(self, group=None, overlap=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bytes_last = 0
+        self._early = []           # (work, flat buffer, gradient tensors) of reductions in flight
+        if not overlap:
+            self.early = None      # the interface then keeps the single traversal + one reduction
 
-    def __call__(self, models):
+    def _flatten(self, grads):
+        return torch.cat([g.reshape(-1) for g in grads])
+
+    def early(self, models):
         if self.world == 1:
             return
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
         if not grads:
             return
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        flat.div_(self.world)
-        self.bytes_last = flat.numel() * flat.element_size()
-        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        flat = self._flatten(grads)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._early.append((work, flat, grads))
 
+    def _finish(self, flat, grads):
+        flat.div_(self.world)
+        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        return flat.numel() * flat.element_size()
+
+    def __call__(self, models):
+        if self.world == 1:
+            return
+        early, self._early = self._early, []
+        done = {id(g) for _, _, gs in early for g in gs}
+        grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None and id(p.grad) not in done]
+        nbytes = 0
+        if grads:
+            flat = self._flatten(grads)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            nbytes += self._finish(flat, grads)
+        for work, flat_e, grads_e in early:
+            work.wait()                       # the current stream waits for the collective
+            nbytes += self._finish(flat_e, grads_e)
+        self.bytes_last = nbytes
 
     def all_ranks(self, ok):
         """Logical AND of a 0-d bool tensor over the ranks (a non-finite loss on one rank must stop them all)."""

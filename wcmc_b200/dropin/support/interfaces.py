@@ -193,22 +193,54 @@ class KPCNInterface(BaseInterface):
 
     # ---- one optimisation step -----------------------------------------------------------------
     def train_batch(self, batch, grad_hook_mode=False):
-        out_manif = None
-        if self.use_llpm_buf:
-            self.models["backbone_diffuse"].zero_grad()
-            self.models["backbone_specular"].zero_grad()
-            p_buffers = self._manifold_forward(batch)
-            if self.iters % 1000 == 1:
-                self._dump_pbuffers(p_buffers)
-            _, out_manif = self._split(p_buffers)
-            batch = _with_pbuffer(batch, p_buffers, self._reg_channels(p_buffers))
-        self.models["dncnn"].zero_grad()
-        out = self._regress_forward(batch)
-        loss_dict = self._backward(batch, out, out_manif)
+        loss_dict = self._forward_backward(batch, dump=self.iters % 1000 == 1)
         if grad_hook_mode:  # gradients only; no logging, no parameter update
             return
         self._logging(loss_dict)
         self._optimization()
+
+    def _forward_backward(self, batch, dump=False):
+        """Forward passes + the two backward passes of `train_batch` (:139-251) -> loss dict; shared with the
+        CUDA-graph step (wcmc_b200.engine.GraphedTrainStep captures exactly this)."""
+        out_manif = None
+        self._p_full = None
+        if self.use_llpm_buf:
+            self.models["backbone_diffuse"].zero_grad()
+            self.models["backbone_specular"].zero_grad()
+            p_buffers = self._manifold_forward(batch)
+            if dump:
+                self._dump_pbuffers(p_buffers)
+            _, out_manif = self._split(p_buffers)
+            batch = _with_pbuffer(batch, p_buffers, self._reg_channels(p_buffers))
+            self._p_full = p_buffers
+        self.models["dncnn"].zero_grad()
+        out = self._regress_forward(batch)
+        try:
+            return self._backward(batch, out, out_manif)
+        finally:
+            self._p_full = None
+
+    def _run_backward(self, roots):
+        """One autograd traversal with both loss roots (same gradients as the reference's `L_diffuse.backward();
+        L_specular.backward()`, :237-238).  Data parallel with an overlapping exchange (`grad_sync.early`): the
+        traversal is cut at the p-buffers -- first the KPCN part (gradients of `dncnn` and of the two p-buffers),
+        then the all-reduce of `dncnn`'s gradients is started asynchronously, then the path-embedding networks
+        back-propagate while those 23.6 MB are on the wire."""
+        early = getattr(self.grad_sync, "early", None)
+        p_full = getattr(self, "_p_full", None)
+        if early is None or p_full is None or getattr(self.grad_sync, "world", 1) == 1:
+            torch.autograd.backward(roots)
+            return
+        params = [p for p in self.models["dncnn"].parameters() if p.requires_grad]
+        p_outs = [p_full["diffuse"], p_full["specular"]]
+        grads = torch.autograd.grad(roots, params + p_outs, allow_unused=True)
+        for p, g in zip(params, grads):
+            if g is not None:
+                p.grad = g if p.grad is None else p.grad + g
+        early({"dncnn": self.models["dncnn"]})
+        pairs = [(o, g) for o, g in zip(p_outs, grads[len(params):]) if g is not None]
+        if pairs:
+            torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
 
     def _backward(self, batch, out, p_buffers):
         assert "radiance" in out and "diffuse" in out and "specular" in out
@@ -232,7 +264,7 @@ class KPCNInterface(BaseInterface):
             # the reference calls L_diffuse.backward(); L_specular.backward() (:237-238): the two graphs share no
             # parameter, so one traversal with both roots gives the same gradients and lets the branches' backward
             # kernels (recorded on different streams) overlap
-            torch.autograd.backward([branch_loss["diffuse"], branch_loss["specular"]])
+            self._run_backward([branch_loss["diffuse"], branch_loss["specular"]])
             with torch.no_grad():
                 losses["l_total"] = fused["l_total"] if fused is not None else \
                     self.loss_funcs["l_recon"](total, tgt_total).detach()

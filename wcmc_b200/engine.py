@@ -52,18 +52,7 @@ class GraphedTrainStep:
         _losses.DEFER_FINITE_CHECK = True
         _losses.FINITE_FLAGS.clear()
         try:
-            batch = self.static
-            out_manif = None
-            if itf.use_llpm_buf:
-                itf.models["backbone_diffuse"].zero_grad()
-                itf.models["backbone_specular"].zero_grad()
-                p_buffers = itf._manifold_forward(batch)
-                _, out_manif = itf._split(p_buffers)
-                from support.interfaces import _with_pbuffer
-                batch = _with_pbuffer(batch, p_buffers, itf._reg_channels(p_buffers))
-            itf.models["dncnn"].zero_grad()
-            out = itf._regress_forward(batch)
-            loss = itf._backward(batch, out, out_manif)
+            loss = itf._forward_backward(self.static)
             flags = list(_losses.FINITE_FLAGS)
         finally:
             _losses.DEFER_FINITE_CHECK = False
@@ -96,6 +85,15 @@ class GraphedTrainStep:
                     self.flags = ok
                 self.ok_i32 = ok.to(torch.int32).reshape(1)
                 self.fused.step(clip=1.0, ok_flag=self.ok_i32, count=False)
+
+    def release(self):
+        """Drops the captured graph and its static buffers (call before tearing a process group down: the graph
+        holds the NCCL kernels of the in-graph gradient all-reduce)."""
+        torch.cuda.synchronize()
+        if self.graph is not None:
+            self.graph.reset()
+        self.graph = None
+        self.loss = self.flags = None
 
     def __call__(self, batch):
         itf = self.itf

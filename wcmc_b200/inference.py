@@ -39,6 +39,54 @@ def denoise_frame(kpcn, batch, padded=False):
     return kpcn(batch)
 
 
+@torch.no_grad()
+def denoise_raw_frame(kpcn, raw):
+    """raw (H,W,S,104) fp32 cuda: the renderer's per-sample buffer of one frame.  GPU preprocessing (SURVEY 8(f) N3:
+    `DenoiseDataset._preprocess_kpcn`, datasets.py:487-582, as kernels) -> whole-frame KPCN denoise; nothing visits the
+    host.  -> dict(radiance, diffuse, specular), each (1,3,H,W)."""
+    from . import preprocess
+    return denoise_frame(kpcn, preprocess.frame_batch(raw))
+
+
+@torch.no_grad()
+def denoise_stream(kpcn, host_frames, out_host=None, device=None):
+    """Denoises a sequence of frames held in (pinned) host memory with the transfers overlapped: the host -> device
+    copy of frame i+1 runs on a copy stream while frame i is computed (engine.DevicePrefetcher) and the radiance of
+    frame i goes back to pinned host memory on a third stream, so a frame costs max(compute, transfer) instead of
+    their sum (the reference's loop does blocking `.cuda()` / `.cpu()` per tile, test_models.py:55-75).
+    host_frames: iterable of dicts (un-padded kpcn_* tensors, (B,C,H,W)); out_host: optional list of pinned
+    (B,3,H,W) buffers, reused round-robin.  Returns the list of host radiance tensors in frame order; the caller
+    synchronises (`torch.cuda.synchronize()`) before reading them."""
+    from .engine import DevicePrefetcher
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    pf = DevicePrefetcher(host_frames, device)
+    out_stream = torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+    results = []
+    slot_free = {}
+    for i, batch in enumerate(pf):
+        rad = denoise_frame(kpcn, batch)["radiance"]
+        pf.release()
+        done = torch.cuda.Event()
+        done.record(cur)
+        if out_host:
+            host = out_host[i % len(out_host)]
+            if id(host) in slot_free:
+                slot_free[id(host)].synchronize()      # the previous copy into this pinned buffer has finished
+        else:
+            host = torch.empty(rad.shape, dtype=rad.dtype).pin_memory()
+        with torch.cuda.stream(out_stream):
+            out_stream.wait_event(done)
+            host.copy_(rad, non_blocking=True)
+            rad.record_stream(out_stream)
+            ev = torch.cuda.Event()
+            ev.record(out_stream)
+            slot_free[id(host)] = ev
+        results.append(host)
+    cur.wait_stream(out_stream)
+    return results
+
+
 # ------------------------------------------------------------------------------------------------
 # SURVEY.md §8(f) N2: the reference's tile protocol (FullImageDataset + test_models.inference) and its
 # one-pass equivalent

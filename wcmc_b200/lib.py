@@ -790,7 +790,7 @@ def pathnet_final_fwd(emb, emb_coff, prop, prop_coff, packed, acts, slope, outc,
     return out
 
 
-# ---- preprocessing of raw sample buffers (not yet validated on a GPU) ----------------
+# ---- preprocessing of raw sample buffers -------------------------------------------
 def preprocess_kpcn(raw):
     """raw (H,W,S,104) fp32 cuda -> (H,W,44) fp32: DenoiseDataset._preprocess_kpcn (datasets.py:487-582)."""
     lib = init(raw.device)
