@@ -43,7 +43,7 @@ constexpr int kGgSmemBudget = 208 * 1024;
 
 struct GgLayer {
     CUtensorMap tmdy, tmx;
-    float* ws;
+    float* ws;                       // slabs [slab][tap][cout_p][cin_p]
     int tiles_x, tiles_y, total_tiles;
     int ksize, pad, taps;
     int cin_p, cout_p;
@@ -51,49 +51,62 @@ struct GgLayer {
     int cstride, tpg, groups;        // TMEM column stride of a tap, taps per group, groups
     int halo_w, box_h, b_plane, b_planes;
     int stage_bytes, stages;
-    int per_team, teams, first_cta;
     int dtype;
 };
 
+// A CHAIN = layers of identical structure (filter size, channel counts), e.g. the seven 100->100 layers of a KPCN
+// stack: their pixel tiles form one line that the chain's teams cut into equal contiguous pieces, whatever the layer
+// boundaries -- a team that crosses a boundary drains its accumulators into the finished layer's slab and goes on
+// with the next layer's tensor maps.  Balance is then limited by three or four chains, not by nine layers.
+struct GgSeg { int layer, t0, t1, slab; };            // tiles [t0, t1) of `layer`, partial sums -> slab `slab`
+struct GgChain { int first_cta, per_team, teams, first_team; };
+constexpr int kGgMaxSeg = 4;
+constexpr int kGgMaxTeams = 148;
+
 struct GgParams {
-    int n_layers;
+    int n_layers, n_chains;
+    GgChain C[kGgMaxLayers];
     GgLayer L[kGgMaxLayers];
+    GgSeg S[kGgMaxTeams][kGgMaxSeg];
+    unsigned char nseg[kGgMaxTeams];
 };
 
 __global__ void __launch_bounds__(kGgThreads, 1) conv_wgrad_group_kernel(const __grid_constant__ GgParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    __shared__ uint64_t full[kGgMaxStages], empty[kGgMaxStages], acc_full;
+    __shared__ uint64_t full[kGgMaxStages], empty[kGgMaxStages], acc_full, acc_empty;
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // ---- which layer, which member of which team ----
-    int li = 0;
-    while (li + 1 < P.n_layers && static_cast<int>(blockIdx.x) >= P.L[li + 1].first_cta) ++li;
-    const GgLayer& L = P.L[li];
-    const int local = blockIdx.x - L.first_cta;
-    const int team = local / L.per_team;
-    int r = local - team * L.per_team;
-    const int grp = r % L.groups; r /= L.groups;
-    const int cit = r % L.ci_tiles;
-    const int mtile = r / L.ci_tiles;
-    const int tap0 = grp * L.tpg;
-    const int ntap = min(L.tpg, L.taps - tap0);
-    const int ky_first = tap0 / L.ksize;
-    const int ci0 = cit * L.nt, co0 = mtile * 128;
-    const int my_tiles = (L.total_tiles - team + L.teams - 1) / L.teams;
-    const int stages = L.stages;
+    // ---- which chain, which member of which team ----
+    int ci_ = 0;
+    while (ci_ + 1 < P.n_chains && static_cast<int>(blockIdx.x) >= P.C[ci_ + 1].first_cta) ++ci_;
+    const GgChain& C = P.C[ci_];
+    const int local = blockIdx.x - C.first_cta;
+    const int team_l = local / C.per_team;
+    const int team = C.first_team + team_l;              // row of the segment table
+    const int nseg = P.nseg[team];
+    const GgLayer& L0 = P.L[P.S[team][0].layer];         // structure (identical for every layer of the chain)
+    int r = local - team_l * C.per_team;
+    const int grp = r % L0.groups; r /= L0.groups;
+    const int cit = r % L0.ci_tiles;
+    const int mtile = r / L0.ci_tiles;
+    const int tap0 = grp * L0.tpg;
+    const int ntap = min(L0.tpg, L0.taps - tap0);
+    const int ky_first = tap0 / L0.ksize;
+    const int ci0 = cit * L0.nt, co0 = mtile * 128;
+    const int stages = L0.stages;
+    const int stage_bytes = L0.stage_bytes;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&L.tmdy);
-        tma_prefetch_desc(&L.tmx);
         for (int i = 0; i < stages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 512);
@@ -104,91 +117,113 @@ __global__ void __launch_bounds__(kGgThreads, 1) conv_wgrad_group_kernel(const _
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t stage_tx = static_cast<uint32_t>(2 * kGgAPlane + L.b_planes * L.halo_w * L.box_h * 128);
+            const uint32_t stage_tx = static_cast<uint32_t>(2 * kGgAPlane + L0.b_planes * L0.halo_w * L0.box_h * 128);
             int s = 0, ph = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const int tile = team + i * L.teams;
-                const int tx = tile % L.tiles_x;
-                const int ty = (tile / L.tiles_x) % L.tiles_y;
-                const int n = tile / (L.tiles_x * L.tiles_y);
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], stage_tx);
-                uint8_t* st = smem + s * L.stage_bytes;
-                tma_load_4d(st, &L.tmdy, &full[s], co0, tx * kGgTileW, ty * kGgTileH, n);
-                tma_load_4d(st + kGgAPlane, &L.tmdy, &full[s], co0 + 64, tx * kGgTileW, ty * kGgTileH, n);
-                for (int pl = 0; pl < L.b_planes; ++pl)
-                    tma_load_4d(st + 2 * kGgAPlane + pl * L.b_plane, &L.tmx, &full[s], ci0 + pl * 64,
-                                tx * kGgTileW - L.pad, ty * kGgTileH - L.pad + ky_first, n);
-                if (++s == stages) { s = 0; ph ^= 1; }
+            for (int sg = 0; sg < nseg; ++sg) {
+                const GgSeg seg = P.S[team][sg];
+                const GgLayer& L = P.L[seg.layer];
+                tma_prefetch_desc(&L.tmdy);
+                tma_prefetch_desc(&L.tmx);
+                const int per_img = L.tiles_x * L.tiles_y;
+                for (int tile = seg.t0; tile < seg.t1; ++tile) {
+                    const int n = tile / per_img;
+                    const int rr = tile - n * per_img;
+                    const int ty = rr / L.tiles_x, tx = rr - ty * L.tiles_x;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], stage_tx);
+                    uint8_t* st = smem + s * stage_bytes;
+                    tma_load_4d(st, &L.tmdy, &full[s], co0, tx * kGgTileW, ty * kGgTileH, n);
+                    tma_load_4d(st + kGgAPlane, &L.tmdy, &full[s], co0 + 64, tx * kGgTileW, ty * kGgTileH, n);
+                    for (int pl = 0; pl < L.b_planes; ++pl)
+                        tma_load_4d(st + 2 * kGgAPlane + pl * L.b_plane, &L.tmx, &full[s], ci0 + pl * 64,
+                                    tx * kGgTileW - L.pad, ty * kGgTileH - L.pad + ky_first, n);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         // MMA issuer: warp-uniform control flow, one elected lane issues.
-        const uint32_t idesc = make_idesc_f16(128, L.nt, 1, 1, L.dtype, L.dtype);
-        const uint32_t b_sbo = static_cast<uint32_t>(L.halo_w * 128);
+        const uint32_t idesc = make_idesc_f16(128, L0.nt, 1, 1, L0.dtype, L0.dtype);
+        const uint32_t b_sbo = static_cast<uint32_t>(L0.halo_w * 128);
         const uint32_t a_hi = static_cast<uint32_t>(make_sdesc_sw128(0, kGgAPlane, 1024, 0) >> 32);
         const uint32_t b_hi = static_cast<uint32_t>(make_sdesc_sw128(0, 0, b_sbo, 0) >> 32);
         const uint32_t a_lbo = static_cast<uint32_t>(kGgAPlane >> 4) << 16;
-        const uint32_t b_lbo = static_cast<uint32_t>(L.b_plane >> 4) << 16;
-        const uint32_t b_kstep = static_cast<uint32_t>(2 * L.halo_w * 8);     // two halo rows per K16 step (16-byte units)
-        const int row_step = (L.halo_w - L.ksize) * 8;
-        const int kx0 = tap0 - ky_first * L.ksize;
+        const uint32_t b_lbo = static_cast<uint32_t>(L0.b_plane >> 4) << 16;
+        const uint32_t b_kstep = static_cast<uint32_t>(2 * L0.halo_w * 8);     // two halo rows per K16 step (16-byte units)
+        const int row_step = (L0.halo_w - L0.ksize) * 8;
+        const int kx0 = tap0 - ky_first * L0.ksize;
+        const int ksize = L0.ksize, cstride = L0.cstride;
         int s = 0, ph = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(smem + s * L.stage_bytes);
-            const uint32_t a_lo = a_lbo | (a_base >> 4);
-            uint32_t b_lo = b_lbo | ((a_base + 2 * kGgAPlane + static_cast<uint32_t>(kx0 * 128)) >> 4);
-            int kx = kx0;
-            if (elect_one()) {
-                for (int tl = 0; tl < ntap; ++tl) {
-                    const uint32_t d = tmem_base + tl * L.cstride;
-#pragma unroll
-                    for (int j = 0; j < kGgTileH / 2; ++j) {
-                        const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + j * 128);
-                        const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + j * b_kstep);
-                        umma_bf16(d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
-                    }
-                    b_lo += 8;
-                    if (++kx == L.ksize) { kx = 0; b_lo += row_step; }
-                }
-                umma_commit(&empty[s]);
+        for (int sg = 0; sg < nseg; ++sg) {
+            const int ntiles = P.S[team][sg].t1 - P.S[team][sg].t0;
+            if (sg > 0) {                      // the epilogue warps have drained the previous segment's accumulators
+                mbar_wait(&acc_empty, (sg - 1) & 1);
+                tc_fence_after();
             }
+            for (int i = 0; i < ntiles; ++i) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + s * stage_bytes);
+                const uint32_t a_lo = a_lbo | (a_base >> 4);
+                uint32_t b_lo = b_lbo | ((a_base + 2 * kGgAPlane + static_cast<uint32_t>(kx0 * 128)) >> 4);
+                int kx = kx0;
+                if (elect_one()) {
+                    for (int tl = 0; tl < ntap; ++tl) {
+                        const uint32_t d = tmem_base + tl * cstride;
+#pragma unroll
+                        for (int j = 0; j < kGgTileH / 2; ++j) {
+                            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + j * 128);
+                            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + j * b_kstep);
+                            umma_bf16(d, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                        }
+                        b_lo += 8;
+                        if (++kx == ksize) { kx = 0; b_lo += row_step; }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) umma_commit(&acc_full);
             __syncwarp();
-            if (++s == stages) { s = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(&acc_full);
-        __syncwarp();
     } else {
         // epilogue: TMEM lane = cout row, columns = (tap, cin)
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
-        mbar_wait(&acc_full, 0);
-        tc_fence_after();
-        int ncc = (L.cin_p - ci0) >> 4;
-        if (ncc > (L.nt >> 4)) ncc = L.nt >> 4;
-        const size_t mat = static_cast<size_t>(L.cout_p) * L.cin_p;
-        for (int tl = 0; tl < ntap; ++tl) {
-            float* dst = L.ws + (static_cast<size_t>(team) * L.taps + (tap0 + tl)) * mat +
-                         static_cast<size_t>(co) * L.cin_p + ci0;
-            for (int cc = 0; cc < ncc; ++cc) {
-                uint32_t v[16];
-                if (my_tiles > 0) {
-                    tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * L.cstride + cc * 16, v);
-                    tmem_ld_wait16(v);
-                } else {
+        int ncc = (L0.cin_p - ci0) >> 4;
+        if (ncc > (L0.nt >> 4)) ncc = L0.nt >> 4;
+        const size_t mat = static_cast<size_t>(L0.cout_p) * L0.cin_p;
+        for (int sg = 0; sg < nseg; ++sg) {
+            const GgSeg seg = P.S[team][sg];
+            const GgLayer& L = P.L[seg.layer];
+            const bool any = seg.t1 > seg.t0;
+            mbar_wait(&acc_full, sg & 1);
+            tc_fence_after();
+            for (int tl = 0; tl < ntap; ++tl) {
+                float* dst = L.ws + (static_cast<size_t>(seg.slab) * L.taps + (tap0 + tl)) * mat +
+                             static_cast<size_t>(co) * L.cin_p + ci0;
+                for (int cc = 0; cc < ncc; ++cc) {
+                    uint32_t v[16];
+                    if (any) {
+                        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * L.cstride + cc * 16, v);
+                        tmem_ld_wait16(v);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = 0;
-                }
-                if (co < L.cout_p) {
-                    float4* o = reinterpret_cast<float4*>(dst + cc * 16);
+                        for (int i = 0; i < 16; ++i) v[i] = 0;
+                    }
+                    if (co < L.cout_p) {
+                        float4* o = reinterpret_cast<float4*>(dst + cc * 16);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        for (int i = 0; i < 4; ++i)
+                            o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty);
         }
     }
     tc_fence_before();
@@ -273,36 +308,99 @@ int gg_plan_layer(const wcmc_wgrad_layer& l, GgPlan* p) {
     return 0;
 }
 
-double gg_cta_cost(const GgPlan& p) {
-    const int tiles = (p.total_tiles + p.teams - 1) / p.teams;
-    return tiles * p.tile_clk + 6000.0;    // + prologue / epilogue
+// ---- chains, teams, segments --------------------------------------------------------------------------------
+struct GgChainPlan {
+    std::vector<int> layers;       // indices into the launch's layer list, in order
+    int per_team = 0, teams = 1;
+    long tiles = 0;                // pixel tiles of all its layers
+    double tile_clk = 0.0;
+};
+
+bool gg_same_structure(const wcmc_wgrad_layer& a, const GgPlan& pa, const wcmc_wgrad_layer& b, const GgPlan& pb) {
+    return a.ksize == b.ksize && a.cin == b.cin && a.cin_p == b.cin_p && a.cout_p == b.cout_p && pa.nt == pb.nt &&
+           pa.cstride == pb.cstride && pa.tpg == pb.tpg && pa.stage_bytes == pb.stage_bytes && pa.stages == pb.stages;
 }
 
-// deals the SMs out to the layers: every layer starts with one team, the rest go one team at a time to the layer
-// whose CTAs currently have the most work
-int gg_assign(std::vector<GgPlan>& plans, int sms) {
+double gg_chain_cost(const GgChainPlan& c) {
+    const long tiles = (c.tiles + c.teams - 1) / c.teams;
+    return tiles * c.tile_clk + 6000.0 * (1.0 + c.layers.size() / static_cast<double>(c.teams));   // + prologue / drains
+}
+
+// One launch: chains of structurally identical layers; the SMs are dealt out one team at a time to the chain whose
+// CTAs currently carry the most work; each chain's tile line is then cut into equal contiguous pieces.
+struct GgLaunchPlan {
+    std::vector<GgChainPlan> chains;
+    std::vector<std::vector<GgSeg>> segs;     // per team (global order: chain by chain)
+    std::vector<int> slabs;                   // per layer: number of partial-sum slabs
+    int ctas = 0;
+};
+
+int gg_plan_launch(const wcmc_wgrad_layer* layers, const std::vector<GgPlan>& plans, int first, int n, int sms,
+                   GgLaunchPlan* out) {
+    std::vector<GgChainPlan>& ch = out->chains;
+    for (int k = 0; k < n; ++k) {
+        const int i = first + k;
+        int found = -1;
+        for (size_t c = 0; c < ch.size(); ++c)
+            if (gg_same_structure(layers[first + ch[c].layers[0]], plans[first + ch[c].layers[0]], layers[i], plans[i])) {
+                found = static_cast<int>(c);
+                break;
+            }
+        if (found < 0) {
+            GgChainPlan c;
+            c.per_team = plans[i].per_team;
+            c.tile_clk = plans[i].tile_clk;
+            ch.push_back(c);
+            found = static_cast<int>(ch.size()) - 1;
+        }
+        ch[found].layers.push_back(k);
+        ch[found].tiles += plans[i].total_tiles;
+    }
     int used = 0;
-    for (auto& p : plans) used += p.per_team;
+    for (auto& c : ch) used += c.per_team;
     if (used > sms) return -1;
     for (;;) {
         int best = -1;
         double worst = 0.0;
-        for (size_t i = 0; i < plans.size(); ++i) {
-            const GgPlan& p = plans[i];
-            if (p.teams >= p.total_tiles || used + p.per_team > sms) continue;
-            const double c = gg_cta_cost(p);
+        for (size_t i = 0; i < ch.size(); ++i) {
+            if (ch[i].teams >= ch[i].tiles || used + ch[i].per_team > sms) continue;
+            const double c = gg_chain_cost(ch[i]);
             if (c > worst) { worst = c; best = static_cast<int>(i); }
         }
         if (best < 0) break;
-        // stop when the most loaded layer cannot be helped any more (its team would not fit): adding teams elsewhere
-        // only adds slab traffic
         double top = 0.0;
-        for (const auto& p : plans) top = std::max(top, gg_cta_cost(p));
-        if (gg_cta_cost(plans[best]) < 0.85 * top) break;
-        plans[best].teams += 1;
-        used += plans[best].per_team;
+        for (const auto& c : ch) top = std::max(top, gg_chain_cost(c));
+        if (gg_chain_cost(ch[best]) < 0.85 * top) break;     // the most loaded chain cannot be helped: stop adding slabs
+        ch[best].teams += 1;
+        used += ch[best].per_team;
     }
-    return used;
+    out->ctas = used;
+    out->slabs.assign(n, 0);
+    for (auto& c : ch) {
+        // a team that would cross more than kGgMaxSeg layers (many tiny layers, one team) cannot happen with the
+        // shapes of the path; guard anyway by giving such a chain one team per layer at least
+        for (int t = 0; t < c.teams; ++t) {
+            const long b = c.tiles * t / c.teams, e = c.tiles * (t + 1) / c.teams;
+            std::vector<GgSeg> sg;
+            long base = 0;
+            for (int k : c.layers) {
+                const long nt = plans[first + k].total_tiles;
+                const long lo = std::max(b, base), hi = std::min(e, base + nt);
+                if (hi > lo) {
+                    GgSeg s;
+                    s.layer = k;
+                    s.t0 = static_cast<int>(lo - base);
+                    s.t1 = static_cast<int>(hi - base);
+                    s.slab = out->slabs[k]++;
+                    sg.push_back(s);
+                }
+                base += nt;
+            }
+            if (sg.empty() || sg.size() > static_cast<size_t>(kGgMaxSeg)) return -2;
+            out->segs.push_back(sg);
+        }
+    }
+    return 0;
 }
 
 int gg_check_layer(const wcmc_wgrad_layer& l, int i) {
@@ -320,34 +418,42 @@ int gg_check_layer(const wcmc_wgrad_layer& l, int i) {
     return WCMC_OK;
 }
 
-size_t gg_layer_ws(const wcmc_wgrad_layer& l, const GgPlan& p) {
-    return static_cast<size_t>(p.teams) * l.ksize * l.ksize * l.cout_p * l.cin_p * sizeof(float);
+size_t gg_layer_ws(const wcmc_wgrad_layer& l, int slabs) {
+    return static_cast<size_t>(slabs) * l.ksize * l.ksize * l.cout_p * l.cin_p * sizeof(float);
 }
 
-// splits [first, first + n) into launches of at most kGgMaxLayers layers whose one-team-each footprint fits the SMs
-int gg_chunks(const wcmc_wgrad_layer* layers, int n, std::vector<std::pair<int, int>>* out,
-              std::vector<GgPlan>* plans_out) {
-    const int sms = wcmc_num_sms();
+// splits the layer list into launches of at most kGgMaxLayers layers whose one-team-per-chain footprint fits the SMs
+struct GgLaunch { int first, n; GgLaunchPlan plan; };
+
+int gg_chunks(const wcmc_wgrad_layer* layers, int n, std::vector<GgLaunch>* out, std::vector<GgPlan>* plans_out) {
+    const int sms = std::min(wcmc_num_sms(), kGgMaxTeams);
+    plans_out->resize(n);
+    for (int i = 0; i < n; ++i) {
+        gg_plan_layer(layers[i], &(*plans_out)[i]);
+        if ((*plans_out)[i].per_team > sms) {
+            wcmc_set_error("wgrad_group: layer %d needs %d CTAs per team (> %d SMs)", i, (*plans_out)[i].per_team, sms);
+            return WCMC_ESHAPE;
+        }
+    }
     int i = 0;
     while (i < n) {
-        std::vector<GgPlan> plans;
-        int used = 0, j = i;
-        while (j < n && j - i < kGgMaxLayers) {
-            GgPlan p;
-            gg_plan_layer(layers[j], &p);
-            if (p.per_team > sms) {
-                wcmc_set_error("wgrad_group: layer %d needs %d CTAs per team (> %d SMs)", j, p.per_team, sms);
+        int cnt = std::min(kGgMaxLayers, n - i);
+        for (;;) {
+            GgLaunch L;
+            L.first = i;
+            L.n = cnt;
+            const int rc = gg_plan_launch(layers, *plans_out, i, cnt, sms, &L.plan);
+            if (rc == 0) {
+                out->push_back(L);
+                break;
+            }
+            if (cnt == 1) {
+                wcmc_set_error("wgrad_group: cannot plan layer %d (%d)", i, rc);
                 return WCMC_ESHAPE;
             }
-            if (used + p.per_team > sms) break;
-            used += p.per_team;
-            plans.push_back(p);
-            ++j;
+            cnt = (cnt + 1) / 2;     // fewer layers per launch
         }
-        gg_assign(plans, sms);
-        out->push_back({i, j - i});
-        for (auto& p : plans) plans_out->push_back(p);
-        i = j;
+        i += cnt;
     }
     return WCMC_OK;
 }
@@ -368,11 +474,12 @@ extern "C" size_t wcmc_conv2d_wgrad_group_workspace(const wcmc_wgrad_layer* laye
     }
     for (int i = 0; i < n; ++i)
         if (gg_check_layer(layers[i], i) != WCMC_OK) return 0;
-    std::vector<std::pair<int, int>> chunks;
+    std::vector<GgLaunch> launches;
     std::vector<GgPlan> plans;
-    if (gg_chunks(layers, n, &chunks, &plans) != WCMC_OK) return 0;
+    if (gg_chunks(layers, n, &launches, &plans) != WCMC_OK) return 0;
     size_t tot = 0;
-    for (int i = 0; i < n; ++i) tot += (gg_layer_ws(layers[i], plans[i]) + 255) / 256 * 256;
+    for (const auto& L : launches)
+        for (int k = 0; k < L.n; ++k) tot += (gg_layer_ws(layers[L.first + k], L.plan.slabs[k]) + 255) / 256 * 256;
     return tot;
 }
 
@@ -403,23 +510,24 @@ extern "C" int wcmc_conv2d_wgrad_group(const wcmc_wgrad_layer* layers, int n, in
         int rc = gg_check_layer(layers[i], i);
         if (rc) return rc;
     }
-    std::vector<std::pair<int, int>> chunks;
+    std::vector<GgLaunch> launches;
     std::vector<GgPlan> plans;
-    int rc = gg_chunks(layers, n, &chunks, &plans);
+    int rc = gg_chunks(layers, n, &launches, &plans);
     if (rc) return rc;
     std::vector<wcmc_wgrad_reduce_desc> red(n);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     size_t off = 0;
-    for (const auto& ch : chunks) {
-        GgParams P;
-        P.n_layers = ch.second;
-        int cta = 0, smem_need = 0;
-        for (int k = 0; k < ch.second; ++k) {
-            const int i = ch.first + k;
+    static thread_local GgParams P;     // 16 KB: kept off the stack; a launch copies it into the kernel parameters
+    for (const auto& LN : launches) {
+        P.n_layers = LN.n;
+        int smem_need = 0;
+        for (int k = 0; k < LN.n; ++k) {
+            const int i = LN.first + k;
             const wcmc_wgrad_layer& l = layers[i];
             const GgPlan& p = plans[i];
             GgLayer& G = P.L[k];
-            const size_t need = gg_layer_ws(l, p);
+            const int slabs = LN.plan.slabs[k];
+            const size_t need = gg_layer_ws(l, slabs);
             WCMC_REQUIRE(off + need <= workspace_bytes, WCMC_EWORKSPACE, "wgrad_group: workspace too small (%zu < %zu)",
                          workspace_bytes, off + need);
             G.ws = reinterpret_cast<float*>(ws + off);
@@ -451,15 +559,31 @@ extern "C" int wcmc_conv2d_wgrad_group(const wcmc_wgrad_layer* layers, int n, in
             G.cstride = p.cstride; G.tpg = p.tpg; G.groups = p.groups;
             G.halo_w = p.halo_w; G.box_h = p.box_h; G.b_plane = p.b_plane; G.b_planes = p.b_planes;
             G.stage_bytes = p.stage_bytes; G.stages = p.stages;
-            G.per_team = p.per_team; G.teams = p.teams; G.first_cta = cta;
             G.dtype = dtype;
-            cta += p.per_team * p.teams;
             smem_need = std::max(smem_need, p.stage_bytes * p.stages);
             wcmc_wgrad_reduce_desc& d = red[i];
             d.ws = G.ws; d.dw = l.dw; d.scale = l.scale;
-            d.nsplit = p.teams; d.nsplit_b = p.teams; d.taps_a = 0;
+            d.nsplit = slabs; d.nsplit_b = slabs; d.taps_a = 0;
             d.cout = l.cout; d.cin = l.cin; d.taps = G.taps; d.cout_p = l.cout_p; d.cin_p = l.cin_p;
             d.accumulate = l.accumulate;
+        }
+        P.n_chains = static_cast<int>(LN.plan.chains.size());
+        int cta = 0, team = 0;
+        for (int c = 0; c < P.n_chains; ++c) {
+            const GgChainPlan& cp = LN.plan.chains[c];
+            P.C[c].first_cta = cta;
+            P.C[c].per_team = cp.per_team;
+            P.C[c].teams = cp.teams;
+            P.C[c].first_team = team;
+            cta += cp.per_team * cp.teams;
+            team += cp.teams;
+        }
+        WCMC_REQUIRE(team <= kGgMaxTeams && team == static_cast<int>(LN.plan.segs.size()), WCMC_ESHAPE,
+                     "wgrad_group: internal plan error (%d teams)", team);
+        for (int t = 0; t < team; ++t) {
+            const auto& sg = LN.plan.segs[t];
+            P.nseg[t] = static_cast<unsigned char>(sg.size());
+            for (size_t k = 0; k < sg.size(); ++k) P.S[t][k] = sg[k];
         }
         const int smem_bytes = smem_need + 1024;
         WCMC_FUNC_SMEM(conv_wgrad_group_kernel, kGgSmemBudget + 1024);
@@ -469,7 +593,8 @@ extern "C" int wcmc_conv2d_wgrad_group(const wcmc_wgrad_layer* layers, int n, in
     return wcmc_wgrad_reduce_batch(red.data(), n, stream_);
 }
 
-// Plan of one chunk for tools / tests: teams per layer (host only).
+// Plan for tools / tests (host only): per layer the number of partial-sum slabs (= K-split teams that touch it), the
+// CTAs of its chain, taps per group and the TMEM column stride.
 extern "C" int wcmc_conv2d_wgrad_group_plan(const wcmc_wgrad_layer* layers, int n, int* teams_out, int* ctas_out,
                                             int* tpg_out, int* cstride_out) {
     WCMC_REQUIRE(layers != nullptr && n > 0, WCMC_ESHAPE, "wgrad_group_plan: no layers");
@@ -477,15 +602,20 @@ extern "C" int wcmc_conv2d_wgrad_group_plan(const wcmc_wgrad_layer* layers, int 
         int rc = gg_check_layer(layers[i], i);
         if (rc) return rc;
     }
-    std::vector<std::pair<int, int>> chunks;
+    std::vector<GgLaunch> launches;
     std::vector<GgPlan> plans;
-    int rc = gg_chunks(layers, n, &chunks, &plans);
+    int rc = gg_chunks(layers, n, &launches, &plans);
     if (rc) return rc;
-    for (int i = 0; i < n; ++i) {
-        if (teams_out) teams_out[i] = plans[i].teams;
-        if (ctas_out) ctas_out[i] = plans[i].teams * plans[i].per_team;
-        if (tpg_out) tpg_out[i] = plans[i].tpg;
-        if (cstride_out) cstride_out[i] = plans[i].cstride;
+    for (const auto& L : launches) {
+        for (const auto& c : L.plan.chains)
+            for (int k : c.layers)
+                if (ctas_out) ctas_out[L.first + k] = c.teams * c.per_team;
+        for (int k = 0; k < L.n; ++k) {
+            const int i = L.first + k;
+            if (teams_out) teams_out[i] = L.plan.slabs[k];
+            if (tpg_out) tpg_out[i] = plans[i].tpg;
+            if (cstride_out) cstride_out[i] = plans[i].cstride;
+        }
     }
-    return static_cast<int>(chunks.size());
+    return static_cast<int>(launches.size());
 }

@@ -45,26 +45,45 @@ class GradAllReduce:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._early.append((work, flat, grads))
 
+    def drain(self):
+        """Waits for and forgets reductions started by `early` whose step never reached `__call__` (gradient-only
+        passes: `train_batch(grad_hook_mode=True)`, the eager warm-up runs before a CUDA-graph capture)."""
+        early, self._early = self._early, []
+        for work, _, _ in early:
+            work.wait()
+
     def _finish(self, flat, grads):
         flat.div_(self.world)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
         return flat.numel() * flat.element_size()
 
-    def __call__(self, models):
+    def __call__(self, models, ok=None):
+        """Reduces what `early` has not taken yet and waits for the early part.  `ok` (optional 0-d bool tensor: this
+        rank's losses are finite): its negation rides along as one more element of the last gradient buffer, so
+        "every rank takes or skips the update together" costs no collective of its own; returns the combined flag."""
         if self.world == 1:
-            return
+            return ok
         early, self._early = self._early, []
         done = {id(g) for _, _, gs in early for g in gs}
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None and id(p.grad) not in done]
         nbytes = 0
-        if grads:
-            flat = self._flatten(grads)
+        all_ok = None
+        if grads or ok is not None:
+            parts = [g.reshape(-1) for g in grads]
+            if ok is not None:
+                parts.append((~ok).to(parts[0].dtype if parts else torch.float32).reshape(1))
+            flat = torch.cat(parts)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            nbytes += self._finish(flat, grads)
+            if ok is not None:
+                all_ok = flat[-1] == 0
+                flat = flat[:-1]
+            if grads:
+                nbytes += self._finish(flat, grads)
         for work, flat_e, grads_e in early:
             work.wait()                       # the current stream waits for the collective
             nbytes += self._finish(flat_e, grads_e)
         self.bytes_last = nbytes
+        return all_ok
 
     def all_ranks(self, ok):
         """Logical AND of a 0-d bool tensor over the ranks (a non-finite loss on one rank must stop them all)."""

@@ -204,6 +204,9 @@ class KPCNInterface(BaseInterface):
         CUDA-graph step (wcmc_b200.engine.GraphedTrainStep captures exactly this)."""
         out_manif = None
         self._p_full = None
+        drain = getattr(self.grad_sync, "drain", None)
+        if drain is not None:
+            drain()        # an exchange started by a step that never reached _logging (gradient-only pass)
         if self.use_llpm_buf:
             self.models["backbone_diffuse"].zero_grad()
             self.models["backbone_specular"].zero_grad()

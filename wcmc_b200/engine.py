@@ -19,6 +19,8 @@ import torch
 
 from support import losses as _losses
 
+from . import ddp as _ddp
+
 
 class GraphedTrainStep:
     def __init__(self, itf, example_batch, warmup=3):
@@ -43,6 +45,8 @@ class GraphedTrainStep:
                 if self.stage is not None:
                     self.stage.begin_step()
                 self._fwd_bwd()
+            if getattr(itf.grad_sync, "drain", None) is not None:
+                itf.grad_sync.drain()      # the warm-up passes stop before _logging: nothing may stay in flight
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._capture()
@@ -80,8 +84,12 @@ class GraphedTrainStep:
             self.flags = ok
             if self.fused is not None:
                 if self.sync_in_graph:
-                    itf.grad_sync(itf.models)
-                    ok = itf.grad_sync.all_ranks(ok)      # every rank takes or skips the update together
+                    # every rank takes or skips the update together: the flag rides in the gradient all-reduce
+                    if isinstance(itf.grad_sync, _ddp.GradAllReduce):
+                        ok = itf.grad_sync(itf.models, ok=ok)
+                    else:                                 # a user-supplied callable(models) [+ all_ranks]
+                        itf.grad_sync(itf.models)
+                        ok = itf.grad_sync.all_ranks(ok)
                     self.flags = ok
                 self.ok_i32 = ok.to(torch.int32).reshape(1)
                 self.fused.step(clip=1.0, ok_flag=self.ok_i32, count=False)
