@@ -411,7 +411,25 @@ def main():
         from wcmc_b200.engine import GraphedTrainStep
         graphed = GraphedTrainStep(itf, dev)
 
+    # The synthetic batch repeats, so a long run over-fits it and, at the reference's lr 1e-4, eventually diverges -- in
+    # fp32 as well (profiles/r02_long_run_800_steps.txt: backend and fp32 oracle side by side).  A run of many steps
+    # therefore puts the weights / Adam moments of the end of the warm-up back every RESET steps (three _foreach_copy_ launches inside
+    # the timed region: extra work, nothing skipped); runs of <= RESET steps never see it.
+    RESET = 200
+    state = {"n": 0, "live": None, "init": None}
+
+    def snapshot():
+        live = [p_ for m in models.values() for p_ in m.parameters()]
+        for o in optims.values():
+            for st in o.state.values():
+                live += [st["exp_avg"], st["exp_avg_sq"]]
+        state["live"], state["init"] = live, [t.detach().clone() for t in live]
+
     def step(batch):
+        state["n"] += 1
+        if state["n"] % RESET == 0 and state["init"] is not None:
+            with torch.no_grad():
+                torch._foreach_copy_(state["live"], state["init"])
         if use_graph:
             graphed(batch)
         else:
@@ -438,6 +456,7 @@ def main():
 
     for _ in range(args.warmup):
         step(dev)
+    snapshot()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
