@@ -104,6 +104,17 @@ int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x
                 int mask_coff, float slope, float* colsum, const float* colsum_scale, int flags,
                 void* stream);
 
+/* the LAST layer of a KPCN branch (5x5, 100 -> 441) fused with softmax + the 21x21 kernel-apply
+ * (sbmc.KPCN.forward: ConvChain -> KernelApply, called at /root/reference/support/interfaces.py:310): same
+ * implicit GEMM, but the epilogue keeps a running softmax over the 441 logits of its pixels across the four n tiles
+ * and gathers the radiance neighbourhood from a shared-memory tile, so the logits (1764 B per pixel, written once
+ * and read once by the unfused pair of launches) never reach HBM.  Inference only (no statistics for a backward).
+ *   out[n,c,y,x] = sum_k softmax_k(conv(x, w)[n,y,x,:] + bias) * data0[n,c,y+k/21-10,x+k%21-10]
+ * data, out: (N,3,Ho,Wo) fp32 NCHW (data zero outside).  cout_p must be 448, ksize 5, ka_ksize 21.            */
+int wcmc_conv2d_kernel_apply(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                             const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
+                             const float* data, float* out, int ka_ksize, int flags, void* stream);
+
 /* ---- K3: convolution weight gradient (tcgen05, MN-major operands, split-K) --------------------
  * Autograd of nn.Conv2d w.r.t. its weight (reference: `L_diffuse.backward()`,
  * /root/reference/support/interfaces.py:237-238).

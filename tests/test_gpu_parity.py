@@ -262,6 +262,32 @@ def test_step_glue_kernels_vs_torch(backend):
     assert all(torch.equal(a, b_) for a, b_ in zip((l_d, l_s, l_t, rmse), again))
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 44, 36), (1, 37, 61), (8, 96, 96)])
+@pytest.mark.parametrize("flags", [0, 1 << 21, (1 << 20) | (1 << 4), (1 << 20) | (2 << 4), (1 << 21) | (2 << 4)])
+def test_fused_last_conv_kernel_apply_vs_separate_launches(backend, oracle, n, h, w, flags):
+    """wcmc_conv2d_kernel_apply (last 5x5 layer -> running softmax over the four n tiles -> 21x21 gather,
+    logits never in HBM) against the two separate launches (fp32 logits + wcmc_kernel_apply_fwd) and against the
+    oracle's softmax + kernel_weighting on the same logits; single-CTA and CTA-pair launches, one and two M tiles per
+    region (the two warp halves then split columns / tiles differently), ragged maps."""
+    lib = backend.lib
+    from wcmc_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n * 100 + h)
+    dt = ops.ACT_DTYPE
+    x = lib.nchw_to_nhwc(torch.randn(n, 100, h, w, device="cuda", generator=g).relu(), dtype=dt)
+    wt = torch.randn(441, 100, 5, 5, device="cuda", generator=g) * 0.02
+    b = torch.randn(441, device="cuda", generator=g) * 0.5
+    wf, _, bp = lib.pack_weights(wt, b, want_bias=True, dtype=dt)
+    data = torch.rand(n, 3, h - 4, w - 4, device="cuda", generator=g) * 3
+    logits = lib.conv2d(x, wf, bp, 5, 0, act=0, out_dtype=torch.float32)
+    want, _ = lib.kernel_apply_fwd(logits, data, 21, want_stats=False)
+    got = lib.conv2d_kernel_apply(x, wf, bp, data, 5, 0, 21, flags=flags)
+    assert got.shape == want.shape and rel(got, want) < 2e-5, rel(got, want)
+    if h <= 61:
+        k = torch.softmax(logits[..., :441].permute(0, 3, 1, 2).double(), 1).view(n, 21, 21, h - 4, w - 4)
+        ref, _ = oracle.modules.kernel_weighting(data.double(), k)
+        assert rel(got, ref) < 2e-5
+
+
 @pytest.mark.parametrize("mt,nt", [(1, 0), (2, 0), (2, 64), (1, 48)])
 def test_conv_tilings_agree(backend, mt, nt):
     lib = backend.lib
@@ -703,6 +729,36 @@ def test_full_frame_denoise_vs_oracle_and_tiling(backend, oracle):
         t = net(tile)["radiance"]                        # (1,3,92,92) = frame rows y0+18 .. y0+110
     full = out["radiance"][..., y0 + 18:y0 + 110, x0 + 18:x0 + 110]
     assert rel(t[..., 10:-10, 10:-10], full[..., 10:-10, 10:-10]) < TOL_IMG
+
+
+def test_720p_denoise_fused_vs_oracle(backend, oracle):
+    """BASELINE configs[3] at its full size: 1280x720, whole frame in one pass, last conv -> softmax -> kernel-apply
+    fused (logits never in HBM) against the fp32 oracle KPCN on the replicate-padded frame (north_star: <= 1e-3), and
+    against the un-fused launches of the same backend."""
+    from wcmc_b200 import inference, ops
+    torch.manual_seed(0)
+    ref = oracle.KPCN(34)
+    net = backend.KPCN(34)
+    net.load_state_dict(ref.state_dict())
+    net.cuda().eval()
+    ref.cuda().eval()
+    batch = to_cuda({k: v for k, v in make_batch(batch=1, size=0, height=720, width=1280, seed=7, paths=False,
+                                                 llpm_channel=False).items() if k.startswith("kpcn")})
+    assert ops.FUSE_KERNEL_APPLY
+    out = inference.denoise_frame(net, batch)
+    ops.FUSE_KERNEL_APPLY = False
+    try:
+        unfused = inference.denoise_frame(net, batch)
+    finally:
+        ops.FUSE_KERNEL_APPLY = True
+    with torch.no_grad():
+        want = ref(inference.pad_frame(batch))
+    errs = {k: rel(out[k], want[k]) for k in ("radiance", "diffuse", "specular")}
+    record("test_720p_denoise_fused_vs_oracle", bound=TOL_IMG, fused_vs_unfused=rel(out["radiance"], unfused["radiance"]),
+           **errs)
+    assert tuple(out["radiance"].shape) == (1, 3, 720, 1280)
+    assert all(e < TOL_IMG for e in errs.values()), errs
+    assert rel(out["radiance"], unfused["radiance"]) < 1e-4
 
 
 def test_fused_clip_adam_matches_torch(backend):

@@ -57,6 +57,11 @@ struct ConvParams {
     int flags;
     float* colsum;             // optional: colsum[ch] += colsum_scale * sum over valid pixels of the output
     const float* colsum_scale;  // device scalar or null
+    // fused softmax + kernel-apply epilogue (KA instantiations): the logits never reach HBM
+    const float* ka_data;      // (N, 3, Ho, Wo) fp32: the radiance buffer the predicted kernels filter
+    float* ka_out;             // (N, 3, Ho, Wo) fp32
+    int ka_k, ka_taps;         // 21, 441
+    int ka_off;                // byte offset of the staging area (data halo + merge buffer) in shared memory
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -153,7 +158,19 @@ __device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int r
     return it;
 }
 
-template <bool PAIR, int TPS>
+// k-th work item of a CTA.  Plain launches stride the items over the grid.  KA launches keep ALL n tiles of a region
+// on one CTA, back to back: the fused epilogue carries a running softmax over the 441 logits of its pixels across
+// the four 112-column tiles (the flash-attention recurrence), so the tiles of a region must arrive in order.
+template <bool KA>
+__device__ __forceinline__ int item_at(const ConvParams& p, int item0, int item_step, int k) {
+    if (!KA) return item0 + k * item_step;
+    const int g = k / p.n_tiles;
+    return (item0 + g * item_step) * p.n_tiles + (k - g * p.n_tiles);
+}
+
+constexpr int kKaHaloRows = 16 + 20;     // region rows + the 21x21 footprint
+
+template <bool PAIR, int TPS, bool KA = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                   const ConvParams p) {
@@ -219,7 +236,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         if (lane == 0) {
             int ps = 0, ph = 0, loaded = 0;
             const bool dry = (p.flags & (1 << 17)) != 0;   // tuning knob: planes loaded once (wrong results)
-            for (int item = item0; item < n_items; item += item_step) {
+            for (int k = 0, item; (item = item_at<KA>(p, item0, item_step, k)) < n_items; ++k) {
                 const Item w = decode_item<PAIR>(p, item, rank);
                 for (int c = 0; c < p.nch; ++c) {
                     mbar_wait(&plane_empty[ps], ph ^ 1);
@@ -251,7 +268,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         if (lane == 0) {
             int bs = 0, ph = 0, loaded = 0;
             const bool dry = (p.flags & (1 << 16)) != 0;   // tuning knob: weight ring filled once (wrong results)
-            for (int item = item0; item < n_items; item += item_step) {
+            for (int k = 0, item; (item = item_at<KA>(p, item0, item_step, k)) < n_items; ++k) {
                 const int n0 = (item % p.n_tiles) * p.nt;
                 for (int c = 0; c < p.nch; ++c) {
                     for (int tap = 0; tap < taps; tap += TPS) {   // one stage = TPS taps, one box each
@@ -305,8 +322,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             br.base_lo = smem_u32(bst) >> 4; br.stride_lo = static_cast<uint32_t>(p.b_stride) >> 4;
             br.cur_lo = br.base_lo; br.tap_lo = static_cast<uint32_t>(p.tap_stride) >> 4;
             br.stages = p.b_stages; br.idx = 0; br.phase = 0;
-            int ps = 0, pph = 0, it = 0;
-            for (int item = item0; item < n_items; item += item_step, ++it) {
+            int ps = 0, pph = 0;
+            for (int it = 0; item_at<KA>(p, item0, item_step, it) < n_items; ++it) {
                 const int buf = it & 1;
                 if (PAIR) mbar_wait_cluster(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
                 else mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -358,9 +375,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         const int cc0 = (p.mt == 2) ? 0 : half;
         const int ccs = (p.mt == 2) ? 1 : 2;
         const int t = (p.mt == 2) ? half : 0;
-        int it = 0;
         const uint32_t acc_empty_leader = PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;
-        for (int item = item0; item < n_items; item += item_step, ++it) {
+        // ---- KA: running softmax + weighted gather state of this thread's pixel (carried over the n tiles of a region) ----
+        float4* ka_halo = reinterpret_cast<float4*>(smem + p.ka_off);          // [36][region_w + 20] (c0, c1, c2, -)
+        const int ka_pitch = region_w + 20;
+        float* ka_merge = reinterpret_cast<float*>(smem + p.ka_off) + 4 * kKaHaloRows * ka_pitch;   // [128][5]
+        float ka_m = -INFINITY, ka_l = 0.f, ka_a0 = 0.f, ka_a1 = 0.f, ka_a2 = 0.f;
+        const int epi_tid = threadIdx.x - 96;      // 0..255 among the epilogue warps
+        for (int it = 0, item; (item = item_at<KA>(p, item0, item_step, it)) < n_items; ++it) {
             const int buf = it & 1;
             const Item w = decode_item<PAIR>(p, item, rank);
             const int n0 = w.n0, rx = w.rx, ry = w.ry, n = w.n;
@@ -374,7 +396,64 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
 
+            if (KA && n0 == 0) {
+                // first n tile of a region: stage the (16+20) x (region_w+20) neighbourhood of the radiance buffer
+                // (zero outside the image, like the Halide op's constant_exterior) and reset the running softmax
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done with the previous region's halo
+                const int gy0 = ry * 16 - (p.ka_k >> 1), gx0 = rx * region_w - (p.ka_k >> 1);
+                const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
+                const float* dn = p.ka_data + static_cast<size_t>(n) * 3 * plane;
+                for (int i = epi_tid; i < kKaHaloRows * ka_pitch; i += 256) {
+                    const int hy = i / ka_pitch, hx = i - hy * ka_pitch;
+                    const int gy = gy0 + hy, gx = gx0 + hx;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gy >= 0 && gy < p.Ho && gx >= 0 && gx < p.Wo) {
+                        const float* d = dn + static_cast<size_t>(gy) * p.Wo + gx;
+                        v = make_float4(__ldg(d), __ldg(d + plane), __ldg(d + 2 * plane), 0.f);
+                    }
+                    ka_halo[i] = v;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                ka_m = -INFINITY; ka_l = 0.f; ka_a0 = ka_a1 = ka_a2 = 0.f;
+            }
+            // one 16-logit chunk of the fused epilogue: z = acc + bias (base-2 scaled), running max / sum / weighted sums
+            auto process_ka = [&](const uint32_t (&v)[16], int cc) {
+                const int ch = n0 + cc * 16;
+                float z[16];
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = __ldg(b4 + i);
+                    z[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + b.x) * 1.4426950408889634f;
+                    z[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + b.y) * 1.4426950408889634f;
+                    z[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + b.z) * 1.4426950408889634f;
+                    z[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) + b.w) * 1.4426950408889634f;
+                }
+                float mx = ka_m;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (ch + i < p.ka_taps) mx = fmaxf(mx, z[i]);
+                const float sc = exp2f(ka_m - mx);         // 0 on the first chunk (ka_m = -inf)
+                ka_l *= sc; ka_a0 *= sc; ka_a1 *= sc; ka_a2 *= sc;
+                ka_m = mx;
+                int dy = ch / p.ka_k, dx = ch - dy * p.ka_k;
+                const float4* hrow = ka_halo + (ty + dy) * ka_pitch + 8 * t + tx;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (ch + i < p.ka_taps) {
+                        const float e = exp2f(z[i] - mx);
+                        const float4 nb = hrow[dx];
+                        ka_l += e;
+                        ka_a0 = fmaf(e, nb.x, ka_a0);
+                        ka_a1 = fmaf(e, nb.y, ka_a1);
+                        ka_a2 = fmaf(e, nb.z, ka_a2);
+                    }
+                    if (++dx == p.ka_k) { dx = 0; hrow += ka_pitch; }
+                }
+            };
+
             auto process = [&](const uint32_t (&v)[16], int cc) {
+                if (KA) { process_ka(v, cc); return; }
                 if (p.flags & (1 << 18)) return;               // tuning knob: epilogue without math / stores
                 if (!valid && p.colsum == nullptr) return;
                 const int ch = n0 + cc * 16;
@@ -466,6 +545,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(acc_empty_leader + buf * 8);
             else mbar_arrive(&acc_empty[buf]);
+            if (KA && n0 + p.nt >= p.cout_p) {
+                // last n tile of the region: out_c = sum_k softmax_k * neighbour_c,k.  With one M tile the two warp
+                // halves split the columns of the same pixels: merge the two partial softmax states first.
+                if (p.mt == 1) {
+                    if (half == 1) {
+                        float* mg = ka_merge + m * 5;
+                        mg[0] = ka_m; mg[1] = ka_l; mg[2] = ka_a0; mg[3] = ka_a1; mg[4] = ka_a2;
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (half == 0) {
+                        const float* mg = ka_merge + m * 5;
+                        const float mo = mg[0], mx = fmaxf(ka_m, mo);
+                        const float s0 = exp2f(ka_m - mx), s1 = exp2f(mo - mx);
+                        ka_l = ka_l * s0 + mg[1] * s1;
+                        ka_a0 = ka_a0 * s0 + mg[2] * s1;
+                        ka_a1 = ka_a1 * s0 + mg[3] * s1;
+                        ka_a2 = ka_a2 * s0 + mg[4] * s1;
+                    }
+                }
+                if (valid && (p.mt == 2 || half == 0)) {
+                    const float inv = 1.f / ka_l;
+                    const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
+                    float* o = p.ka_out + static_cast<size_t>(n) * 3 * plane + static_cast<size_t>(oy) * p.Wo + ox;
+                    o[0] = ka_a0 * inv;
+                    o[plane] = ka_a1 * inv;
+                    o[2 * plane] = ka_a2 * inv;
+                }
+            }
         }
     }
 
@@ -512,10 +619,10 @@ int wcmc_conv_set_model(int which, int v) {
     return 0;
 }
 
-template <bool PAIR, int TPS>
+template <bool PAIR, int TPS, bool KA = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvParams& p, int grid, int smem_bytes,
                        cudaStream_t stream) {
-    WCMC_FUNC_SMEM((conv_igemm_kernel<PAIR, TPS>), kConvSmemMax + 1024);
+    WCMC_FUNC_SMEM((conv_igemm_kernel<PAIR, TPS, KA>), kConvSmemMax + 1024);
     if (PAIR) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -529,20 +636,21 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<PAIR, TPS>, tmx, tmw, p));
+        WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<PAIR, TPS, KA>, tmx, tmw, p));
         return WCMC_OK;
     }
-    conv_igemm_kernel<PAIR, TPS><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
+    conv_igemm_kernel<PAIR, TPS, KA><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
 
-extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
-                           const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
-                           void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
-                           int mask_cs, int mask_coff, float slope, float* colsum, const float* colsum_scale,
-                           int flags, void* stream_) {
+static int conv2d_impl(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                       const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
+                       void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
+                       int mask_cs, int mask_coff, float slope, float* colsum, const float* colsum_scale,
+                       int flags, const float* ka_data, float* ka_out, int ka_k, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool ka = ka_out != nullptr;
     WCMC_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5, WCMC_ESHAPE, "conv2d: ksize %d not in {1,3,5}", ksize);
     WCMC_REQUIRE((x_dtype == WCMC_BF16 || x_dtype == WCMC_F16) && (w_dtype == WCMC_BF16 || w_dtype == WCMC_F16) &&
                      (y_dtype == WCMC_BF16 || y_dtype == WCMC_F16 || y_dtype == WCMC_F32),
@@ -554,11 +662,11 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
                  "conv2d: cin_p (%d) and cout_p (%d) must be positive multiples of 16", cin_p, cout_p);
     WCMC_REQUIRE(x_cs % 8 == 0 && x_coff % 8 == 0 && x_coff + cin_p <= x_cs, WCMC_ESHAPE,
                  "conv2d: input channel stride/offset (%d,%d) must be multiples of 8", x_cs, x_coff);
-    WCMC_REQUIRE(y_cs % 8 == 0 && y_coff % 8 == 0 && y_coff + cout_p <= y_cs, WCMC_ESHAPE,
+    WCMC_REQUIRE(ka || (y_cs % 8 == 0 && y_coff % 8 == 0 && y_coff + cout_p <= y_cs), WCMC_ESHAPE,
                  "conv2d: output channel stride/offset (%d,%d) invalid", y_cs, y_coff);
     WCMC_REQUIRE(mask == nullptr || (mask_cs % 8 == 0 && mask_coff % 8 == 0), WCMC_ESHAPE,
                  "conv2d: mask channel stride/offset must be multiples of 8");
-    WCMC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+    WCMC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ka || (reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                      (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                  WCMC_EALIGN, "conv2d: pointers must be 16-byte aligned");
     const int Ho = H + 2 * pad - ksize + 1, Wo = W + 2 * pad - ksize + 1;
@@ -621,6 +729,9 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     p.mask = static_cast<const __nv_bfloat16*>(mask); p.mask_cs = mask_cs; p.mask_coff = mask_coff;
     p.slope = slope; p.flags = flags;
     p.colsum = colsum; p.colsum_scale = colsum_scale;
+    p.ka_data = ka_data; p.ka_out = ka_out; p.ka_k = ka_k; p.ka_taps = ka_k * ka_k; p.ka_off = 0;
+    // fused epilogue: data neighbourhood (16+20) x (8 mt + 20) float4 + the 128 x 5 merge buffer of the two warp halves
+    const int ka_bytes = ka ? ((kKaHaloRows * (8 * mt + 20) * 16 + 128 * 5 * 4 + 1023) / 1024) * 1024 : 0;
 
     CUtensorMap tmx, tmw;
     {
@@ -650,7 +761,7 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     if (ksize > 1 && p.plane_slots > 2 &&
         (kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride) / p.tap_stride < 4)
         p.plane_slots = 2;   // the deeper halo ring must leave room for a useful weight ring
-    const int b_room = kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride;
+    const int b_room = kConvSmemMax - kBarBytes - p.plane_slots * p.plane_stride - ka_bytes;
     int tps = 1;
     if (g_conv_row_stages && !(flags & (1 << 22)) && ksize > 1 && b_room / (ksize * p.tap_stride) >= 3) tps = ksize;
     p.b_stride = tps * p.tap_stride;
@@ -658,7 +769,20 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
     if (ksize == 1 && p.b_stages > 4) p.b_stages = 4;
     WCMC_REQUIRE(p.b_stages >= 2, WCMC_ESHAPE, "conv2d: shared memory carve-up failed");
-    const int smem_bytes = 1024 + kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
+    p.ka_off = kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
+    const int smem_bytes = 1024 + p.ka_off + ka_bytes;
+    if (ka) {
+        // all n tiles of a region stay on one CTA (pair): the grid is sized in regions, not items
+        if (pair) {
+            const int groups = p.pair_items / p.n_tiles;
+            const int grid = 2 * groups < (sms & ~1) ? 2 * groups : (sms & ~1);
+            if (tps == 5) return launch_conv<true, 5, true>(tmx, tmw, p, grid, smem_bytes, stream);
+            return launch_conv<true, 1, true>(tmx, tmw, p, grid, smem_bytes, stream);
+        }
+        const int groups = p.total_items / p.n_tiles;
+        if (tps == 5) return launch_conv<false, 5, true>(tmx, tmw, p, groups < sms ? groups : sms, smem_bytes, stream);
+        return launch_conv<false, 1, true>(tmx, tmw, p, groups < sms ? groups : sms, smem_bytes, stream);
+    }
     if (pair) {
         WCMC_REQUIRE(p.nt % 16 == 0, WCMC_ESHAPE, "conv2d: pair launch needs an n tile that is a multiple of 16");
         const int grid = 2 * p.pair_items < (sms & ~1) ? 2 * p.pair_items : (sms & ~1);
@@ -670,4 +794,29 @@ extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int 
     if (tps == 5) return launch_conv<false, 5>(tmx, tmw, p, grid, smem_bytes, stream);
     if (tps == 3) return launch_conv<false, 3>(tmx, tmw, p, grid, smem_bytes, stream);
     return launch_conv<false, 1>(tmx, tmw, p, grid, smem_bytes, stream);
+}
+
+extern "C" int wcmc_conv2d(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                           const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize, int pad,
+                           void* y, int y_dtype, int y_cs, int y_coff, int act, const void* mask,
+                           int mask_cs, int mask_coff, float slope, float* colsum, const float* colsum_scale,
+                           int flags, void* stream_) {
+    WCMC_REQUIRE(y != nullptr, WCMC_ESHAPE, "conv2d: null output");
+    return conv2d_impl(x, x_dtype, N, H, W, x_cs, x_coff, cin_p, w_packed, w_dtype, cout_p, bias, ksize, pad, y, y_dtype,
+                       y_cs, y_coff, act, mask, mask_cs, mask_coff, slope, colsum, colsum_scale, flags, nullptr, nullptr,
+                       0, stream_);
+}
+
+// the last layer of a KPCN branch fused with softmax + 21x21 kernel-apply -- the 441 logits of a
+// pixel live in TMEM / registers only (1.65 GB of fp32 logits per 720p branch neither written nor re-read).
+extern "C" int wcmc_conv2d_kernel_apply(const void* x, int x_dtype, int N, int H, int W, int x_cs, int x_coff, int cin_p,
+                                        const void* w_packed, int w_dtype, int cout_p, const float* bias, int ksize,
+                                        int pad, const float* data, float* out, int ka_ksize, int flags, void* stream_) {
+    WCMC_REQUIRE(data != nullptr && out != nullptr && bias != nullptr, WCMC_ESHAPE, "conv2d_kernel_apply: null pointer");
+    WCMC_REQUIRE(ksize == 5 && ka_ksize == 21 && cout_p == 448, WCMC_ESHAPE,
+                 "conv2d_kernel_apply: built for the KPCN head (5x5 conv -> 441 logits -> 21x21 kernels); got k %d, "
+                 "kernel %d, cout_p %d", ksize, ka_ksize, cout_p);
+    return conv2d_impl(x, x_dtype, N, H, W, x_cs, x_coff, cin_p, w_packed, w_dtype, cout_p, bias, ksize, pad, nullptr,
+                       WCMC_F32, 0, 0, WCMC_ACT_LINEAR, nullptr, 0, 0, 0.f, nullptr, nullptr, flags, data, out, ka_ksize,
+                       stream_);
 }

@@ -33,7 +33,7 @@ class KPCN(nn.Module):
                              (tuple(x.shape[-2:]), self.depth, chain.ksize, chain.ksize))
         tgt = torch.empty((0, 0, ho, wo), device="meta")
         layers, params = chain.spec()
-        return ops.KPCNBranchFn.apply(x, crop_like(buf, tgt), self.ksize, layers, *params)
+        return ops.apply(ops.KPCNBranchFn, x, crop_like(buf, tgt), self.ksize, layers, *params)
 
     def forward(self, data):
         from wcmc_b200 import streams

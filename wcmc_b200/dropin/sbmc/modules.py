@@ -140,7 +140,7 @@ class ConvChain(nn.Module):
 
     def forward(self, x):
         layers, params = self.spec()
-        return ops.ConvChainFn.apply(x, layers, *params)
+        return ops.apply(ops.ConvChainFn, x, layers, *params)
 
 
 class _UNetLevel(nn.Module):
@@ -193,7 +193,7 @@ class Autoencoder(nn.Module):
             raise ValueError("Autoencoder: spatial size %s must be divisible by %d (2x pooling / exact 2x "
                              "bilinear up-sampling per level)" % (tuple(x.shape[-2:]), div))
         spec, params = self.spec()
-        return ops.AutoencoderFn.apply(x, spec, *params)
+        return ops.apply(ops.AutoencoderFn, x, spec, *params)
 
 
 class KernelApply(nn.Module):

@@ -35,4 +35,4 @@ class PathNet(nn.Module):
             u_spec, u_params = self.propagation.spec()
             f_layers, f_params = self.final.spec()
         spec = wops.PathNetSpec(embedding=e_layers, unet=u_spec, final=f_layers)
-        return wops.PathNetFn.apply(paths, spec, *(e_params + u_params + f_params))
+        return wops.apply(wops.PathNetFn, paths, spec, *(e_params + u_params + f_params))

@@ -65,6 +65,8 @@ SIGNATURES = {
     "wcmc_pack_weights_batch": (c_int, [ctypes.POINTER(PackDesc), c_int, c_int, c_void_p]),
     "wcmc_conv2d": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
                     + [c_int] * 4 + [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "wcmc_conv2d_kernel_apply": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                         c_void_p, c_int, c_int, c_void_p]),
     "wcmc_conv2d_wgrad_workspace": (c_size_t, [c_int] * 7),
     "wcmc_conv2d_wgrad": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 6 + [c_void_p]
                           + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -375,6 +377,23 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype
          ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),
          0 if mask is None else mask.shape[3], mask_coff, float(slope), _p(colsum), _p(colsum_scale), flags,
          _stream())
+    return out
+
+
+def conv2d_kernel_apply(x, w_packed, bias, data, ksize, pad, ka_ksize=21, x_coff=0, flags=0, cin=None, cout=None):
+    """Last KPCN layer fused with softmax + kernel-apply (inference): x (N,H,W,Cs) 16-bit NHWC, w_packed
+    (448, k*k, cin_p), bias fp32 (448), data (N,3,Ho,Wo) fp32 -> out (N,3,Ho,Wo) fp32.  The logits stay on chip."""
+    lib = init(x.device)
+    n, h, w, xcs = _h16(x).shape
+    cout_p, taps, cin_p = _h16(w_packed).shape
+    assert taps == ksize * ksize and bias.dtype == torch.float32 and bias.numel() >= cout_p
+    ho, wo = h + 2 * pad - ksize + 1, w + 2 * pad - ksize + 1
+    assert data.dtype == torch.float32 and data.is_contiguous() and tuple(data.shape) == (n, 3, ho, wo)
+    out = torch.empty_like(data)
+    _run(lib.wcmc_conv2d_kernel_apply, "conv2d_k%d" % ksize,
+         2.0 * n * ho * wo * ksize * ksize * (cin or cin_p) * (cout or cout_p),
+         x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, bias.data_ptr(),
+         ksize, pad, data.data_ptr(), out.data_ptr(), ka_ksize, flags, _stream())
     return out
 
 

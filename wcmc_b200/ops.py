@@ -21,6 +21,7 @@ optimiser state / biases, fp32 logits + softmax + kernel-apply, fp32 PathNet out
 weight-gradient accumulation.  WCMC_ACT_DTYPE=bf16 switches every 16-bit tensor to bf16.
 """
 import os
+import threading
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -34,6 +35,25 @@ ACT_DTYPE = {"f16": torch.float16, "fp16": torch.float16, "bf16": torch.bfloat16
 GRAD_DTYPE = ACT_DTYPE
 GRAD_TARGET = 256.0  # max |scaled incoming gradient|
 DEBUG_TAP = None     # tests may set this to a list to capture the per-layer dz tensors
+
+
+_CALL = threading.local()
+
+
+def apply(fn, *args):
+    """fn.apply(*args) with the caller's grad mode visible to fn.forward: inside a Function's forward grad mode is
+    always off and `ctx.needs_input_grad` is True for parameters even under torch.no_grad(), so without this a
+    validation pass would save (and write to HBM) every activation a backward pass would need."""
+    prev = getattr(_CALL, "grad", True)
+    _CALL.grad = torch.is_grad_enabled()
+    try:
+        return fn.apply(*args)
+    finally:
+        _CALL.grad = prev
+
+
+def _needs_backward(ctx):
+    return getattr(_CALL, "grad", True) and any(ctx.needs_input_grad)
 
 
 def grad_scale(g):
@@ -179,7 +199,7 @@ class BatchedWeightNormFn(torch.autograd.Function):
 class ConvChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, layers, *params):
-        need = any(ctx.needs_input_grad)
+        need = _needs_backward(ctx)
         packed = pack_chain(layers, params, need_dgrad=need)
         xin = _to_nhwc(x, layers[0].cin_p)
         acts = chain_forward(xin, layers, packed)
@@ -218,12 +238,29 @@ def _act_bwd_full(dy: Slice, y: Slice, layer: LayerSpec):
 # ------------------------------------------------------------------------------------------------
 # KPCN branch: conv chain -> softmax -> kernel apply
 # ------------------------------------------------------------------------------------------------
+# inference: last layer -> softmax -> kernel-apply in ONE kernel (wcmc_conv2d_kernel_apply; 0 = separate launches)
+FUSE_KERNEL_APPLY = os.environ.get("WCMC_FUSE_KA", "1") != "0"
+
+
 class KPCNBranchFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, data, ksize, layers, *params):
-        need = any(ctx.needs_input_grad)
+        need = _needs_backward(ctx)
         packed = pack_chain(layers, params, need_dgrad=need)
         xin = _to_nhwc(x, layers[0].cin_p)
+        last = layers[-1]
+        if (FUSE_KERNEL_APPLY and not need and ksize == 21 and last.ksize == 5 and last.cout == 441 and last.act == 0
+                and data.shape[1] == 3 and len(layers) > 1):
+            # nothing is saved for a backward pass, so the 441 logits never have to exist in HBM
+            acts = chain_forward(xin, layers[:-1], packed[:-1])
+            cur = acts[-1]
+            data = data.contiguous().float()
+            ho, wo = cur.t.shape[1] + 2 * last.pad - 4, cur.t.shape[2] + 2 * last.pad - 4
+            assert tuple(data.shape[-2:]) == (ho, wo), "data and kernels must share spatial size"
+            wf, _, bp = packed[-1]
+            ctx.layers, ctx.ksize, ctx.need_dx = layers, ksize, False
+            return lib.conv2d_kernel_apply(cur.t, wf, bp, data, last.ksize, last.pad, ksize, x_coff=cur.coff,
+                                           cin=last.cin, cout=last.cout)
         acts = chain_forward(xin, layers, packed, last_fp32=True)
         logits = acts[-1].t  # (N,Ho,Wo,cout_p) fp32
         data = data.contiguous().float()
@@ -263,7 +300,7 @@ class KernelApplyFn(torch.autograd.Function):
         logits = torch.zeros((n, h, w, cs), dtype=torch.float32, device=kernels.device)
         logits[..., :k2] = kernels.permute(0, 2, 3, 1)
         data = data.contiguous().float()
-        need = any(ctx.needs_input_grad)
+        need = _needs_backward(ctx)
         out, stats = lib.kernel_apply_fwd(logits, data, ksize, want_stats=need)
         ctx.k2 = k2
         ctx.ksize = ksize
@@ -355,7 +392,7 @@ def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True, inv_scale=None):
 class AutoencoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, spec, *params):
-        need = any(ctx.needs_input_grad)
+        need = _needs_backward(ctx)
         xin = _to_nhwc(x, spec.left[0].cin_p)
         y, uctx = unet_forward(spec, xin, list(params), need)
         ctx.spec, ctx.need_dx, ctx.cin = spec, ctx.needs_input_grad[0], x.shape[1]
@@ -402,7 +439,7 @@ class PathNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, paths, spec, *params):
         b, s, nf, h, w = paths.shape
-        need = any(ctx.needs_input_grad)
+        need = _needs_backward(ctx)
         ne, nu = 2 * len(spec.embedding), spec.unet.n_params()
         # one launch packs the weights of all 20 layers (embedding, U-Net, final)
         p_all = pack_chain(list(spec.embedding) + unet_layers(spec.unet) + list(spec.final), params, need)
