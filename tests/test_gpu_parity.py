@@ -15,6 +15,10 @@ pytestmark = pytest.mark.gpu
 
 TOL_IMG = 1e-3
 TOL_GRAD = 1e-2
+# The raw manifold term on the SMALL golden cases: 2 patches x 2 spp x 40^2 crop to 4 x 4 pixels = 64 rows per loss
+# call, so the ~7e-4 fp16 storage error of the p-buffer does not average out over the mean (measured 1.1e-3 /
+# 2.0e-3, profiles/parity_r02.txt).  At the north-star size (541,696 rows) the same term sits at 2.4e-4 and is held to
+# TOL_IMG = 1e-3 like every other loss (test_full_size_wcmc_step_vs_oracle).
 TOL_MANIF = 5e-3
 
 
@@ -628,10 +632,10 @@ def test_full_size_wcmc_step_vs_oracle(backend, oracle):
     torch.manual_seed(77)
     loss, _, _ = oracle.ref.kpcn_train_step(ref_models, ref_optims, batch, use_llpm_buf=True, manif_learn=True,
                                             w_manif=0.1)
-    record("test_full_size_wcmc_step_vs_oracle", bound_loss=TOL_IMG, bound_manif=TOL_MANIF,
+    record("test_full_size_wcmc_step_vs_oracle", bound_loss=TOL_IMG, bound_manif=TOL_IMG,
            **{k: rel(itf.m_losses["m_" + k], v) for k, v in loss.items()})
     for k, v in loss.items():
-        assert rel(itf.m_losses["m_" + k], v) < (TOL_MANIF if "manif" in k else TOL_IMG), k
+        assert rel(itf.m_losses["m_" + k], v) < TOL_IMG, k        # north_star: every loss, manifold terms included
     for name in models:
         go_, gr_ = _grads(models[name]), _grads(ref_models[name])
         per = {k: rel(go_[k], gr_[k]) for k in go_}
