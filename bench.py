@@ -209,7 +209,7 @@ def bench_preprocess(pk):
     KPCN buffer and the 37-channel path descriptors, against the HBM roofline.  Algorithmic bytes: every raw float is
     read once (416 B per sample) by each of the two kernels' consumers -- kpcn reads the 13 raw channels it needs per
     sample (two 28-byte runs = 4 sectors of 32 B) and writes 176 B per pixel; llpm reads one 176-byte run and writes
-    148 B per sample."""
+    148 B per sample (six sectors in)."""
     import torch
     from wcmc_b200 import preprocess
     h, w, s = 720, 1280, 4
@@ -232,7 +232,7 @@ def bench_preprocess(pk):
     ms_k = timed(lambda: preprocess.preprocess_kpcn(raw))
     ms_l = timed(lambda: preprocess.preprocess_llpm(raw))
     by_k = h * w * (s * 128.0 + 176.0 + 2 * 72.0)      # 4 sectors per sample + the 44-channel pixel + 18 workspace floats twice
-    by_l = h * w * s * (176.0 + 148.0)
+    by_l = h * w * s * (192.0 + 148.0)                 # six 32-byte sectors cover the 176-byte run it reads
     return {"workload": "raw (720,1280,4,104) fp32 -> (720,1280,44) + (720,1280,4,37), L2 flushed between repetitions",
             "kpcn_ms": round(ms_k, 4), "kpcn_gbs": round(by_k / ms_k / 1e6, 1), "kpcn_frac_of_hbm": round(by_k / ms_k / 1e6 / pk["hbm_gbs"], 4),
             "llpm_ms": round(ms_l, 4), "llpm_gbs": round(by_l / ms_l / 1e6, 1), "llpm_frac_of_hbm": round(by_l / ms_l / 1e6 / pk["hbm_gbs"], 4)}

@@ -239,6 +239,13 @@ int wcmc_fmse_perm_fwd(const float* p, long p_sb, long p_ss, long p_sc, long p_s
 /* dp (B,S,C,H,W) contiguous fp32 = sum over modes of
  *   g*coef*( w[i] (P_i - P_idx(i)) + w[inv(i)] (P_i - P_inv(i)) ),  g = *scale (device float) or 1.
  * FeatureMSE: w = e, coef = 1/(B*n), scale = upstream gradient.  GRS: w = dL/de, coef = 1.     */
+/* the same, writing d p through element strides (batch, sample, channel, row; unit x stride): the gradient lands in
+ * the interior of a zero-filled tensor of the UNcropped p-buffer's shape, so no slice-backward copies are needed */
+int wcmc_fmse_perm_bwd_strided(const float* p, long p_sb, long p_ss, long p_sc, long p_sh, const int64_t* idx_patch,
+                               const int64_t* idx_batch, const int32_t* inv_patch, const int32_t* inv_batch,
+                               const float* w_patch, const float* w_batch, const float* scale, float coef_patch,
+                               float coef_batch, int B, int S, int C, int H, int W, float* dp, long d_sb, long d_ss,
+                               long d_sc, long d_sh, void* stream);
 int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_sc, long p_sh, const int64_t* idx_patch,
                        const int64_t* idx_batch, const int32_t* inv_patch, const int32_t* inv_batch,
                        const float* w_patch, const float* w_batch, const float* scale, float coef_patch,
@@ -339,8 +346,10 @@ typedef struct {
     float lr, beta1, beta2, eps;
 } wcmc_adam_tensor;
 int wcmc_adam_chunk(void);
+/* dev_nonfinite_count (optional, device uint64): gradient elements that were NaN / inf -- an fp16 overflow in the 16-bit
+ * backward pass -- are skipped (parameter and moments untouched) and counted here instead of poisoning the weights.   */
 int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const int* dev_blocks, int nblocks, int* dev_step,
-                        const int* dev_ok_flag, float clip, void* stream);
+                        const int* dev_ok_flag, float clip, unsigned long long* dev_nonfinite_count, void* stream);
 
 /* ---- K9: p-buffer statistics + concatenation (/root/reference/support/interfaces.py:165-180) ----------------
  * out (B, Cin+cr+1, HW) = cat[kpcn_in (B,Cin,HW), mean_S p[:, :, c0:c0+cr], var_S(p[:, :, c0:c0+cr]).mean(C) / S]
@@ -366,6 +375,13 @@ size_t wcmc_image_losses_workspace(void);
 int wcmc_image_losses(const float* r_d, const float* r_s, const float* radiance, const float* t_d, const float* t_s,
                       const float* t_t, const long* host_strides9, int B, int h, int w, float eps, float* sgn_d,
                       float* sgn_s, float* sums4, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out2 = { target / max|g|, max|g| / target } over n fp32 values in one launch: the per-pass loss scale that keeps the
+ * fp16 gradients of a backward pass in range (wcmc_b200/ops.py::grad_scale).  workspace: wcmc_absmax_scale_workspace()
+ * bytes, zero-filled once by the caller and then kept.                                                            */
+size_t wcmc_absmax_scale_workspace(void);
+int wcmc_absmax_scale(const float* g, long n, float target, float* out2, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 /* ---- device-side pairing permutations for the throughput mode of the loss (the reference draws
  * torch.randperm on the CPU, /root/reference/support/losses.py:35, :50; the parity mode keeps that) ----

@@ -115,3 +115,37 @@ def test_fmse_full_size_properties(losses):
     assert rel(l2, l1) < 1e-5
     rows = p.grad.permute(0, 1, 3, 4, 2).reshape(-1, c).double()
     assert float(rows.sum(0).abs().max()) < 1e-6 * float(rows.abs().sum(0).max())
+
+
+def test_fmse_crop_inside_the_function_matches_crop_like(losses):
+    """FeatureMSE.forward_cropped(p, ref): the centred crop taken inside the autograd Function (strided kernel reads,
+    gradient written into the interior of a zero-filled full-size tensor) == forward(crop_like(p, ref), ref)."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    p1 = torch.rand(2, 3, 4, 40, 44, device="cuda", generator=g).requires_grad_(True)
+    p2 = p1.detach().clone().requires_grad_(True)
+    ref = torch.rand(2, 3, 20, 28, device="cuda", generator=g) * 2
+    lf = losses.FeatureMSE(non_local=True)
+    n1, n2 = 3 * 20 * 28, 2 * 3 * 20 * 28
+    ip, ib = torch.randperm(n1, generator=torch.Generator().manual_seed(1)).cuda(), torch.randperm(n2, generator=torch.Generator().manual_seed(2)).cuda()
+    a = lf.forward_cropped(p1, ref, ip, ib)
+    from support.utils import crop_like
+    b = lf(crop_like(p2, ref), ref, ip, ib)
+    assert torch.equal(a, b)
+    (a * 3.0).backward()
+    (b * 3.0).backward()
+    assert torch.equal(p1.grad, p2.grad) and float(p1.grad[..., :10, :].abs().sum()) == 0.0
+    # same size: falls back to the plain call
+    q = torch.rand(2, 3, 4, 20, 28, device="cuda", generator=g).requires_grad_(True)
+    assert torch.equal(lf.forward_cropped(q, ref, ip, ib), lf(q, ref, ip, ib))
+
+
+def test_absmax_scale_kernel(losses):
+    from wcmc_b200 import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for n in (1, 5, 1000, 203136 * 3 + 1, 12582912):
+        x = torch.randn(n, device="cuda", generator=g) * 3e-4
+        out = lib.absmax_scale(x, 256.0)
+        amax = float(x.abs().max())
+        assert abs(float(out[0]) - 256.0 / amax) <= 1e-6 * 256.0 / amax and abs(float(out[1]) - amax / 256.0) <= 1e-6 * amax
+    s, inv = ops.grad_scale(torch.zeros(7, device="cuda"))
+    assert torch.isfinite(s).all() and float(s * inv) == pytest.approx(1.0, rel=1e-5)

@@ -48,3 +48,54 @@ def test_graphed_step_with_nccl_allreduce_world2(tmp_path):
         for k, v in rec.items():
             if k.startswith("loss_rel_"):
                 assert v < (5e-3 if "manif" in k else 1e-3), (k, v)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under `gpurun --gpus 2`)")
+def test_dataparallel_two_devices_and_non_current_device():
+    """The reference's own multi-GPU mode (single process, `nn.DataParallel`, replicas in threads,
+    /root/reference/train_kpcn.py:266-269) and its `--single_gpu --device_id 1` mode (models on a device that is not
+    torch's current one, :259-263): per-device kernel attributes, thread-local launch state and the device guard of the
+    ctypes layer.  Outputs and gradients must equal a plain single-device run."""
+    import torch.nn as nn
+    from wcmc_b200 import dropin, lib
+    from wcmc_b200.synth import make_batch
+    dropin.install()
+    lib.init(0)
+    from sbmc import KPCN
+    from support.networks import PathNet
+    torch.manual_seed(0)
+    base = KPCN(34).cuda(0)
+    data = {k: v.cuda(0) for k, v in make_batch(batch=4, size=48, seed=3, paths=False, llpm_channel=False).items()}
+    want = base(data)
+    (want["diffuse"].mean() + want["specular"].mean()).backward()
+    g_want = torch.cat([p.grad.flatten() for p in base.parameters()]).clone()
+    # (a) the same model living on cuda:1 while torch's current device stays cuda:0
+    assert torch.cuda.current_device() == 0
+    other = KPCN(34)
+    other.load_state_dict(base.state_dict())
+    other.cuda(1)
+    out1 = other({k: v.cuda(1) for k, v in data.items()})
+    (out1["diffuse"].mean() + out1["specular"].mean()).backward()
+    g1 = torch.cat([p.grad.flatten() for p in other.parameters()])
+    assert out1["radiance"].device.index == 1
+    torch.testing.assert_close(out1["radiance"].cpu(), want["radiance"].cpu(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(g1.cpu(), g_want.cpu(), rtol=1e-4, atol=1e-7)
+    # (b) nn.DataParallel over both devices: the batch is scattered 2 + 2, replicas run in two threads
+    for p in base.parameters():
+        p.grad = None
+    dp = nn.DataParallel(base, device_ids=[0, 1], output_device=0)
+    out = dp(data)
+    assert tuple(out["radiance"].shape) == tuple(want["radiance"].shape)
+    torch.testing.assert_close(out["radiance"], want["radiance"], rtol=1e-5, atol=1e-6)
+    # gradients: mean over the gathered batch == mean of the two half-batch means
+    (out["diffuse"].mean() + out["specular"].mean()).backward()
+    g_dp = torch.cat([p.grad.flatten() for p in base.parameters()])
+    torch.testing.assert_close(g_dp, g_want, rtol=2e-3, atol=1e-6)
+    # the path-embedding network (two streams, weight-norm override per thread) under DataParallel as well
+    torch.manual_seed(1)
+    pn = PathNet(ic=36, outc=3).cuda(0)
+    pb = {k: v.cuda(0) for k, v in make_batch(batch=4, spp=2, size=32, seed=5).items()}
+    with torch.no_grad():
+        p_want = pn(pb)
+        p_dp = nn.DataParallel(pn, device_ids=[0, 1], output_device=0)(pb)
+    torch.testing.assert_close(p_dp, p_want, rtol=1e-5, atol=1e-6)

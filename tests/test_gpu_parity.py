@@ -808,6 +808,19 @@ def test_fused_clip_adam_matches_torch(backend):
     for q, b in zip(pb, before):
         assert torch.equal(q.detach(), b)
     assert int(fused.t_dev) == 5
+    # a NaN / inf gradient element (fp16 overflow in a 16-bit backward pass) is skipped and counted, never applied
+    for q in pb:
+        q.grad = torch.full_like(q, 0.5)
+    pb[0].grad.view(-1)[3] = float("nan")
+    pb[2].grad.view(-1)[10] = float("inf")
+    before = [q.detach().clone() for q in pb]
+    fused.step(clip=1.0)
+    assert fused.nonfinite_count() == 2
+    assert float(pb[0].detach().view(-1)[3]) == float(before[0].view(-1)[3])
+    assert float(pb[2].detach().view(-1)[10]) == float(before[2].view(-1)[10])
+    assert all(torch.isfinite(q).all() for q in pb) and not torch.equal(pb[1].detach(), before[1])
+    st = ob[0].state[pb[0]]
+    assert torch.isfinite(st["exp_avg"]).all() and torch.isfinite(st["exp_avg_sq"]).all()
 
 
 def test_fused_adam_checkpoint_is_interchangeable_with_torch(backend, tmp_path):

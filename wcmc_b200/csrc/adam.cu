@@ -21,7 +21,8 @@ constexpr int kAdamChunk = 256 * 16;  // elements per CTA
 
 __global__ void __launch_bounds__(kAdamThreads)
 adam_clip_kernel(const wcmc_adam_tensor* __restrict__ tensors, const int2* __restrict__ blocks,
-                 const int* __restrict__ step, const int* __restrict__ ok_flag, float clip) {
+                 const int* __restrict__ step, const int* __restrict__ ok_flag, float clip,
+                 unsigned long long* __restrict__ nonfinite) {
     if (ok_flag != nullptr && *ok_flag == 0) return;
     const int2 bk = blocks[blockIdx.x];
     const wcmc_adam_tensor T = tensors[bk.x];
@@ -40,7 +41,12 @@ adam_clip_kernel(const wcmc_adam_tensor* __restrict__ tensors, const int2* __res
     const long end = min(T.n, base + kAdamChunk);
     const bool vec = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) |
                        reinterpret_cast<uintptr_t>(T.m) | reinterpret_cast<uintptr_t>(T.v)) & 15) == 0;
+    // A non-finite gradient element (an fp16 overflow somewhere in a 16-bit backward pass, which fp32 training would not
+    // have) must not reach the weights: torch's Adam would write NaN into p, m and v for good.  Such an element is
+    // left alone -- no update, moments untouched -- and counted; the host reports the count (KPCNInterface).
+    unsigned bad = 0;
     auto upd = [&](float& p, float& g, float& m, float& v) {
+        if (!isfinite(g)) { ++bad; return; }
         if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);
         m = fmaf(g - m, w1, m);
         v = fmaf(w2 * g, g, v * b2);
@@ -77,6 +83,7 @@ adam_clip_kernel(const wcmc_adam_tensor* __restrict__ tensors, const int2* __res
             if (clip > 0.f) T.g[j] = g;
         }
     }
+    if (bad != 0 && nonfinite != nullptr) atomicAdd(nonfinite, static_cast<unsigned long long>(bad));
 }
 
 __global__ void adam_tick_kernel(int* step, const int* ok_flag) {
@@ -88,13 +95,14 @@ __global__ void adam_tick_kernel(int* step, const int* ok_flag) {
 extern "C" int wcmc_adam_chunk(void) { return kAdamChunk; }
 
 extern "C" int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const int* dev_blocks, int nblocks,
-                                   int* dev_step, const int* dev_ok_flag, float clip, void* stream_) {
+                                   int* dev_step, const int* dev_ok_flag, float clip,
+                                   unsigned long long* dev_nonfinite_count, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WCMC_REQUIRE(dev_tensors != nullptr && dev_blocks != nullptr && dev_step != nullptr && nblocks >= 0,
                  WCMC_ESHAPE, "adam_clip_step: null pointer");
     if (nblocks > 0) {
         adam_clip_kernel<<<nblocks, kAdamThreads, 0, stream>>>(dev_tensors, reinterpret_cast<const int2*>(dev_blocks),
-                                                               dev_step, dev_ok_flag, clip);
+                                                               dev_step, dev_ok_flag, clip, dev_nonfinite_count);
         WCMC_LAUNCH_CHECK();
     }
     adam_tick_kernel<<<1, 1, 0, stream>>>(dev_step, dev_ok_flag);

@@ -149,7 +149,7 @@ fmse_perm_bwd_kernel(PView pv, const int64_t* __restrict__ idx_patch, const int6
                      const int32_t* __restrict__ inv_patch, const int32_t* __restrict__ inv_batch,
                      const float* __restrict__ w_patch, const float* __restrict__ w_batch,
                      const float* __restrict__ scale, float coef_patch, float coef_batch, int B, int S, int C,
-                     int H, int W, float* __restrict__ dp) {
+                     int H, int W, float* __restrict__ dp, long d_sb, long d_ss, long d_sc, long d_sh) {
     const int hw = H * W;
     const int n = S * hw;
     const int b = blockIdx.y;
@@ -182,12 +182,12 @@ fmse_perm_bwd_kernel(PView pv, const int64_t* __restrict__ idx_patch, const int6
         w_bi = w_batch[gi] * coef_batch * g;
         w_ki = w_batch[ki] * coef_batch * g;
     }
-    float* out = dp + ((static_cast<long>(b) * S + s) * C) * hw + r;
+    float* out = dp + b * d_sb + s * d_ss + y * d_sh + x;
     for (int c = 0; c < C; ++c) {
         const float v = pi[c * pv.sc];
         float d = w_i * (v - pj[c * pv.sc]) + w_ji * (v - pji[c * pv.sc]);
         if (pk != nullptr) d += w_bi * (v - pk[c * pv.sc]) + w_ki * (v - pki[c * pv.sc]);
-        out[static_cast<long>(c) * hw] = d;
+        out[c * d_sc] = d;
     }
 }
 
@@ -228,11 +228,12 @@ extern "C" int wcmc_fmse_perm_fwd(const float* p, long p_sb, long p_ss, long p_s
     return WCMC_OK;
 }
 
-extern "C" int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_sc, long p_sh,
-                                  const int64_t* idx_patch, const int64_t* idx_batch, const int32_t* inv_patch,
-                                  const int32_t* inv_batch, const float* w_patch, const float* w_batch,
-                                  const float* scale, float coef_patch, float coef_batch, int B, int S, int C,
-                                  int H, int W, float* dp, void* stream) {
+extern "C" int wcmc_fmse_perm_bwd_strided(const float* p, long p_sb, long p_ss, long p_sc, long p_sh,
+                                          const int64_t* idx_patch, const int64_t* idx_batch, const int32_t* inv_patch,
+                                          const int32_t* inv_batch, const float* w_patch, const float* w_batch,
+                                          const float* scale, float coef_patch, float coef_batch, int B, int S, int C,
+                                          int H, int W, float* dp, long d_sb, long d_ss, long d_sc, long d_sh,
+                                          void* stream) {
     WCMC_REQUIRE(B > 0 && S > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, WCMC_ESHAPE,
                  "fmse_perm_bwd: bad shape B=%d S=%d C=%d H=%d W=%d", B, S, C, H, W);
     WCMC_REQUIRE(p && idx_patch && inv_patch && w_patch && dp, WCMC_ESHAPE, "fmse_perm_bwd: null pointer");
@@ -243,7 +244,18 @@ extern "C" int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_s
     PView pv{p, p_sb, p_ss, p_sc, p_sh};
     fmse_perm_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         pv, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch, B, S, C, H,
-        W, dp);
+        W, dp, d_sb, d_ss, d_sc, d_sh);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
+}
+
+extern "C" int wcmc_fmse_perm_bwd(const float* p, long p_sb, long p_ss, long p_sc, long p_sh,
+                                  const int64_t* idx_patch, const int64_t* idx_batch, const int32_t* inv_patch,
+                                  const int32_t* inv_batch, const float* w_patch, const float* w_batch,
+                                  const float* scale, float coef_patch, float coef_batch, int B, int S, int C,
+                                  int H, int W, float* dp, void* stream) {
+    const long hw = static_cast<long>(H) * W;
+    return wcmc_fmse_perm_bwd_strided(p, p_sb, p_ss, p_sc, p_sh, idx_patch, idx_batch, inv_patch, inv_batch, w_patch,
+                                      w_batch, scale, coef_patch, coef_batch, B, S, C, H, W, dp, S * C * hw, C * hw, hw, W,
+                                      stream);
 }

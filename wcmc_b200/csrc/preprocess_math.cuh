@@ -56,22 +56,27 @@ WCMC_HD void mean_var(const float (&x)[kMaxSpp][C], int S, float (&mean)[C], flo
     }
 }
 
-// The 18 per-pixel values of one pixel (r = its S x 104 raw floats) -> o; returns the mean depth (for the image maximum).
+// The 13 raw channels the KPCN statistics read, per sample: total radiance 2..4, diffuse 5..7, albedo 66..68,
+// normal 69..71, depth 72 (datasets.py:223-266).  kRawIdx[j] = raw channel of value j.
+constexpr int kNeed = 13;
+WCMC_HD int raw_index(int j) { return j < 6 ? 2 + j : 60 + j; }    // 0..5 -> 2..7, 6..12 -> 66..72
+
+// The 18 per-pixel values of one pixel from the (sanitised) 13 needed values of each of its S samples -> o; returns the
+// mean depth (for the image maximum).  v[s] = {total r,g,b, diffuse r,g,b, albedo r,g,b, normal x,y,z, depth}.
 //   o: 0..2 diffuse | 3 diffuse_v | 4..6 specular | 7 specular_v | 8..10 normal | 11 normal_v | 12 depth (mean, not yet
 //      normalised) | 13 depth_v (not yet normalised) | 14..16 albedo | 17 albedo_v
-WCMC_HD float kpcn_pixel_stats(const float* r, int S, float* o) {
+WCMC_HD float kpcn_stats_from_values(const float (*v)[kNeed], int S, float* o) {
     const float eps = 0.00316f;
     float spc[kMaxSpp][3], dif[kMaxSpp][3], alb[kMaxSpp][3], nrm[kMaxSpp][3], dep[kMaxSpp][1];
     for (int s = 0; s < S; ++s) {
-        const float* q = r + s * kRawC;
         for (int c = 0; c < 3; ++c) {
-            const float d = fmaxf(sane(WCMC_PREP_LD(q + 5 + c)), 0.f);                       // np.maximum(diffuse, 0)
+            const float d = fmaxf(v[s][3 + c], 0.f);                                         // np.maximum(diffuse, 0)
             dif[s][c] = d;
-            spc[s][c] = fmaxf(fmaxf(sane(WCMC_PREP_LD(q + 2 + c)), 0.f) - d, 0.f);          // specular sample (:541-543)
-            alb[s][c] = sane(WCMC_PREP_LD(q + 66 + c));
-            nrm[s][c] = sane(WCMC_PREP_LD(q + 69 + c));
+            spc[s][c] = fmaxf(fmaxf(v[s][c], 0.f) - d, 0.f);                                 // specular sample (:541-543)
+            alb[s][c] = v[s][6 + c];
+            nrm[s][c] = v[s][9 + c];
         }
-        dep[s][0] = sane(WCMC_PREP_LD(q + 72));
+        dep[s][0] = v[s][12];
     }
     float m3[3], v3[3], m1[1], v1[1];
     mean_var<3>(alb, S, m3, v3);   // albedo first: the diffuse factorisation needs it
@@ -94,6 +99,14 @@ WCMC_HD float kpcn_pixel_stats(const float* r, int S, float* o) {
     o[12] = m1[0];
     o[13] = v1[0];
     return m1[0];
+}
+
+// The same from the pixel's S x 104 raw floats (r).
+WCMC_HD float kpcn_pixel_stats(const float* r, int S, float* o) {
+    float v[kMaxSpp][kNeed];
+    for (int s = 0; s < S; ++s)
+        for (int j = 0; j < kNeed; ++j) v[s][j] = sane(WCMC_PREP_LD(r + s * kRawC + raw_index(j)));
+    return kpcn_stats_from_values(v, S, o);
 }
 
 // Output channel c (0..43) of pixel p from the per-pixel workspace: depth normalisation by the image maximum `md`

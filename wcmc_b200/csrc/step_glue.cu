@@ -149,7 +149,65 @@ image_losses_kernel(const float* __restrict__ rd, const float* __restrict__ rs, 
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// out[0] = target / max|g|, out[1] = max|g| / target   (the per-pass loss scale of the 16-bit backward, ops.grad_scale;
+// round 1: abs + amax + clamp + reciprocal + two multiplies = six ATen launches and a temporary the size of g)
+__global__ void __launch_bounds__(kGlueThreads)
+absmax_scale_kernel(const float* __restrict__ g, long n, float target, float* __restrict__ partial,
+                    unsigned* __restrict__ ticket, float* __restrict__ out) {
+    float m = 0.f;
+    const long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long i = blockIdx.x * static_cast<long>(kGlueThreads) + threadIdx.x; i < n4;
+         i += static_cast<long>(gridDim.x) * kGlueThreads) {
+        const float4 v = __ldg(g4 + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) m = fmaxf(m, fabsf(__ldg(g + (n4 << 2) + threadIdx.x)));
+    __shared__ float red[kGlueThreads / 32];
+    __shared__ bool last;
+    m = wcmc::warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 1; j < kGlueThreads / 32; ++j) m = fmaxf(m, red[j]);
+        partial[blockIdx.x] = m;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        float v = 0.f;
+        for (unsigned j = threadIdx.x; j < gridDim.x; j += 32) v = fmaxf(v, __ldcg(partial + j));
+        v = wcmc::warp_max(v);
+        if (threadIdx.x == 0) {
+            v = fmaxf(v, 1e-30f);
+            out[0] = target / v;
+            out[1] = v / target;
+            *ticket = 0u;
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" size_t wcmc_absmax_scale_workspace(void) { return (2 * 148 + 4) * sizeof(float); }
+
+extern "C" int wcmc_absmax_scale(const float* g, long n, float target, float* out2, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WCMC_REQUIRE(g && out2 && n > 0 && target > 0.f, WCMC_ESHAPE, "absmax_scale: bad arguments");
+    WCMC_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, WCMC_EALIGN, "absmax_scale: g must be 16-byte aligned");
+    WCMC_REQUIRE(workspace && workspace_bytes >= wcmc_absmax_scale_workspace(), WCMC_EWORKSPACE,
+                 "absmax_scale: workspace too small");
+    float* partial = static_cast<float*>(workspace);
+    unsigned* ticket = reinterpret_cast<unsigned*>(partial + 2 * 148);       // caller zero-fills the workspace ONCE
+    const int grid = static_cast<int>(std::min<long>((n / 4 + kGlueThreads - 1) / kGlueThreads + 1, 2L * 148));
+    absmax_scale_kernel<<<grid, kGlueThreads, 0, stream>>>(g, n, target, partial, ticket, out2);
+    WCMC_LAUNCH_CHECK();
+    return WCMC_OK;
+}
 
 extern "C" int wcmc_pbuffer_concat_fwd(const float* kpcn_in, const float* p, float* out, int B, int S, int C, int c0,
                                        int cr, int Cin, int HW, void* stream_) {

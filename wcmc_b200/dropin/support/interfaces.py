@@ -257,7 +257,11 @@ class KPCNInterface(BaseInterface):
                 tgt = crop_like(batch["target_" + name], pred)
                 loss = fused["l_" + name] if fused is not None else self.loss_funcs["l_" + name](pred, tgt)
                 if self.manif_learn:
-                    l_manif = self.loss_funcs["l_manif"](crop_like(p_buffers[name], pred), tgt)
+                    lm = self.loss_funcs["l_manif"]
+                    if hasattr(lm, "forward_cropped"):     # the crop of crop_like() taken inside the loss Function
+                        l_manif = lm.forward_cropped(p_buffers[name], tgt)
+                    else:
+                        l_manif = lm(crop_like(p_buffers[name], pred), tgt)
                     losses["l_manif_" + name] = l_manif.detach()
                     # the reference adds in place AFTER taking `.detach()` of the branch loss, so the
                     # logged l_diffuse / l_specular include the weighted manifold term (:221-232)
@@ -367,6 +371,10 @@ class KPCNInterface(BaseInterface):
 
     def get_epoch_summary(self, mode, norm):
         if mode == "train":
+            fa = self._fused_adam
+            if fa and fa.nonfinite_count():
+                print("[wcmc_b200] %d non-finite gradient elements were skipped by the fused optimiser so far "
+                      "(16-bit backward overflow)" % fa.nonfinite_count())
             print("[][][]", end=" ")
             for key in self.m_losses:
                 if key == "m_val":

@@ -126,8 +126,13 @@ class _FmseFn(torch.autograd.Function):
     forward launch (wcmc_fmse_perm_fwd) and one gather-only backward launch (wcmc_fmse_perm_bwd)."""
 
     @staticmethod
-    def forward(ctx, p, ref, idx_patch, idx_batch):
-        r = lib.fmse_perm_fwd(p, ref, idx_patch, idx_batch)
+    def forward(ctx, p, ref, idx_patch, idx_batch, crop=None):
+        # crop = (y0, x0, h, w): `p` is the UNcropped p-buffer and the centred crop of crop_like() is taken here, as a
+        # strided view the kernels read directly; the backward then writes straight into the interior of a zero-filled
+        # tensor of p's shape (autograd's own slice-backward would allocate, fill and copy once per cropped dimension)
+        ctx.crop = crop
+        pv = p if crop is None else p[..., crop[0]:crop[0] + crop[2], crop[1]:crop[1] + crop[3]]
+        r = lib.fmse_perm_fwd(pv, ref, idx_patch, idx_batch)
         _check_flag(r["nonfinite"])
         ctx.save_for_backward(p, idx_patch, idx_batch, r["inv_patch"], r["inv_batch"], r["e_patch"], r["e_batch"])
         loss = r["loss"]
@@ -138,9 +143,15 @@ class _FmseFn(torch.autograd.Function):
         p, idx_patch, idx_batch, inv_patch, inv_batch, e_patch, e_batch = ctx.saved_tensors
         rows = e_patch.numel()
         coef_p = (1.0 if idx_batch is not None else 2.0) / rows
-        dp = lib.fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, e_patch, e_batch,
-                               g.reshape(1).float().contiguous(), coef_p, 1.0 / rows)
-        return dp, None, None, None
+        crop = ctx.crop
+        pv, out, full = p, None, None
+        if crop is not None:
+            pv = p[..., crop[0]:crop[0] + crop[2], crop[1]:crop[1] + crop[3]]
+            full = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+            out = full[..., crop[0]:crop[0] + crop[2], crop[1]:crop[1] + crop[3]]
+        dp = lib.fmse_perm_bwd(pv, idx_patch, idx_batch, inv_patch, inv_batch, e_patch, e_batch,
+                               g.reshape(1).float().contiguous(), coef_p, 1.0 / rows, out=out)
+        return (dp if full is None else full), None, None, None, None
 
 
 class _PairDisplacementFn(torch.autograd.Function):
@@ -181,7 +192,24 @@ class FeatureMSE(torch.nn.Module):
     def forward(self, p_buffer, ref, idx_patch=None, idx_batch=None):
         p, r = _views(p_buffer, ref)
         idx_patch, idx_batch = _perms(p, self.rng, self.non_local, idx_patch, idx_batch, self.stage)
-        return _FmseFn.apply(p, r, idx_patch, idx_batch)
+        return _FmseFn.apply(p, r, idx_patch, idx_batch, None)
+
+    def forward_cropped(self, p_buffer, ref, idx_patch=None, idx_batch=None):
+        """forward(crop_like(p_buffer, ref), ref) with the centred crop (support/utils.py:24-42) taken inside the
+        autograd Function: same value and gradient, no slice-backward copies of the (B,S,C,H,W) gradient."""
+        h, w = ref.shape[-2:]
+        dh, dw = p_buffer.shape[-2] - h, p_buffer.shape[-1] - w
+        if dh < 0 or dw < 0 or (dh == 0 and dw == 0) or not p_buffer.is_cuda or p_buffer.dtype != torch.float32 \
+                or p_buffer.stride(4) != 1:
+            from support.utils import crop_like
+            return self.forward(crop_like(p_buffer, ref), ref, idx_patch, idx_batch)
+        crop = (max(dh // 2, 0), max(dw // 2, 0), h, w)
+        r = ref.to(p_buffer.device, torch.float32)
+        if r.stride(3) != 1:
+            r = r.contiguous()
+        pv = p_buffer[..., crop[0]:crop[0] + h, crop[1]:crop[1] + w]
+        idx_patch, idx_batch = _perms(pv, self.rng, self.non_local, idx_patch, idx_batch, self.stage)
+        return _FmseFn.apply(p_buffer, r, idx_patch, idx_batch, crop)
 
 
 class GlobalRelativeSimilarityLoss(torch.nn.Module):

@@ -105,6 +105,10 @@ SIGNATURES = {
     "wcmc_preprocess_kpcn_workspace": (c_size_t, [c_int, c_int]),
     "wcmc_preprocess_kpcn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "wcmc_preprocess_llpm": (c_int, [c_void_p, ctypes.c_long, c_void_p, c_void_p]),
+    "wcmc_fmse_perm_bwd_strided": (c_int, [c_void_p] + [c_long] * 4 + [c_void_p] * 7 + [c_float, c_float] + [c_int] * 5
+                                   + [c_void_p] + [c_long] * 4 + [c_void_p]),
+    "wcmc_absmax_scale_workspace": (c_size_t, []),
+    "wcmc_absmax_scale": (c_int, [c_void_p, c_long, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "wcmc_pbuffer_concat_fwd": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "wcmc_pbuffer_concat_bwd": (c_int, [c_void_p] * 2 + [c_int] * 7 + [c_void_p]),
     "wcmc_recombine": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -113,7 +117,7 @@ SIGNATURES = {
                           + [c_size_t, c_void_p]),
     "wcmc_random_permutation": (c_int, [c_void_p, c_long, c_void_p, ctypes.c_uint, c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
-    "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
     "wcmc_fmse_allpairs_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
@@ -660,18 +664,21 @@ def fmse_perm_fwd(p, ref, idx_patch, idx_batch=None):
     return r
 
 
-def fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch):
-    """-> dp (B,S,C,H,W) contiguous fp32 (see include/wcmc.h)."""
+def fmse_perm_bwd(p, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch,
+                  out=None):
+    """-> dp (B,S,C,H,W) contiguous fp32 (see include/wcmc.h); or written into `out`, a (B,S,C,H,W) fp32 view with
+    unit x stride (the interior of a zero-filled tensor of the uncropped p-buffer's shape)."""
     lib = init(p.device)
     b, s, c, h, w = p.shape
-    dp = torch.empty((b, s, c, h, w), dtype=torch.float32, device=p.device)
+    dp = torch.empty((b, s, c, h, w), dtype=torch.float32, device=p.device) if out is None else out
+    assert dp.dtype == torch.float32 and tuple(dp.shape) == (b, s, c, h, w) and dp.stride(4) == 1
     for t in (w_patch, w_batch):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == b * s * h * w)
     modes = 2 if idx_batch is not None else 1
     work = b * s * h * w * (c * 4.0 * (2 + 2 * modes) + modes * 20.0)
-    _run(lib.wcmc_fmse_perm_bwd, "fmse_perm_bwd", work, *_pview(p), idx_patch.data_ptr(), _p(idx_batch),
+    _run(lib.wcmc_fmse_perm_bwd_strided, "fmse_perm_bwd", work, *_pview(p), idx_patch.data_ptr(), _p(idx_batch),
          inv_patch.data_ptr(), _p(inv_batch), w_patch.data_ptr(), _p(w_batch), _p(scale), float(coef_patch),
-         float(coef_batch), b, s, c, h, w, dp.data_ptr(), _stream())
+         float(coef_batch), b, s, c, h, w, dp.data_ptr(), *dp.stride()[:4], _stream())
     return dp
 
 
@@ -724,6 +731,24 @@ def recombine(albedo, r_d, r_s):
 
 
 _loss_ws = {}
+_scale_ws = {}
+
+
+def absmax_scale(g, target):
+    """-> fp32 (2,) device tensor [target / max|g|, max|g| / target] in one launch (no host sync)."""
+    lib = init(g.device)
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    if g.data_ptr() % 16:
+        g = g.clone()
+    key = (g.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _scale_ws.get(key)
+    if ws is None:
+        ws = _scale_ws[key] = torch.zeros(lib.wcmc_absmax_scale_workspace(), dtype=torch.uint8, device=g.device)
+    out = torch.empty(2, dtype=torch.float32, device=g.device)
+    _run(lib.wcmc_absmax_scale, "absmax_scale", g.numel() * 4.0, g.data_ptr(), g.numel(), float(target), out.data_ptr(),
+         ws.data_ptr(), ws.numel(), _stream())
+    return out
+
 
 
 def image_losses(r_d, t_d, r_s, t_s, rad, t_t, eps, want_signs):
@@ -935,11 +960,12 @@ def pathnet_embed_bwd(d_emb, d_red, inv_scale, emb, h2, h1, x16, packed, acts, s
 
 
 # ---- K12: fused clip + Adam ------------------------------------------------------------------------
-def adam_clip_step(dev_tensors, dev_blocks, nblocks, dev_step, ok_flag, clip, nbytes=0.0):
-    """dev_tensors: uint8 device tensor holding AdamTensor structs; dev_blocks: int32 (nblocks, 2)."""
+def adam_clip_step(dev_tensors, dev_blocks, nblocks, dev_step, ok_flag, clip, nbytes=0.0, nonfinite=None):
+    """dev_tensors: uint8 device tensor holding AdamTensor structs; dev_blocks: int32 (nblocks, 2); nonfinite: optional
+    int64 (1,) device counter of skipped NaN / inf gradient elements."""
     lib = init(dev_step.device)
     _run(lib.wcmc_adam_clip_step, "adam_clip_step", nbytes, dev_tensors.data_ptr(), dev_blocks.data_ptr(), nblocks,
-         dev_step.data_ptr(), _p(ok_flag), float(clip), _stream())
+         dev_step.data_ptr(), _p(ok_flag), float(clip), _p(nonfinite), _stream())
 
 
 # ---- K11: all-pairs loss (extension) --------------------------------------------------------------------

@@ -57,10 +57,12 @@ def _needs_backward(ctx):
 
 
 def grad_scale(g):
-    """-> (s, 1/s) as 1-element fp32 device tensors, s = GRAD_TARGET / max|g| (no host sync)."""
-    amax = g.detach().abs().amax().float().clamp_min(1e-30)
-    s = (GRAD_TARGET / amax).reshape(1)
-    return s, (amax / GRAD_TARGET).reshape(1)
+    """-> (s, 1/s) as 1-element fp32 device tensors, s = GRAD_TARGET / max|g| (one launch, no host sync)."""
+    g = g.detach()
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        g = g.float().contiguous()
+    out = lib.absmax_scale(g, GRAD_TARGET)
+    return out[0:1], out[1:2]
 LEAKY_SLOPE = 0.01
 
 
@@ -115,9 +117,11 @@ def chain_forward(x: Slice, layers, packed, out: Optional[Slice] = None, last_fp
     return acts
 
 
-def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=True, inv_scale=None):
+def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=True, inv_scale=None, db_pool=None):
     """dz = (loss-scaled) gradient w.r.t. the PRE-activation output of the last layer (16-bit NHWC
-    slice).  Returns (dx Slice or None [still scaled], [dw0, db0, dw1, db1, ...] [un-scaled fp32])."""
+    slice).  Returns (dx Slice or None [still scaled], [dw0, db0, dw1, db1, ...] [un-scaled fp32]).
+    db_pool: optional [zero-filled fp32 tensor, offset]: the bias gradients of this chain are carved out of it (the
+    U-Net's five chains share one memset instead of one fill launch each)."""
     grads = [None] * (2 * len(layers))
     # bias gradients of layers 0..L-2 come for free from the epilogue of the data-gradient launch that
     # produces their dz (column sums); the last layer's is a column-sum kernel accumulating into the same
@@ -127,7 +131,11 @@ def chain_backward(dz: Slice, acts, layers, packed, need_dx, want_param_grads=Tr
         offs = [0]
         for l in layers:
             offs.append(offs[-1] + l.cout_p)
-        db_all = torch.zeros(offs[-1], dtype=torch.float32, device=dz.t.device)
+        if db_pool is not None:
+            db_all = db_pool[0][db_pool[1]:db_pool[1] + offs[-1]]
+            db_pool[1] += offs[-1]
+        else:
+            db_all = torch.zeros(offs[-1], dtype=torch.float32, device=dz.t.device)
     for i in range(len(layers) - 1, -1, -1):
         l = layers[i]
         xin = acts[i]
@@ -371,21 +379,27 @@ def unet_forward(spec: UNetSpec, x: Slice, params, need_dgrad=True, packed=None)
     return acts_right[-1], ctx
 
 
-def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True, inv_scale=None):
+def unet_backward(spec: UNetSpec, ctx, dy: Slice, need_dx=True, inv_scale=None, db_pool=None):
     """dy = (loss-scaled) gradient w.r.t. the post-activation output.  Returns (dx Slice, flat grads)."""
+    if db_pool is None:   # one zero-filled buffer for the bias gradients of every chain of the U-Net
+        total = sum(l.cout_p for l in unet_layers(spec))
+        db_pool = [torch.zeros(total, dtype=torch.float32, device=dy.t.device), 0]
     if spec.nxt is None:
         dz = _act_bwd_full(dy, ctx["acts_left"][-1], spec.left[-1])
-        return chain_backward(dz, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale)
+        return chain_backward(dz, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale,
+                              db_pool=db_pool)
     c_up, c_left = ctx["c_up"], ctx["c_left"]
     dz = _act_bwd_full(dy, ctx["acts_right"][-1], spec.right[-1])
-    d_cat, g_right = chain_backward(dz, ctx["acts_right"], spec.right, ctx["p_right"], True, inv_scale=inv_scale)
+    d_cat, g_right = chain_backward(dz, ctx["acts_right"], spec.right, ctx["p_right"], True, inv_scale=inv_scale,
+                                    db_pool=db_pool)
     d_up = lib.upsample2_bwd(d_cat.t, c_up, dy_coff=d_cat.coff)
-    d_pool, g_next = unet_backward(spec.nxt, ctx["ctx_next"], Slice(d_up, 0, c_up), True, inv_scale)
+    d_pool, g_next = unet_backward(spec.nxt, ctx["ctx_next"], Slice(d_up, 0, c_up), True, inv_scale, db_pool)
     d_left = lib.maxpool2_bwd(ctx["cat"], d_pool.t, c_left, x_coff=c_up, dy_coff=d_pool.coff, add=d_cat.t,
                               add_coff=d_cat.coff + c_up)
     left_out = ctx["acts_left"][-1]
     dzl = _act_bwd_full(Slice(d_left, 0, c_left), left_out, spec.left[-1])
-    dx, g_left = chain_backward(dzl, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale)
+    dx, g_left = chain_backward(dzl, ctx["acts_left"], spec.left, ctx["p_left"], need_dx, inv_scale=inv_scale,
+                                db_pool=db_pool)
     return dx, g_left + g_next + g_right
 
 

@@ -47,6 +47,7 @@ class FusedClipAdam:
         self._dev_tensors = self._dev_blocks = self._host_keep = None
         self._nblocks = 0
         self._nbytes = 0.0
+        self.nonfinite = torch.zeros(1, dtype=torch.int64, device=self.device)   # skipped NaN / inf gradient elements
         self._steps = []       # the CPU `step` scalars of every parameter that takes part in the update
         self._hyper = None
         self._dirty = True     # state tensors may have been replaced (load_state_dict): re-read step counts
@@ -183,7 +184,8 @@ class FusedClipAdam:
         replay) advances the host-side step count itself with note_step()."""
         if self.refresh() is None:
             return
-        lib.adam_clip_step(self._dev_tensors, self._dev_blocks, self._nblocks, self.t_dev, ok_flag, clip, self._nbytes)
+        lib.adam_clip_step(self._dev_tensors, self._dev_blocks, self._nblocks, self.t_dev, ok_flag, clip, self._nbytes,
+                           self.nonfinite)
         if count:
             self.note_step()
 
@@ -192,6 +194,10 @@ class FusedClipAdam:
         self.t += 1
         if self._steps:
             torch._foreach_add_(self._steps, 1.0)
+
+    def nonfinite_count(self):
+        """Gradient elements skipped so far because they were NaN / inf (host sync)."""
+        return int(self.nonfinite.item())
 
     def sync_state(self):
         """Kept for callers of the round-1 API: the step counts are always current now."""
