@@ -206,10 +206,10 @@ def mlp_flops_per_step(batch, spp, size, outc):
 
 def bench_preprocess(pk):
     """GPU preprocessing of a raw 1280x720, 4-spp OptaGen sample buffer (H,W,S,104) -> the 44-channel
-    KPCN buffer and the 37-channel path descriptors, against the HBM roofline.  Algorithmic bytes: every raw float is
-    read once (416 B per sample) by each of the two kernels' consumers -- kpcn reads the 13 raw channels it needs per
-    sample (two 28-byte runs = 4 sectors of 32 B) and writes 176 B per pixel; llpm reads one 176-byte run and writes
-    148 B per sample (six sectors in)."""
+    KPCN buffer and the 37-channel path descriptors, against the HBM roofline.  Algorithmic bytes = SURVEY 8(f)'s
+    per-unit figure: the whole 416-byte raw row of every sample in (the 13 / 37 channels a kernel needs are scattered
+    over the row; ncu: the statistics pass pulls 1.06 GB of the 1.53 GB buffer from DRAM, the descriptor pass 1.09 GB),
+    176 B per pixel + the 72-byte statistics workspace written and re-read (kpcn), 148 B per sample out (llpm)."""
     import torch
     from wcmc_b200 import preprocess
     h, w, s = 720, 1280, 4
@@ -231,8 +231,8 @@ def bench_preprocess(pk):
         return sorted(ts)[2]
     ms_k = timed(lambda: preprocess.preprocess_kpcn(raw))
     ms_l = timed(lambda: preprocess.preprocess_llpm(raw))
-    by_k = h * w * (s * 128.0 + 176.0 + 2 * 72.0)      # 4 sectors per sample + the 44-channel pixel + 18 workspace floats twice
-    by_l = h * w * s * (192.0 + 148.0)                 # six 32-byte sectors cover the 176-byte run it reads
+    by_k = h * w * (s * 416.0 + 176.0 + 2 * 72.0)
+    by_l = h * w * s * (416.0 + 148.0)
     return {"workload": "raw (720,1280,4,104) fp32 -> (720,1280,44) + (720,1280,4,37), L2 flushed between repetitions",
             "kpcn_ms": round(ms_k, 4), "kpcn_gbs": round(by_k / ms_k / 1e6, 1), "kpcn_frac_of_hbm": round(by_k / ms_k / 1e6 / pk["hbm_gbs"], 4),
             "llpm_ms": round(ms_l, 4), "llpm_gbs": round(by_l / ms_l / 1e6, 1), "llpm_frac_of_hbm": round(by_l / ms_l / 1e6 / pk["hbm_gbs"], 4)}
