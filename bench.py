@@ -182,12 +182,13 @@ def bench_720p(args, KPCN, make_batch):
 # (profile entry, label, bound, key of profiles/ncu_traffic.json "per_kernel" for the DRAM traffic)
 ROOFLINE_ENTRIES = (
     ("conv2d_k5", "conv_igemm_kernel<1,5> (5x5 100-channel KPCN layers, forward + data gradient, tcgen05 cta_group::2)",
-     "tensor", "conv_igemm_kernel<1, 5>"),
+     "tensor", "conv_igemm_kernel<1, 5, 0>"),
     ("conv2d_k3", "conv_igemm_kernel<*,3> (3x3 U-Net layers of PathNet, forward + data gradient)", "tensor",
-     "conv_igemm_kernel<0, 3>"),
-    ("conv2d_wgrad_all", "conv_wgrad_kernel (weight gradients of all 5x5 and 3x3 layers)", "tensor", "conv_wgrad_kernel"),
-    ("conv2d_wgrad_k5", "conv_wgrad_kernel (5x5 layers)", "tensor", "conv_wgrad_kernel"),
-    ("conv2d_wgrad_k3", "conv_wgrad_kernel (3x3 layers)", "tensor", "conv_wgrad_kernel"),
+     "conv_igemm_kernel<0, 3, 0>"),
+    ("conv2d_wgrad_all", "conv_wgrad_group_kernel + wgrad_reduce_batch_kernel (weight gradients of all 5x5 and 3x3 layers, one "
+     "grouped launch per backward pass)", "tensor", "conv_wgrad_group_kernel"),
+    ("conv2d_wgrad_k5", "conv_wgrad_group_kernel (5x5 layers: one launch per KPCN branch)", "tensor", "conv_wgrad_group_kernel"),
+    ("conv2d_wgrad_k3", "conv_wgrad_group_kernel (3x3 layers: one launch per PathNet U-Net)", "tensor", "conv_wgrad_group_kernel"),
     ("kernel_apply_fwd", "kernel_apply_fwd_kernel (8 x 92^2 pixels per launch)", "hbm", "kernel_apply_fwd_kernel<3, 21, 16>"),
     ("kernel_apply_bwd", "kernel_apply_bwd_kernel", "hbm", "kernel_apply_bwd_kernel<3, 1, 21, 16>"),
     ("pathnet_embed_fwd", "pathnet_embed_fwd_kernel", "hbm", "pathnet_embed_fwd_kernel"),

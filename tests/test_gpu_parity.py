@@ -292,6 +292,36 @@ def test_fused_last_conv_kernel_apply_vs_separate_launches(backend, oracle, n, h
         assert rel(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,pad", [(8, 128, 128, 64, 64, 3, 1), (2, 37, 53, 64, 64, 3, 1),
+                                                  (8, 64, 64, 64, 128, 3, 1), (8, 64, 64, 128, 64, 3, 1), (3, 40, 40, 39, 100, 5, 0)])
+def test_conv_resident_weights_is_bit_identical(backend, n, h, w, cin, cout, k, pad):
+    """Layers whose whole weight tensor fits the shared-memory ring load it once per CTA (`b_resident`) instead of
+    re-streaming it for every work item: same MMAs in the same order, so the output must not change by a bit
+    (knob conv_resident = 0 restores the streaming ring)."""
+    lib = backend.lib
+    rt = lib.load()
+    from wcmc_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    dt = ops.ACT_DTYPE
+    x = lib.nchw_to_nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g), dtype=dt)
+    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.05
+    b = torch.randn(cout, device="cuda", generator=g)
+    wf, wd, bp = lib.pack_weights(wt, b, want_bias=True, dtype=dt)
+    outs = {}
+    for res in (1, 0):
+        assert rt.wcmc_tuning_set(b"conv_resident", res) == 0
+        try:
+            y = lib.conv2d(x, wf, bp, k, pad, act=1, flags=1 << 21)          # single-CTA launch (residency needs it)
+            dx = lib.conv2d(y, wd, None, k, k - 1 - pad, act=0, mask=x, flags=1 << 21)
+            outs[res] = (y, dx)
+        finally:
+            rt.wcmc_tuning_set(b"conv_resident", 1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1][0], outs[0][0]) and torch.equal(outs[1][1], outs[0][1])
+    ref = torch.relu(F.conv2d(lib.nhwc_to_nchw(x, cin).double(), wt.to(dt).double(), b.double(), padding=pad))
+    assert rel(lib.nhwc_to_nchw(outs[1][0], cout), ref) < 2e-3
+
+
 @pytest.mark.parametrize("mt,nt", [(1, 0), (2, 0), (2, 64), (1, 48)])
 def test_conv_tilings_agree(backend, mt, nt):
     lib = backend.lib

@@ -20,9 +20,9 @@ for d in per.values():
     agg[name][1] += b
 ours = {k: {"launches": v[0], "dram_bytes_per_launch": int(v[1] / v[0])} for k, v in sorted(agg.items())
         if any(t in k for t in ("conv_", "pathnet", "kernel_apply", "fmse", "adam", "slab", "wgrad"))}
-k5 = ours.get("conv_igemm_kernel<1, 5>", {"dram_bytes_per_launch": None, "launches": 0})
+k5 = ours.get("conv_igemm_kernel<1, 5, 0>", ours.get("conv_igemm_kernel<1, 5>", {"dram_bytes_per_launch": None, "launches": 0}))
 print(json.dumps({"conv_igemm_k5_bytes_per_launch": k5["dram_bytes_per_launch"],
                   "source": "%s (dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d "
-                            "conv_igemm_kernel<1, 5> launches = the CTA-pair 5x5 KPCN layers, forward + data gradient)"
+                            "conv_igemm_kernel<1, 5, 0> launches = the CTA-pair 5x5 KPCN layers, forward + data gradient)"
                             % (path, k5["launches"]),
                   "per_kernel": ours}, indent=1))

@@ -46,6 +46,7 @@ struct ConvParams {
     int halo_w, halo_h;
     int plane_stride, b_stride, b_stages, plane_slots;  // shared-memory carve-up
     int tap_stride;                                      // bytes between the taps of one weight stage
+    int b_resident;   // 1: the weight ring holds ALL taps / chunks of the (single) n tile: loaded once per CTA, then reused
     void* out;
     int out_cs, out_coff, out_dtype;
     int x_dtype, w_dtype;
@@ -98,6 +99,7 @@ struct BRing {
     uint32_t cur_lo;    // (address of the current stage) >> 4
     uint32_t tap_lo;    // stride between the taps of one stage >> 4
     int stages, idx, phase;
+    bool loaded;   // resident weights: every stage has been waited for once, later items skip the barrier
 };
 
 // All taps of one 64-channel chunk.  A weight stage carries TPS taps (1, or a whole kernel row: TPS = ksize), so
@@ -111,8 +113,10 @@ __device__ __forceinline__ void mma_chunk(BRing& br, int taps, int ksize, int ro
                                           uint32_t idesc, uint32_t& accum) {
     int kx = 0;
     for (int tap = 0; tap < taps; tap += TPS) {
-        mbar_wait(&br.full[br.idx], br.phase);
-        tc_fence_after();
+        if (!br.loaded) {
+            mbar_wait(&br.full[br.idx], br.phase);
+            tc_fence_after();
+        }
         if (elect_one()) {
 #pragma unroll
             for (int u = 0; u < TPS; ++u)
@@ -269,6 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             int bs = 0, ph = 0, loaded = 0;
             const bool dry = (p.flags & (1 << 16)) != 0;   // tuning knob: weight ring filled once (wrong results)
             for (int k = 0, item; (item = item_at<KA>(p, item0, item_step, k)) < n_items; ++k) {
+                if (p.b_resident && k > 0) break;      // the ring already holds every tap of every chunk
                 const int n0 = (item % p.n_tiles) * p.nt;
                 for (int c = 0; c < p.nch; ++c) {
                     for (int tap = 0; tap < taps; tap += TPS) {   // one stage = TPS taps, one box each
@@ -296,7 +301,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     }
                 }
             }
-            for (int i = 0; i < kBStages; ++i) {   // tail, as for the halos
+            for (int i = 0; i < kBStages && !p.b_resident; ++i) {   // tail, as for the halos
                 mbar_wait(&b_empty[bs], ph ^ 1);
                 if (++bs == kBStages) { bs = 0; ph ^= 1; }
             }
@@ -321,7 +326,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             br.full = b_full; br.empty = b_empty;
             br.base_lo = smem_u32(bst) >> 4; br.stride_lo = static_cast<uint32_t>(p.b_stride) >> 4;
             br.cur_lo = br.base_lo; br.tap_lo = static_cast<uint32_t>(p.tap_stride) >> 4;
-            br.stages = p.b_stages; br.idx = 0; br.phase = 0;
+            br.stages = p.b_stages; br.idx = 0; br.phase = 0; br.loaded = false;
             int ps = 0, pph = 0;
             for (int it = 0; item_at<KA>(p, item0, item_step, it) < n_items; ++it) {
                 const int buf = it & 1;
@@ -361,6 +366,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
                     else umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
+                if (p.b_resident) br.loaded = true;     // one item has walked the whole (non-recycling) ring
             }
         }
     } else {
@@ -382,18 +388,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
         float* ka_merge = reinterpret_cast<float*>(smem + p.ka_off) + 4 * kKaHaloRows * ka_pitch;   // [128][5]
         float ka_m = -INFINITY, ka_l = 0.f, ka_a0 = 0.f, ka_a1 = 0.f, ka_a2 = 0.f;
         const int epi_tid = threadIdx.x - 96;      // 0..255 among the epilogue warps
+        // The bias of the item's n tile is staged in shared memory (second half of the barrier KB) while the item's
+        // MMAs still run: fetched per 16-column chunk from global memory it put one L2 round trip (~700 clocks) into
+        // the dependent chain of every chunk -- 3-5 k clocks per item, the "fixed per-item cost" of the small layers.
+        float* bias_s = reinterpret_cast<float*>(smem + 512);
         for (int it = 0, item; (item = item_at<KA>(p, item0, item_step, it)) < n_items; ++it) {
             const int buf = it & 1;
             const Item w = decode_item<PAIR>(p, item, rank);
             const int n0 = w.n0, rx = w.rx, ry = w.ry, n = w.n;
             int ncc = (p.cout_p - n0) >> 4;
             if (ncc > (p.nt >> 4)) ncc = p.nt >> 4;
-            mbar_wait(&acc_full[buf], (it >> 1) & 1);
-            tc_fence_after();
             const int oy = ry * 16 + ty;
             const int ox = rx * region_w + 8 * t + tx;
             const bool valid = w.live && (oy < p.Ho) && (ox < p.Wo);
             const size_t pix = (static_cast<size_t>(n) * p.Ho + oy) * p.Wo + ox;
+            if (p.bias != nullptr) {
+                asm volatile("bar.sync 3, 256;" ::: "memory");      // nobody still reads the previous item's bias
+                if (epi_tid < p.nt) bias_s[epi_tid] = (n0 + epi_tid < p.cout_p) ? __ldg(p.bias + n0 + epi_tid) : 0.f;
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+            }
+            if (p.mask != nullptr && valid) {
+                // pull this pixel's mask row (the dgrad's ReLU mask, 2 bytes per channel) towards L1 while the MMAs run
+                const __nv_bfloat16* mrow = p.mask + pix * p.mask_cs + p.mask_coff + n0;
+                for (int cc = cc0; cc < ncc; cc += ccs)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(mrow + cc * 16));
+            }
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 256 + t * 128;
 
             if (KA && n0 == 0) {
@@ -420,10 +441,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
             auto process_ka = [&](const uint32_t (&v)[16], int cc) {
                 const int ch = n0 + cc * 16;
                 float z[16];
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+                const float4* b4 = reinterpret_cast<const float4*>(bias_s + cc * 16);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 b = __ldg(b4 + i);
+                    const float4 b = b4[i];
                     z[4 * i + 0] = (__uint_as_float(v[4 * i + 0]) + b.x) * 1.4426950408889634f;
                     z[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) + b.y) * 1.4426950408889634f;
                     z[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) + b.z) * 1.4426950408889634f;
@@ -461,10 +482,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
                 if (p.bias != nullptr) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + ch);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + cc * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        float4 b = __ldg(b4 + i);
+                        const float4 b = b4[i];
                         f[4 * i + 0] += b.x;
                         f[4 * i + 1] += b.y;
                         f[4 * i + 2] += b.z;
@@ -604,6 +625,8 @@ static int g_conv_pair = 1;
 int wcmc_conv_set_pair(int v) { g_conv_pair = v ? 1 : 0; return 0; }
 static int g_conv_row_stages = 1;
 int wcmc_conv_set_row_stages(int v) { g_conv_row_stages = v ? 1 : 0; return 0; }
+static int g_conv_resident = 1;    // wcmc_tuning_set("conv_resident", 0 | 1): weights resident in shared memory when they fit
+int wcmc_conv_set_resident(int v) { g_conv_resident = v ? 1 : 0; return 0; }
 // measurement knobs of the launch-shape model (defaults = the values measured in round 1):
 //   "conv_pair_min_clk"  single-CTA MMA clocks above which a layer is launched on CTA pairs (20000)
 //   "conv_item_clk"      fixed per-item cost of the M-tiles-per-region model (1000)
@@ -768,6 +791,20 @@ static int conv2d_impl(const void* x, int x_dtype, int N, int H, int W, int x_cs
     p.b_stages = b_room / p.b_stride;
     if (p.b_stages > kMaxBStages) p.b_stages = kMaxBStages;
     if (ksize == 1 && p.b_stages > 4) p.b_stages = 4;
+    // Resident weights: a layer whose whole weight tensor (one n tile, every tap of every 64-channel chunk) fits the ring
+    // loads it ONCE per CTA.  The 64-channel 3x3 U-Net layers re-streamed 73 KB of weights per 2-tile item -- with the
+    // 41 KB halo that is 33 B/clk per SM, the TMA delivery limit (the same ~32 B/clk seen in the weight-gradient
+    // kernel), for 3.4 k clocks of MMAs: bandwidth-bound on data that never changes.  Exactly `need` stages are kept so
+    // that every item starts at stage 0 again.
+    p.b_resident = 0;
+    {
+        const int need = ((ksize * ksize + tps - 1) / tps) * p.nch;
+        if (g_conv_resident && !pair && !ka && ksize > 1 && p.n_tiles == 1 && (ksize * ksize) % tps == 0 &&
+            need <= p.b_stages && !(flags & (1 << 16))) {
+            p.b_resident = 1;
+            p.b_stages = need;
+        }
+    }
     WCMC_REQUIRE(p.b_stages >= 2, WCMC_ESHAPE, "conv2d: shared memory carve-up failed");
     p.ka_off = kBarBytes + p.plane_slots * p.plane_stride + p.b_stages * p.b_stride;
     const int smem_bytes = 1024 + p.ka_off + ka_bytes;
