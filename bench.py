@@ -523,9 +523,12 @@ def main():
                          % (h2d_bytes / 1e6, 700.0),
                    "precision": "fp16 operands (loss-scaled gradients), fp32 accumulate / master weights / losses",
                    "perm_rng": args.perm_rng, "cuda_graph": bool(use_graph), "branch_streams": bool(streams.ENABLED),
-                   "grad_exchange": (None if world == 1 else ("nccl all-reduce in the step graph; dncnn's half overlapped "
-                                     "with the path-embedding networks' backward" if sync.early is not None else
-                                     "nccl all-reduce in the step graph, after both backward passes"))},
+                   "grad_exchange": (None if world == 1 else "%s in the step graph%s" % (
+                       {"multimem": "own two-shot kernel over the NVSwitch multicast mapping (multimem.ld_reduce / st)",
+                        "peer": "own two-shot kernel over NVLink peer loads / stores",
+                        "nccl": "nccl all-reduce"}[sync.peer_transport()],
+                       "; dncnn's half overlapped with the path-embedding networks' backward"
+                       if sync.early is not None else ", after both backward passes"))},
         "e2e": {"value": batch_per_gpu * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

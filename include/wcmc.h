@@ -390,6 +390,22 @@ int wcmc_absmax_scale(const float* g, long n, float target, float* out2, void* w
  * that read the same counter value.                                                                        */
 int wcmc_random_permutation(int64_t* out, long n, unsigned long long* state, unsigned salt, void* stream);
 
+/* ---- data-parallel gradient exchange over NVSwitch peer memory (replaces nn.DataParallel's per-step gradient
+ * reduction onto GPU 0, /root/reference/train_kpcn.py:266-269; one process per GPU here) -----------------------
+ * In-place sum x scale over `world` ranks of the region [offset_floats, +n_floats) of a buffer that every rank has
+ * allocated symmetrically: `local` = this rank's mapping, `peers_dev` = DEVICE array of the `world` mappings as seen
+ * from this rank (peers_dev[rank] == local), `multicast` = multicast mapping of the same buffer or NULL (then the
+ * kernel sums peer loads in rank order: deterministic).  Two-shot: rank r reduces slice r and broadcasts it; the
+ * replicas end bit-identical.  The kernel synchronises the ranks itself through flags at byte `flag_offset_bytes`
+ * of the buffer (wcmc_grad_exchange_flag_bytes() bytes, zero-filled ONCE by the caller before the first launch on
+ * any rank, behind every region ever exchanged); `channel` 0 or 1 selects an independent set of flags so that two
+ * exchanges may be in flight at once.  Every rank must issue the same sequence of calls per channel (same region
+ * sizes); a rank that never arrives makes the others trap after ~4 s instead of hanging.  Safe to capture in a
+ * CUDA graph.  Regions and offsets in floats, multiples of 4.                                                  */
+size_t wcmc_grad_exchange_flag_bytes(void);
+int wcmc_grad_exchange(float* local, float* multicast, float* const* peers_dev, long flag_offset_bytes,
+                       long offset_floats, long n_floats, int rank, int world, int channel, float scale, void* stream);
+
 /* ---- K11: all-pairs form of the path-disentangling loss on the tensor cores (EXTENSION: the reference
  * pairs each row with one random partner, /root/reference/support/losses.py:33-61; this is the quantity
  * that estimator samples, BASELINE.json north_star (4) / configs[4]; oracle/allpairs_ref.py) ---------

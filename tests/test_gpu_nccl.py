@@ -50,6 +50,50 @@ def test_graphed_step_with_nccl_allreduce_world2(tmp_path):
                 assert v < (5e-3 if "manif" in k else 1e-3), (k, v)
 
 
+def _run_exchange_worker(tmp_path, world, extra=()):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "exchange_worker.py"),
+           str(tmp_path), *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    recs = [json.load(open(tmp_path / ("rank%d.json" % i))) for i in range(world)]
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "peer_exchange_world%d.json" % world), "w") as f:
+            json.dump(recs, f, indent=1)
+    return recs
+
+
+def _check_exchange(recs, world):
+    ran = 0
+    for rec in recs:
+        for name, t in rec["transports"].items():
+            if "unavailable" in t:
+                continue
+            ran += 1
+            assert t["replicas_identical"], (name, t)
+            assert t["max_abs_err"] < 1e-5 and t["graph_two_channels_max_abs_err"] < 1e-5, (name, t)
+            if world <= 2:     # one fp32 add (commutative) and an exact scale: nothing left to differ in
+                assert t["bitwise_equal_to_nccl"], (name, t)
+    return ran
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under `gpurun --gpus 2`)")
+def test_peer_exchange_kernel_matches_nccl_world2(tmp_path):
+    """`wcmc_grad_exchange` (multicast and peer-load variants) == NCCL all-reduce on ragged sizes, both channels in
+    flight, eager and graph-replayed.  The symmetric allocation must exist on an NVSwitch box: no skip here."""
+    recs = _run_exchange_worker(tmp_path, 2)
+    assert _check_exchange(recs, 2) >= 2, recs     # at least one transport on both ranks
+    assert all("unavailable" not in r["transports"]["peer"] for r in recs), recs
+
+
+def test_peer_exchange_kernel_single_rank(tmp_path):
+    """The same kernel with a one-rank group (what a 1-GPU box can exercise: flags, epochs, slices, graph replay)."""
+    recs = _run_exchange_worker(tmp_path, 1)
+    if _check_exchange(recs, 1) == 0:
+        pytest.skip("symmetric memory unavailable with one rank: %s" % recs[0]["transports"])
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run under `gpurun --gpus 2`)")
 def test_dataparallel_two_devices_and_non_current_device():
     """The reference's own multi-GPU mode (single process, `nn.DataParallel`, replicas in threads,

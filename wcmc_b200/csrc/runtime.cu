@@ -114,6 +114,7 @@ int wcmc_conv_set_pair(int v);       // conv_igemm.cu
 int wcmc_conv_set_model(int which, int v);  // conv_igemm.cu
 int wcmc_wgrad_group_set(int which, int v); // conv_wgrad_group.cu
 int wcmc_conv_set_resident(int v);          // conv_igemm.cu
+int wcmc_exchange_set_blocks(int v);        // grad_exchange.cu
 extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "ka_tile_w") == 0 && wcmc_ka_set_tile(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_uniform") == 0) return wcmc_wgrad_set_uniform(value);
@@ -122,6 +123,7 @@ extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "conv_pair_min_clk") == 0 && wcmc_conv_set_model(0, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_item_clk") == 0 && wcmc_conv_set_model(1, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_resident") == 0) return wcmc_conv_set_resident(value);
+    if (name != nullptr && strcmp(name, "exchange_blocks") == 0 && wcmc_exchange_set_blocks(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_group_pack") == 0) return wcmc_wgrad_group_set(0, value);
     if (name != nullptr && strcmp(name, "wgrad_group") == 0) return wcmc_wgrad_group_set(1, value);
     if (name != nullptr && strcmp(name, "conv_plane_slots") == 0 && wcmc_conv_set_model(2, value) == 0) return WCMC_OK;

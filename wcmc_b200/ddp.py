@@ -9,28 +9,119 @@ the reference's step order requires it: after both backward passes, before clip_
 Adam (support/interfaces.py:237-238 -> :261 -> :271).  A stock DistributedDataParallel wrapper
 does not fit: each of the two backward passes touches only half of `dncnn`'s parameters.
 """
+import os
+import warnings
+
 import torch
 import torch.distributed as dist
 
 
+class PeerExchange:
+    """A symmetric fp32 buffer (same size on every rank of `group`, every rank's copy mapped into every other rank's
+    address space, one multicast mapping where the switch offers it) plus the in-place all-reduce kernel over it
+    (`wcmc_grad_exchange`, csrc/grad_exchange.cu).  torch's symmetric-memory allocator provides the mappings; the
+    data path is this package's own kernel.  Construction is a collective."""
+
+    def __init__(self, n_floats, group=None, device=None, multicast=True):
+        import torch.distributed._symmetric_memory as symm
+        from . import lib
+        group = group if group is not None else dist.group.WORLD
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.capacity = (int(n_floats) + 3) // 4 * 4
+        self.flag_offset = self.capacity * 4
+        self.buf = symm.empty(self.capacity + lib.grad_exchange_flag_bytes() // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()                      # the flags start at zero on every rank ...
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        dist.barrier(group)                   # ... before any rank can launch
+        self.rank, self.world = self.hdl.rank, self.hdl.world_size
+        self.multicast_ptr = int(self.hdl.multicast_ptr) if multicast else 0
+        self.peers_dev = int(self.hdl.buffer_ptrs_dev)
+        self._lib = lib
+
+    @property
+    def transport(self):
+        return "multimem" if self.multicast_ptr else "peer"
+
+    def all_reduce_(self, n, scale=1.0, channel=0, offset=0):
+        """buf[offset:offset+n] <- scale * sum over ranks, on the current stream (n is rounded up to 4 floats)."""
+        n4 = (int(n) + 3) // 4 * 4
+        assert offset % 4 == 0 and offset + n4 <= self.capacity
+        self._lib.grad_exchange(self.buf, self.multicast_ptr, self.peers_dev, self.flag_offset, offset, n4, self.rank,
+                                self.world, channel, scale)
+        return self.buf[offset:offset + n]
+
+
 class GradAllReduce:
-    """Callable(models) for KPCNInterface.grad_sync.  Works with any initialised process group
-    (nccl on GPUs, gloo in the CPU tests).
+    """Callable(models) for KPCNInterface.grad_sync.  Works with any initialised process group.
+
+    Transport (`transport=` or WCMC_EXCHANGE; default "auto"): on CUDA the gradients travel through this package's own
+    NVSwitch kernel over symmetric peer memory (`PeerExchange`: "multimem" = in-switch reduction + multicast, "peer" =
+    peer loads / stores in rank order), falling back to "nccl" (`dist.all_reduce`) when the symmetric allocation is
+    not available on the machine; gloo groups (the CPU tests) always take `dist.all_reduce`.
 
     Overlap: `early(models)` may be called DURING the backward pass for models whose gradients are already complete
     (the interface calls it for `dncnn` once the KPCN part of the traversal is done, while the two path-embedding
-    networks still back-propagate): it starts an asynchronous all-reduce of those gradients on the process group's
-    own stream.  `__call__` then only reduces what is left and waits for the early part -- under a CUDA-graph
-    capture the whole pattern becomes a fork / join inside the graph.  Every rank issues the same collectives in
-    the same order."""
+    networks still back-propagate): it starts the exchange of those gradients on a side stream.  `__call__` then only
+    reduces what is left and waits for the early part -- under a CUDA-graph capture the whole pattern becomes a
+    fork / join inside the graph.  Every rank issues the same exchanges in the same order."""
 
-    def __init__(self, group=None, overlap=True):
+    def __init__(self, group=None, overlap=True, transport=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bytes_last = 0
-        self._early = []           # (work, flat buffer, gradient tensors) of reductions in flight
+        self._early = []           # (work | None, flat buffer, gradient tensors) of reductions in flight
+        self.transport = (transport or os.environ.get("WCMC_EXCHANGE", "auto")).lower()
+        assert self.transport in ("auto", "nccl", "peer", "multimem")
+        self._px = {}              # channel -> PeerExchange
+        self._side = None
         if not overlap:
             self.early = None      # the interface then keeps the single traversal + one reduction
+
+    # ---- transport ------------------------------------------------------------------------------------------------
+    def _use_peer(self, grads):
+        return self.transport != "nccl" and self.world > 1 and bool(grads) and grads[0].is_cuda
+
+    def _exchange(self, channel, n):
+        """The symmetric buffer of `channel`, large enough for n floats, or None (-> dist.all_reduce)."""
+        px = self._px.get(channel)
+        if px is not None and px.capacity >= n:
+            return px
+        if px is None and channel in self._px:
+            return None                              # tried before, not available
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("GradAllReduce: the symmetric exchange buffer must exist before a CUDA-graph capture "
+                               "(call prepare(models) first)")
+        err = None
+        try:
+            px = PeerExchange(n, self.group, multicast=self.transport != "peer")
+            if self.transport == "multimem" and not px.multicast_ptr:
+                raise RuntimeError("no multicast mapping on this machine")
+        except Exception as e:                       # noqa: BLE001 -- whatever the allocator raises
+            px, err = None, e
+        agree = torch.tensor([0 if px is None else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if int(agree) == 0:
+            if self.transport != "auto":
+                raise RuntimeError(f"GradAllReduce(transport={self.transport!r}): symmetric memory unavailable: {err}")
+            warnings.warn(f"GradAllReduce: symmetric peer memory unavailable ({err}); using NCCL all_reduce")
+            px = None
+        self._px[channel] = px
+        return px
+
+    def prepare(self, models):
+        """Allocates the exchange buffers for all of `models`' parameters (a collective; needed before a CUDA-graph
+        capture, otherwise done on first use)."""
+        params = [p for m in models.values() for p in m.parameters()]
+        if not self._use_peer(params):
+            return
+        n = sum(p.numel() for p in params) + 4
+        for channel in (0, 1) if self.early is not None else (1,):
+            self._exchange(channel, n)
+
+    def peer_transport(self):
+        px = [p for p in self._px.values() if p is not None]
+        return px[0].transport if px else "nccl"
 
     def _flatten(self, grads):
         return torch.cat([g.reshape(-1) for g in grads])
@@ -41,19 +132,34 @@ class GradAllReduce:
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
         if not grads:
             return
-        flat = self._flatten(grads)
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._early.append((work, flat, grads))
+        n = sum(g.numel() for g in grads)
+        px = self._exchange(0, n) if self._use_peer(grads) else None
+        if px is None:
+            flat = self._flatten(grads)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._early.append((work, flat, grads))
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            torch.cat([g.reshape(-1) for g in grads], out=px.buf[:n])
+            flat = px.all_reduce_(n, 1.0 / self.world, channel=0)
+        self._early.append((None, flat, grads))
 
     def drain(self):
         """Waits for and forgets reductions started by `early` whose step never reached `__call__` (gradient-only
         passes: `train_batch(grad_hook_mode=True)`, the eager warm-up runs before a CUDA-graph capture)."""
         early, self._early = self._early, []
         for work, _, _ in early:
-            work.wait()
+            if work is not None:
+                work.wait()
+            else:
+                torch.cuda.current_stream().wait_stream(self._side)
 
-    def _finish(self, flat, grads):
-        flat.div_(self.world)
+    def _finish(self, flat, grads, scaled=False):
+        if not scaled:
+            flat.div_(self.world)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
         return flat.numel() * flat.element_size()
 
@@ -72,16 +178,25 @@ class GradAllReduce:
             parts = [g.reshape(-1) for g in grads]
             if ok is not None:
                 parts.append((~ok).to(parts[0].dtype if parts else torch.float32).reshape(1))
-            flat = torch.cat(parts)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            n = sum(t.numel() for t in parts)
+            px = self._exchange(1, n) if self._use_peer(parts) else None
+            if px is None:
+                flat = torch.cat(parts)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                torch.cat(parts, out=px.buf[:n])
+                flat = px.all_reduce_(n, 1.0 / self.world, channel=1)
             if ok is not None:
                 all_ok = flat[-1] == 0
                 flat = flat[:-1]
             if grads:
-                nbytes += self._finish(flat, grads)
+                nbytes += self._finish(flat, grads, scaled=px is not None)
         for work, flat_e, grads_e in early:
-            work.wait()                       # the current stream waits for the collective
-            nbytes += self._finish(flat_e, grads_e)
+            if work is not None:
+                work.wait()                       # the current stream waits for the collective
+            else:
+                torch.cuda.current_stream().wait_stream(self._side)
+            nbytes += self._finish(flat_e, grads_e, scaled=work is None)
         self.bytes_last = nbytes
         return all_ok
 

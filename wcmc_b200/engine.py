@@ -38,6 +38,8 @@ class GraphedTrainStep:
         self.graph = None
         self.loss = None
         self.flags = None
+        if getattr(itf.grad_sync, "prepare", None) is not None:
+            itf.grad_sync.prepare(itf.models)   # symmetric exchange buffers: a collective, not capturable
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -66,7 +68,7 @@ class GraphedTrainStep:
     def _capture(self):
         itf = self.itf
         # clip + Adam (one kernel, predicated on the finite flag) join the graph.  With data parallelism the
-        # NCCL gradient all-reduce sits between backward and update (support/interfaces.py:237-238 -> :261 ->
+        # gradient exchange sits between backward and update (support/interfaces.py:237-238 -> :261 ->
         # :271) and is captured too (WCMC_GRAPH_ALLREDUCE=0 keeps all-reduce + optimiser outside the graph).
         self.sync_in_graph = itf.grad_sync is not None and os.environ.get("WCMC_GRAPH_ALLREDUCE", "1") != "0"
         self.fused = itf._fused() if (itf.grad_sync is None or self.sync_in_graph) else None

@@ -116,6 +116,9 @@ SIGNATURES = {
     "wcmc_image_losses": (c_int, [c_void_p] * 6 + [ctypes.POINTER(c_long), c_int, c_int, c_int, c_float] + [c_void_p] * 4
                           + [c_size_t, c_void_p]),
     "wcmc_random_permutation": (c_int, [c_void_p, c_long, c_void_p, ctypes.c_uint, c_void_p]),
+    "wcmc_grad_exchange_flag_bytes": (c_size_t, []),
+    "wcmc_grad_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_long, c_long, c_int, c_int, c_int, c_float,
+                                   c_void_p]),
     "wcmc_adam_chunk": (c_int, []),
     "wcmc_adam_clip_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "wcmc_fmse_allpairs_workspace": (c_size_t, [c_int, c_int]),
@@ -790,6 +793,24 @@ def random_permutation(n, state, salt=0, out=None):
     _run(lib.wcmc_random_permutation, "random_permutation", n * 8.0, out.data_ptr(), n, state.data_ptr(), int(salt) & 0xFFFFFFFF,
          _stream())
     return out
+
+
+def tuning_set(name, value):
+    """Measurement aid (tools/, A/B runs): forwards to wcmc_tuning_set."""
+    _check(init().wcmc_tuning_set(name.encode(), int(value)), "wcmc_tuning_set")
+
+
+def grad_exchange_flag_bytes():
+    return int(init().wcmc_grad_exchange_flag_bytes())
+
+
+def grad_exchange(buf, multicast_ptr, peers_dev_ptr, flag_offset_bytes, offset, n, rank, world, channel, scale):
+    """In-place sum x scale over the ranks of buf[offset:offset+n] (fp32 symmetric buffer; wcmc_b200/ddp.py owns the
+    mappings).  One kernel per rank, synchronised across the ranks by flags inside the buffer."""
+    lib = init(buf.device)
+    assert buf.dtype == torch.float32 and buf.is_contiguous()
+    _run(lib.wcmc_grad_exchange, "grad_exchange", n * 4.0, buf.data_ptr(), int(multicast_ptr) or None, int(peers_dev_ptr),
+         int(flag_offset_bytes), int(offset), int(n), int(rank), int(world), int(channel), float(scale), _stream())
 
 
 # ---- K6/K7: fused PathNet MLPs ----------------------------------------------------------------------
