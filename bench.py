@@ -528,7 +528,8 @@ def main():
                         "peer": "own two-shot kernel over NVLink peer loads / stores",
                         "nccl": "nccl all-reduce"}[sync.peer_transport()],
                        "; dncnn's half overlapped with the path-embedding networks' backward"
-                       if sync.early is not None else ", after both backward passes"))},
+                       if sync.early is not None else ", after both backward passes")),
+                   "grad_exchange_channels": None if world == 1 else sync.describe()},
         "e2e": {"value": batch_per_gpu * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kAdamThreads)
 adam_clip_kernel(const wcmc_adam_tensor* __restrict__ tensors, const int2* __restrict__ blocks,
                  const int* __restrict__ step, const int* __restrict__ ok_flag, float clip,
                  unsigned long long* __restrict__ nonfinite) {
+    wcmc::pdl_start();
     if (ok_flag != nullptr && *ok_flag == 0) return;
     const int2 bk = blocks[blockIdx.x];
     const wcmc_adam_tensor T = tensors[bk.x];
@@ -87,6 +88,7 @@ adam_clip_kernel(const wcmc_adam_tensor* __restrict__ tensors, const int2* __res
 }
 
 __global__ void adam_tick_kernel(int* step, const int* ok_flag) {
+    wcmc::pdl_start();
     if (ok_flag == nullptr || *ok_flag != 0) *step += 1;
 }
 
@@ -101,11 +103,11 @@ extern "C" int wcmc_adam_clip_step(const wcmc_adam_tensor* dev_tensors, const in
     WCMC_REQUIRE(dev_tensors != nullptr && dev_blocks != nullptr && dev_step != nullptr && nblocks >= 0,
                  WCMC_ESHAPE, "adam_clip_step: null pointer");
     if (nblocks > 0) {
-        adam_clip_kernel<<<nblocks, kAdamThreads, 0, stream>>>(dev_tensors, reinterpret_cast<const int2*>(dev_blocks),
+        WCMC_LAUNCH(adam_clip_kernel, nblocks, kAdamThreads, 0, stream, dev_tensors, reinterpret_cast<const int2*>(dev_blocks),
                                                                dev_step, dev_ok_flag, clip, dev_nonfinite_count);
         WCMC_LAUNCH_CHECK();
     }
-    adam_tick_kernel<<<1, 1, 0, stream>>>(dev_step, dev_ok_flag);
+    WCMC_LAUNCH(adam_tick_kernel, 1, 1, 0, stream, dev_step, dev_ok_flag);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

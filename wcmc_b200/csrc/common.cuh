@@ -65,11 +65,59 @@ int wcmc_func_smem(const void* kernel, int bytes);
     } while (0)
 
 // ------------------------------------------------------------------------------------------
+// launches: programmatic dependent launch (PDL)
+// ------------------------------------------------------------------------------------------
+// Every kernel of this library starts with `pdl_launch_dependents(); pdl_wait();` (after its TMEM allocation, if it has
+// one) and is launched through WCMC_LAUNCH with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// of the stream may become resident as soon as every CTA of this one runs (or has left), set up its barriers /
+// tensor memory / descriptors in the shadow of this kernel's tail, and then blocks in `griddepcontrol.wait` until
+// this grid has COMPLETED and its memory is visible.  Rules that keep this safe:
+//   * nothing touches global memory before pdl_wait() (kernel parameters, tensor maps and shared memory are fine);
+//   * a kernel that allocates tensor memory triggers only AFTER the allocation (otherwise an early dependent could
+//     take the columns a late CTA of this grid still needs, while waiting for this grid: deadlock).
+// A kernel launched without the attribute, or after a kernel that never triggers (torch's), behaves as usual.
+// wcmc_tuning_set("pdl", 0) turns the attribute off.
+int wcmc_pdl_enabled();
+#ifdef __CUDACC__
+namespace wcmc {
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = wcmc_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+}  // namespace wcmc
+#define WCMC_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                           \
+        cudaError_t _e = wcmc::launch_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
+        if (_e != cudaSuccess) {                                                                   \
+            wcmc_set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return WCMC_ECUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
 namespace wcmc {
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_start() {   // kernels without tensor memory: first statement of the kernel
+    pdl_launch_dependents();
+    pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -41,6 +41,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const V8& v, int dt = WCMC
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                     __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int N, int H, int W,
                                     int C8, int dt) {
+    wcmc::pdl_start();
     const int Ho = H / 2, Wo = W / 2;
     const long total = static_cast<long>(N) * Ho * Wo * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -65,6 +66,7 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, int x_c
                                     const __nv_bfloat16* __restrict__ add, int add_cs, int add_coff,
                                     __nv_bfloat16* __restrict__ dx, int dx_cs, int dx_coff, int N, int H, int W,
                                     int C8, int dt) {
+    wcmc::pdl_start();
     const int Ho = H / 2, Wo = W / 2;
     const long total = static_cast<long>(N) * Ho * Wo * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -111,6 +113,7 @@ __device__ __forceinline__ void up2_src(int o, int n_in, int& i0, int& i1, float
 __global__ void upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                      __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int N, int h, int w,
                                      int C8, int dt) {
+    wcmc::pdl_start();
     const int H = 2 * h, W = 2 * w;
     const long total = static_cast<long>(N) * H * W * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -138,6 +141,7 @@ __global__ void upsample2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_
 __global__ void upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, int dy_coff,
                                      __nv_bfloat16* __restrict__ dx, int dx_cs, int dx_coff, int N, int h, int w,
                                      int C8, int dt) {
+    wcmc::pdl_start();
     const int H = 2 * h, W = 2 * w;
     const long total = static_cast<long>(N) * h * w * C8;
     WCMC_GRID_STRIDE(i, total) {
@@ -174,6 +178,7 @@ __global__ void upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int d
 __global__ void spp_reduce_kernel(const __nv_bfloat16* __restrict__ x, int x_cs, int x_coff,
                                   __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int B, int S, long HW,
                                   int C8, float scale, int dt) {
+    wcmc::pdl_start();
     const long total = static_cast<long>(B) * HW * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
@@ -199,6 +204,7 @@ __global__ void spp_broadcast_kernel(const __nv_bfloat16* __restrict__ x, int x_
                                      const __nv_bfloat16* __restrict__ add, int add_cs, int add_coff,
                                      __nv_bfloat16* __restrict__ y, int y_cs, int y_coff, int B, int S, long HW,
                                      int C8, float scale, int dt) {
+    wcmc::pdl_start();
     const long total = static_cast<long>(B) * S * HW * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
@@ -219,6 +225,7 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dy_cs, 
                                const __nv_bfloat16* __restrict__ y, int y_cs, int y_coff,
                                __nv_bfloat16* __restrict__ dz, int dz_cs, int dz_coff, long npix, int C8,
                                float slope, int dt) {
+    wcmc::pdl_start();
     const long total = npix * C8;
     WCMC_GRID_STRIDE(i, total) {
         int c = static_cast<int>(i % C8) * 8;
@@ -249,8 +256,7 @@ extern "C" int wcmc_maxpool2_fwd(const void* x, int x_cs, int x_coff, void* y, i
     WCMC_EW_CHECK("maxpool2_fwd", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, WCMC_ESHAPE, "maxpool2: H, W must be even");
     long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
-    maxpool2_fwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, H, W,
+    WCMC_LAUNCH(maxpool2_fwd_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, H, W,
         C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -262,8 +268,7 @@ extern "C" int wcmc_maxpool2_bwd(const void* x, int x_cs, int x_coff, const void
     WCMC_EW_CHECK("maxpool2_bwd", C, x_cs, x_coff, dy_cs, dy_coff, add_cs, add_coff, dx_cs, dx_coff);
     WCMC_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, WCMC_ESHAPE, "maxpool2: H, W must be even");
     long total = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
-    maxpool2_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff,
+    WCMC_LAUNCH(maxpool2_bwd_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff,
         static_cast<const __nv_bfloat16*>(add), add_cs, add_coff, static_cast<__nv_bfloat16*>(dx), dx_cs, dx_coff,
         N, H, W, C / 8, dtype);
     WCMC_LAUNCH_CHECK();
@@ -275,8 +280,7 @@ extern "C" int wcmc_upsample2_fwd(const void* x, int x_cs, int x_coff, void* y, 
     WCMC_EW_CHECK("upsample2_fwd", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(N > 0 && h > 0 && w > 0, WCMC_ESHAPE, "upsample2: bad shape");
     long total = static_cast<long>(N) * h * w * 4 * (C / 8);
-    upsample2_fwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, h, w,
+    WCMC_LAUNCH(upsample2_fwd_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, N, h, w,
         C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -287,8 +291,7 @@ extern "C" int wcmc_upsample2_bwd(const void* dy, int dy_cs, int dy_coff, void* 
     WCMC_EW_CHECK("upsample2_bwd", C, dy_cs, dy_coff, dx_cs, dx_coff);
     WCMC_REQUIRE(N > 0 && h > 0 && w > 0, WCMC_ESHAPE, "upsample2: bad shape");
     long total = static_cast<long>(N) * h * w * (C / 8);
-    upsample2_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<__nv_bfloat16*>(dx), dx_cs, dx_coff, N, h,
+    WCMC_LAUNCH(upsample2_bwd_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<__nv_bfloat16*>(dx), dx_cs, dx_coff, N, h,
         w, C / 8, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -299,8 +302,7 @@ extern "C" int wcmc_spp_reduce(const void* x, int x_cs, int x_coff, void* y, int
     WCMC_EW_CHECK("spp_reduce", C, x_cs, x_coff, y_cs, y_coff);
     WCMC_REQUIRE(B > 0 && S > 0 && HW > 0, WCMC_ESHAPE, "spp_reduce: bad shape");
     long total = static_cast<long>(B) * HW * (C / 8);
-    spp_reduce_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW,
+    WCMC_LAUNCH(spp_reduce_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW,
         C / 8, scale, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -312,8 +314,7 @@ extern "C" int wcmc_spp_broadcast(const void* x, int x_cs, int x_coff, const voi
     WCMC_EW_CHECK("spp_broadcast", C, x_cs, x_coff, add_cs, add_coff, y_cs, y_coff);
     WCMC_REQUIRE(B > 0 && S > 0 && HW > 0, WCMC_ESHAPE, "spp_broadcast: bad shape");
     long total = static_cast<long>(B) * S * HW * (C / 8);
-    spp_broadcast_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(add), add_cs, add_coff,
+    WCMC_LAUNCH(spp_broadcast_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), x_cs, x_coff, static_cast<const __nv_bfloat16*>(add), add_cs, add_coff,
         static_cast<__nv_bfloat16*>(y), y_cs, y_coff, B, S, HW, C / 8, scale, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -324,8 +325,7 @@ extern "C" int wcmc_act_bwd(const void* dy, int dy_cs, int dy_coff, const void* 
     WCMC_EW_CHECK("act_bwd", C, dy_cs, dy_coff, y_cs, y_coff, dz_cs, dz_coff);
     WCMC_REQUIRE(npix > 0 && (act == WCMC_ACT_RELU || act == WCMC_ACT_LEAKY), WCMC_ESHAPE, "act_bwd: bad args");
     long total = npix * (C / 8);
-    act_bwd_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<const __nv_bfloat16*>(y), y_cs, y_coff,
+    WCMC_LAUNCH(act_bwd_kernel, ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(dy), dy_cs, dy_coff, static_cast<const __nv_bfloat16*>(y), y_cs, y_coff,
         static_cast<__nv_bfloat16*>(dz), dz_cs, dz_coff, npix, C / 8, act == WCMC_ACT_RELU ? 0.f : slope, dtype);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

@@ -40,6 +40,7 @@ fmse_perm_fwd_kernel(PView pv, RView rv, const int64_t* __restrict__ idx_patch,
                      float* __restrict__ e_patch, float* __restrict__ e_batch,
                      int32_t* __restrict__ inv_patch, int32_t* __restrict__ inv_batch,
                      float* __restrict__ partial, int* __restrict__ nonfinite) {
+    wcmc::pdl_start();
     const int hw = H * W;
     const int n = S * hw;
     const int b = blockIdx.y;
@@ -121,6 +122,7 @@ fmse_perm_fwd_kernel(PView pv, RView rv, const int64_t* __restrict__ idx_patch,
 // loss[0] = 1/2 mean e_patch^2, loss[1] = 1/2 mean e_batch^2 (both means over B*n rows)
 __global__ void __launch_bounds__(kThreads)
 fmse_finish_kernel(const float* __restrict__ partial, int nblocks, double inv_rows, float* __restrict__ loss) {
+    wcmc::pdl_start();
     double sp = 0.0, sb = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += kThreads) {
         sp += partial[2 * i];
@@ -150,6 +152,7 @@ fmse_perm_bwd_kernel(PView pv, const int64_t* __restrict__ idx_patch, const int6
                      const float* __restrict__ w_patch, const float* __restrict__ w_batch,
                      const float* __restrict__ scale, float coef_patch, float coef_batch, int B, int S, int C,
                      int H, int W, float* __restrict__ dp, long d_sb, long d_ss, long d_sc, long d_sh) {
+    wcmc::pdl_start();
     const int hw = H * W;
     const int n = S * hw;
     const int b = blockIdx.y;
@@ -218,11 +221,11 @@ extern "C" int wcmc_fmse_perm_fwd(const float* p, long p_sb, long p_ss, long p_s
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     PView pv{p, p_sb, p_ss, p_sc, p_sh};
     RView rv{ref, r_sb, r_sc, r_sh};
-    fmse_perm_fwd_kernel<<<grid, kThreads, 0, st>>>(pv, rv, idx_patch, idx_batch, B, S, C, H, W, e_patch, e_batch,
+    WCMC_LAUNCH(fmse_perm_fwd_kernel, grid, kThreads, 0, st, pv, rv, idx_patch, idx_batch, B, S, C, H, W, e_patch, e_batch,
                                                     inv_patch, inv_batch, static_cast<float*>(workspace),
                                                     nonfinite);
     WCMC_LAUNCH_CHECK();
-    fmse_finish_kernel<<<1, kThreads, 0, st>>>(static_cast<const float*>(workspace), grid.x * grid.y,
+    WCMC_LAUNCH(fmse_finish_kernel, 1, kThreads, 0, st, static_cast<const float*>(workspace), grid.x * grid.y,
                                                1.0 / (static_cast<double>(B) * n), loss);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -242,8 +245,7 @@ extern "C" int wcmc_fmse_perm_bwd_strided(const float* p, long p_sb, long p_ss, 
     const int n = S * H * W;
     dim3 grid((n + kThreads - 1) / kThreads, B);
     PView pv{p, p_sb, p_ss, p_sc, p_sh};
-    fmse_perm_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        pv, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch, B, S, C, H,
+    WCMC_LAUNCH(fmse_perm_bwd_kernel, grid, kThreads, 0, static_cast<cudaStream_t>(stream), pv, idx_patch, idx_batch, inv_patch, inv_batch, w_patch, w_batch, scale, coef_patch, coef_batch, B, S, C, H,
         W, dp, d_sb, d_ss, d_sc, d_sh);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

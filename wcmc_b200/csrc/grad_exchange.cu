@@ -25,14 +25,14 @@
 
 namespace {
 
-constexpr int kXThreads = 512;
+constexpr int kXThreads = 256;   // small CTAs with few registers: they fit next to a resident convolution CTA
 constexpr int kXMaxBlocks = 128;
 constexpr int kXMaxWorld = 16;
 constexpr int kXChannels = 2;
 // uint32 words at the flag offset: flags [channel][block][source rank], then this rank's launch counters [channel][block]
 constexpr int kXFlagWords = kXChannels * kXMaxBlocks * kXMaxWorld + kXChannels * kXMaxBlocks;
 
-int g_blocks = 32;
+int g_blocks = 0;   // 0 = per transport: 64 CTAs feed the multicast path, the peer-load path wants every SM (128)
 
 struct XParams {
     float* local;          // this rank's mapping
@@ -99,8 +99,9 @@ __device__ __forceinline__ void cross_rank_barrier(const XParams& P, uint32_t ep
     __syncthreads();
 }
 
-template <bool MC, int U>
-__global__ void __launch_bounds__(kXThreads) grad_exchange_kernel(const XParams P) {
+// W > 0: compile-time world size (all W x U peer loads of a thread are issued before the first add); W = 0: any world.
+template <bool MC, int U, int W>
+__global__ void __launch_bounds__(kXThreads, 4) grad_exchange_kernel(const XParams P) {
     __shared__ uint32_t s_epoch;
     if (threadIdx.x == 0) {
         uint32_t* counter = reinterpret_cast<uint32_t*>(P.local) + P.flag_word + kXChannels * kXMaxBlocks * kXMaxWorld +
@@ -121,10 +122,29 @@ __global__ void __launch_bounds__(kXThreads) grad_exchange_kernel(const XParams 
                 const long i = base + static_cast<long>(u) * kXThreads;
                 if (i < P.hi4) v[u] = mc_ld_reduce(P.mc + 4 * i);
             }
+        } else if (W > 0) {
+            float4 t[W > 0 ? W : 1][U];
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const float* src = P.peers[q];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long i = base + static_cast<long>(u) * kXThreads;
+                    t[q][u] = i < P.hi4 ? peer_ld(src + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u] = t[0][u];
+#pragma unroll
+                for (int q = 1; q < W; ++q) {   // rank order: the sum does not depend on who computes it
+                    v[u].x += t[q][u].x; v[u].y += t[q][u].y; v[u].z += t[q][u].z; v[u].w += t[q][u].w;
+                }
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < P.world; ++q) {   // rank order: the sum does not depend on who computes it
+            for (int q = 0; q < P.world; ++q) {
                 const float* src = P.peers[q];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(kXThreads) grad_exchange_kernel(const XParams 
 }  // namespace
 
 int wcmc_exchange_set_blocks(int v) {
-    if (v < 1 || v > kXMaxBlocks) return 1;
+    if (v < 0 || v > kXMaxBlocks) return 1;
     g_blocks = v;
     return 0;
 }
@@ -198,14 +218,20 @@ extern "C" int wcmc_grad_exchange(float* local, float* multicast, float* const* 
     P.world = world;
     P.chan = channel;
     P.scale = scale;
-    // every rank must launch the SAME grid (the barriers pair CTAs by index): it depends on the region only
-    constexpr int U = 4;
-    const long per_cta = static_cast<long>(kXThreads) * U;
-    const int grid = static_cast<int>(std::max<long>(1, std::min<long>(g_blocks, (per + per_cta - 1) / per_cta)));
+    // every rank must launch the SAME grid (the barriers pair CTAs by index): it depends on the region and the world only
+    const int want = g_blocks > 0 ? g_blocks : (multicast != nullptr ? 64 : kXMaxBlocks);
+    const long per_cta = static_cast<long>(kXThreads) * 4;
+    const int grid = static_cast<int>(std::max<long>(1, std::min<long>(want, (per + per_cta - 1) / per_cta)));
     if (multicast != nullptr)
-        grad_exchange_kernel<true, U><<<grid, kXThreads, 0, stream>>>(P);
+        grad_exchange_kernel<true, 4, 0><<<grid, kXThreads, 0, stream>>>(P);
+    else if (world == 2)          // peer loads: W x U 16-byte loads in flight per thread
+        grad_exchange_kernel<false, 4, 2><<<grid, kXThreads, 0, stream>>>(P);
+    else if (world == 4)
+        grad_exchange_kernel<false, 2, 4><<<grid, kXThreads, 0, stream>>>(P);
+    else if (world == 8)
+        grad_exchange_kernel<false, 1, 8><<<grid, kXThreads, 0, stream>>>(P);
     else
-        grad_exchange_kernel<false, 2><<<grid, kXThreads, 0, stream>>>(P);
+        grad_exchange_kernel<false, 4, 0><<<grid, kXThreads, 0, stream>>>(P);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

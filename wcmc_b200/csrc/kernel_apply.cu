@@ -88,6 +88,7 @@ template <int C, int KS, int TW>
 __global__ void __launch_bounds__(kKaThreads, 4)
 kernel_apply_fwd_kernel(const float* __restrict__ logits, int l_cs, const float* __restrict__ data,
                         float* __restrict__ out, float* __restrict__ stats, int N, int H, int W, int ks_rt) {
+    wcmc::pdl_start();
     extern __shared__ float4 sm4[];
     const int ks = KS > 0 ? KS : ks_rt;
     const int taps = ks * ks;
@@ -162,6 +163,7 @@ kernel_apply_bwd_kernel(const float* __restrict__ logits, int l_cs, const float*
                         const float* __restrict__ out, const float* __restrict__ stats,
                         const float* __restrict__ gout, void* __restrict__ dlogits, int dl_cs, int N, int H,
                         int W, int ks_rt, const float* __restrict__ scale) {
+    wcmc::pdl_start();
     constexpr bool H16 = DT != WCMC_F32;
     const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     extern __shared__ float4 sm4[];
@@ -279,7 +281,7 @@ static int launch_fwd2(const float* logits, int l_cs, const float* data, float* 
     dim3 grid((W + TW - 1) / TW, (H + kKaTileH - 1) / kKaTileH, N);
     size_t smem = ka_smem_bytes(ks, TW, 0);
     WCMC_FUNC_SMEM((kernel_apply_fwd_kernel<C, KS, TW>), static_cast<int>(smem));
-    kernel_apply_fwd_kernel<C, KS, TW><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, N, H, W, ks);
+    WCMC_LAUNCH((kernel_apply_fwd_kernel<C, KS, TW>), grid, kKaThreads, smem, stream, logits, l_cs, data, out, stats, N, H, W, ks);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -317,7 +319,7 @@ static int launch_bwd2(const float* logits, int l_cs, const float* data, const f
     dim3 grid((W + TW - 1) / TW, (H + kKaTileH - 1) / kKaTileH, N);
     size_t smem = ka_smem_bytes(ks, TW, DT != WCMC_F32 ? dl_cs / 2 : dl_cs);
     WCMC_FUNC_SMEM((kernel_apply_bwd_kernel<C, DT, KS, TW>), static_cast<int>(smem));
-    kernel_apply_bwd_kernel<C, DT, KS, TW><<<grid, kKaThreads, smem, stream>>>(logits, l_cs, data, out, stats, gout,
+    WCMC_LAUNCH((kernel_apply_bwd_kernel<C, DT, KS, TW>), grid, kKaThreads, smem, stream, logits, l_cs, data, out, stats, gout,
                                                                                dl, dl_cs, N, H, W, ks, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

@@ -16,6 +16,7 @@ constexpr int kTrThreads = 256;
 __global__ void __launch_bounds__(kTrThreads)
 nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW,
                     int dst_cs, int dst_coff, int c_fill, int dtype, const float* __restrict__ scale) {
+    wcmc::pdl_start();
     extern __shared__ float tile[];
     const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     const int n = blockIdx.y, p0 = blockIdx.x * kTrPix;
@@ -40,6 +41,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
 __global__ void __launch_bounds__(kTrThreads)
 nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C, int HW,
                     int src_cs, int src_coff, int accumulate, int dtype, const float* __restrict__ scale) {
+    wcmc::pdl_start();
     extern __shared__ float tile[];
     const float sc = scale != nullptr ? __ldg(scale) : 1.f;
     const int n = blockIdx.y, p0 = blockIdx.x * kTrPix;
@@ -65,6 +67,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
                                     __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgrad,
                                     float* __restrict__ bias_p, int cout, int cin, int ks, int cout_p,
                                     int cin_p, int dtype) {
+    wcmc::pdl_start();
     const int taps = ks * ks;
     const long total = static_cast<long>(cout_p) * taps * cin_p;
     if (bias_p != nullptr && blockIdx.x == 0)
@@ -103,6 +106,7 @@ struct PackBatch {
 //   blockIdx.x >= cout_p : dgrad row ci = w[:][ci][:]   cout runs of taps floats          -> dgrad[ci][taps-1-tap][co]
 // Rows / columns beyond the logical channel counts are written as zeros (the convolutions rely on it).
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackBatch pb, int dtype) {
+    wcmc::pdl_start();
     extern __shared__ float row[];
     const wcmc_pack_desc& L = pb.d[blockIdx.y];
     const int taps = L.ksize * L.ksize;
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackBatch
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long npix, int cs, int coff, int cout,
                  float* __restrict__ db, int dtype, const float* __restrict__ scale) {
+    wcmc::pdl_start();
     extern __shared__ float red[];  // [PL][G*8]
     const int G = (cout + 7) >> 3;
     const int PL = 256 / G;
@@ -189,6 +194,7 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, long npix, int cs, int co
 }
 
 __global__ void zero_f32_kernel(float* p, long n) {
+    wcmc::pdl_start();
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long>(gridDim.x) * blockDim.x)
         p[i] = 0.f;
@@ -211,7 +217,7 @@ extern "C" int wcmc_nchw_f32_to_nhwc(const float* src, void* dst, int dst_dtype,
     size_t smem = static_cast<size_t>(c_fill) * 33 * sizeof(float);
     WCMC_REQUIRE(smem <= 200 * 1024, WCMC_ESHAPE, "nchw_to_nhwc: too many channels (%d)", c_fill);
     if (smem > 48 * 1024) WCMC_FUNC_SMEM(nchw_to_nhwc_kernel, static_cast<int>(smem));
-    nchw_to_nhwc_kernel<<<grid, kTrThreads, smem, stream>>>(src, static_cast<__nv_bfloat16*>(dst), C, HW, dst_cs,
+    WCMC_LAUNCH(nchw_to_nhwc_kernel, grid, kTrThreads, smem, stream, src, static_cast<__nv_bfloat16*>(dst), C, HW, dst_cs,
                                                             dst_coff, c_fill, dst_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -227,7 +233,7 @@ extern "C" int wcmc_nhwc_to_nchw_f32(const void* src, int src_dtype, float* dst,
     size_t smem = static_cast<size_t>(C) * 33 * sizeof(float);
     WCMC_REQUIRE(smem <= 200 * 1024, WCMC_ESHAPE, "nhwc_to_nchw: too many channels (%d)", C);
     if (smem > 48 * 1024) WCMC_FUNC_SMEM(nhwc_to_nchw_kernel, static_cast<int>(smem));
-    nhwc_to_nchw_kernel<<<grid, kTrThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, C, HW,
+    WCMC_LAUNCH(nhwc_to_nchw_kernel, grid, kTrThreads, smem, stream, static_cast<const __nv_bfloat16*>(src), dst, C, HW,
                                                             src_cs, src_coff, accumulate, src_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
@@ -241,7 +247,7 @@ extern "C" int wcmc_pack_weights(const float* w, const float* bias, void* dst_fw
                  "pack_weights: bad shape");
     long total = static_cast<long>(cout_p) * cin_p * ksize * ksize;
     int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
-    pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, bias, static_cast<__nv_bfloat16*>(dst_fwd),
+    WCMC_LAUNCH(pack_weights_kernel, blocks, 256, 0, stream, w, bias, static_cast<__nv_bfloat16*>(dst_fwd),
                                                     static_cast<__nv_bfloat16*>(dst_dgrad), dst_bias, cout, cin,
                                                     ksize, cout_p, cin_p, dtype);
     WCMC_LAUNCH_CHECK();
@@ -269,7 +275,7 @@ extern "C" int wcmc_pack_weights_batch(const wcmc_pack_desc* descs, int n, int d
         const int smem = max_floats * static_cast<int>(sizeof(float));
         if (smem > 48 * 1024) WCMC_FUNC_SMEM(pack_weights_batch_kernel, smem);
         dim3 grid(static_cast<unsigned>(max_rows), m);
-        pack_weights_batch_kernel<<<grid, 256, smem, stream>>>(pb, dtype);
+        WCMC_LAUNCH(pack_weights_batch_kernel, grid, 256, smem, stream, pb, dtype);
         WCMC_LAUNCH_CHECK();
     }
     return WCMC_OK;
@@ -281,14 +287,14 @@ extern "C" int wcmc_bias_grad(const void* dy, int dy_dtype, int npix, int dy_cs,
     WCMC_REQUIRE(npix > 0 && cout > 0 && dy_coff + cout <= dy_cs && cout <= 1024, WCMC_ESHAPE,
                  "bias_grad: bad shape");
     if (!accumulate) {
-        zero_f32_kernel<<<1, 256, 0, stream>>>(db, cout);
+        WCMC_LAUNCH(zero_f32_kernel, 1, 256, 0, stream, db, cout);
         WCMC_LAUNCH_CHECK();
     }
     WCMC_REQUIRE(dy_cs % 8 == 0 && dy_coff % 8 == 0 && dy_coff + ((cout + 7) / 8) * 8 <= dy_cs, WCMC_EALIGN,
                  "bias_grad: channel stride/offset must be multiples of 8 and cover cout rounded up to 8");
     int blocks = std::min(592, (npix + 63) / 64);
     const int G = (cout + 7) / 8;
-    bias_grad_kernel<<<blocks, 256, static_cast<size_t>(256 / G) * G * 8 * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(dy),
+    WCMC_LAUNCH(bias_grad_kernel, blocks, 256, static_cast<size_t>(256 / G) * G * 8 * sizeof(float), stream, static_cast<const __nv_bfloat16*>(dy),
                                                                         npix, dy_cs, dy_coff, cout, db, dy_dtype, scale);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

@@ -25,6 +25,7 @@ constexpr int kRounds = 6;
 
 __global__ void __launch_bounds__(kPermThreads)
 feistel_perm_kernel(int64_t* __restrict__ out, long n, int half_bits, unsigned long long* __restrict__ state, uint32_t salt) {
+    wcmc::pdl_start();
     __shared__ uint32_t keys[kRounds];
     if (threadIdx.x < kRounds) {
         const unsigned long long c = state[0];
@@ -70,7 +71,7 @@ extern "C" int wcmc_random_permutation(int64_t* out, long n, unsigned long long*
     int bits = 2;
     while ((1L << bits) < n) bits += 2;          // even number of bits: two equal Feistel halves; domain < 4 n
     const int grid = static_cast<int>(std::min<long>((n + kPermThreads - 1) / kPermThreads, 4L * wcmc_num_sms()));
-    feistel_perm_kernel<<<grid, kPermThreads, 0, stream>>>(out, n, bits / 2, state, salt);
+    WCMC_LAUNCH(feistel_perm_kernel, grid, kPermThreads, 0, stream, out, n, bits / 2, state, salt);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

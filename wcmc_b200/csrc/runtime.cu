@@ -106,6 +106,9 @@ int wcmc_encode_tmap(CUtensorMap* map, int dtype, const void* base, int rank, co
     return WCMC_OK;
 }
 
+static int g_pdl = 1;
+int wcmc_pdl_enabled() { return g_pdl; }
+
 // Tuning hooks for the micro-benchmarks under tools/ (never used by the product path).
 int wcmc_ka_set_tile(int w);         // kernel_apply.cu
 int wcmc_wgrad_set_uniform(int v);   // conv_wgrad.cu
@@ -123,6 +126,7 @@ extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "conv_pair_min_clk") == 0 && wcmc_conv_set_model(0, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_item_clk") == 0 && wcmc_conv_set_model(1, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_resident") == 0) return wcmc_conv_set_resident(value);
+    if (name != nullptr && strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return WCMC_OK; }
     if (name != nullptr && strcmp(name, "exchange_blocks") == 0 && wcmc_exchange_set_blocks(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_group_pack") == 0) return wcmc_wgrad_group_set(0, value);
     if (name != nullptr && strcmp(name, "wgrad_group") == 0) return wcmc_wgrad_group_set(1, value);

@@ -23,6 +23,7 @@ constexpr int kGlueThreads = 256;
 __global__ void __launch_bounds__(kGlueThreads)
 pbuffer_concat_fwd_kernel(const float* __restrict__ kin, const float* __restrict__ p, float* __restrict__ out, int S,
                           int C, int c0, int cr, int Cin, int HW) {
+    wcmc::pdl_start();
     const int b = blockIdx.y;
     const int i = blockIdx.x * kGlueThreads + threadIdx.x;
     if (i >= HW) return;
@@ -52,6 +53,7 @@ pbuffer_concat_fwd_kernel(const float* __restrict__ kin, const float* __restrict
 __global__ void __launch_bounds__(kGlueThreads)
 pbuffer_concat_bwd_kernel(const float* __restrict__ g, float* __restrict__ dp, int S, int C, int c0, int cr, int Cin,
                           int HW) {
+    wcmc::pdl_start();
     const int bs = blockIdx.y, b = bs / S;
     const int i = blockIdx.x * kGlueThreads + threadIdx.x;
     if (i >= HW) return;
@@ -74,6 +76,7 @@ struct CropView {       // (B, 3, H, W) fp32 with unit x stride, read at [y0 + y
 __global__ void __launch_bounds__(kGlueThreads)
 recombine_kernel(CropView alb, const float* __restrict__ rd, const float* __restrict__ rs, float* __restrict__ rad,
                  int h, int w, long n) {
+    wcmc::pdl_start();
     const long i = blockIdx.x * static_cast<long>(kGlueThreads) + threadIdx.x;
     if (i >= n) return;
     const int x = static_cast<int>(i % w);
@@ -93,6 +96,7 @@ image_losses_kernel(const float* __restrict__ rd, const float* __restrict__ rs, 
                     CropView td, CropView ts, CropView tt, float* __restrict__ sgn_d, float* __restrict__ sgn_s,
                     int h, int w, long n, float eps, float* __restrict__ partial, unsigned* __restrict__ ticket,
                     float* __restrict__ sums) {
+    wcmc::pdl_start();
     float acc[kLossSums] = {0.f, 0.f, 0.f, 0.f};
     const float inv_n = 1.0f / static_cast<float>(n);
     for (long i = blockIdx.x * static_cast<long>(kGlueThreads) + threadIdx.x; i < n;
@@ -154,6 +158,7 @@ image_losses_kernel(const float* __restrict__ rd, const float* __restrict__ rs, 
 __global__ void __launch_bounds__(kGlueThreads)
 absmax_scale_kernel(const float* __restrict__ g, long n, float target, float* __restrict__ partial,
                     unsigned* __restrict__ ticket, float* __restrict__ out) {
+    wcmc::pdl_start();
     float m = 0.f;
     const long n4 = n >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -204,7 +209,7 @@ extern "C" int wcmc_absmax_scale(const float* g, long n, float target, float* ou
     float* partial = static_cast<float*>(workspace);
     unsigned* ticket = reinterpret_cast<unsigned*>(partial + 2 * 148);       // caller zero-fills the workspace ONCE
     const int grid = static_cast<int>(std::min<long>((n / 4 + kGlueThreads - 1) / kGlueThreads + 1, 2L * 148));
-    absmax_scale_kernel<<<grid, kGlueThreads, 0, stream>>>(g, n, target, partial, ticket, out2);
+    WCMC_LAUNCH(absmax_scale_kernel, grid, kGlueThreads, 0, stream, g, n, target, partial, ticket, out2);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -217,7 +222,7 @@ extern "C" int wcmc_pbuffer_concat_fwd(const float* kpcn_in, const float* p, flo
     WCMC_REQUIRE(c0 >= 0 && cr > 0 && c0 + cr <= C, WCMC_ESHAPE, "pbuffer_concat_fwd: channel range [%d, %d) of %d", c0,
                  c0 + cr, C);
     dim3 grid((HW + kGlueThreads - 1) / kGlueThreads, B);
-    pbuffer_concat_fwd_kernel<<<grid, kGlueThreads, 0, stream>>>(kpcn_in, p, out, S, C, c0, cr, Cin, HW);
+    WCMC_LAUNCH(pbuffer_concat_fwd_kernel, grid, kGlueThreads, 0, stream, kpcn_in, p, out, S, C, c0, cr, Cin, HW);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -229,7 +234,7 @@ extern "C" int wcmc_pbuffer_concat_bwd(const float* grad_out, float* dp, int B, 
                  "pbuffer_concat_bwd: bad shape");
     WCMC_REQUIRE(c0 >= 0 && cr > 0 && c0 + cr <= C, WCMC_ESHAPE, "pbuffer_concat_bwd: bad channel range");
     dim3 grid((HW + kGlueThreads - 1) / kGlueThreads, B * S);
-    pbuffer_concat_bwd_kernel<<<grid, kGlueThreads, 0, stream>>>(grad_out, dp, S, C, c0, cr, Cin, HW);
+    WCMC_LAUNCH(pbuffer_concat_bwd_kernel, grid, kGlueThreads, 0, stream, grad_out, dp, S, C, c0, cr, Cin, HW);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -240,8 +245,7 @@ extern "C" int wcmc_recombine(const float* albedo, long a_sb, long a_sc, long a_
     WCMC_REQUIRE(albedo && r_d && r_s && radiance && B > 0 && h > 0 && w > 0, WCMC_ESHAPE, "recombine: bad arguments");
     const long n = static_cast<long>(B) * 3 * h * w;
     CropView a{albedo, a_sb, a_sc, a_sh};
-    recombine_kernel<<<static_cast<unsigned>((n + kGlueThreads - 1) / kGlueThreads), kGlueThreads, 0, stream>>>(
-        a, r_d, r_s, radiance, h, w, n);
+    WCMC_LAUNCH(recombine_kernel, static_cast<unsigned>((n + kGlueThreads - 1) / kGlueThreads), kGlueThreads, 0, stream, a, r_d, r_s, radiance, h, w, n);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -263,7 +267,7 @@ extern "C" int wcmc_image_losses(const float* r_d, const float* r_s, const float
         tt{t_t, strides9[6], strides9[7], strides9[8]};
     float* partial = static_cast<float*>(workspace);
     unsigned* ticket = reinterpret_cast<unsigned*>(partial + 4 * 148 * kLossSums);   // caller zero-initialises it ONCE
-    image_losses_kernel<<<grid, kGlueThreads, 0, stream>>>(r_d, r_s, radiance, td, ts, tt, sgn_d, sgn_s, h, w, n, eps,
+    WCMC_LAUNCH(image_losses_kernel, grid, kGlueThreads, 0, stream, r_d, r_s, radiance, td, ts, tt, sgn_d, sgn_s, h, w, n, eps,
                                                            partial, ticket, sums4);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;

@@ -29,6 +29,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 // forward: w[row, :] = g[row] * v[row, :] / ||v[row, :]||, norm[row] saved for the backward pass
 __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const WnBatch wb) {
+    wcmc::pdl_start();
     __shared__ float red[8];
     const wcmc_wn_desc& L = wb.d[blockIdx.y];
     for (int row = blockIdx.x; row < L.rows; row += gridDim.x) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) weight_norm_fwd_kernel(const WnBatch wb) 
 
 // backward: dg[row] = <dw, v> / ||v||;  dv = (g / ||v||) * (dw - v * <dw, v> / ||v||^2)
 __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const WnBatch wb) {
+    wcmc::pdl_start();
     __shared__ float red[8];
     const wcmc_wn_desc& L = wb.d[blockIdx.y];
     for (int row = blockIdx.x; row < L.rows; row += gridDim.x) {
@@ -85,8 +87,8 @@ extern "C" int wcmc_weight_norm_batch(const wcmc_wn_desc* host_descs, int n, int
             max_rows = std::max(max_rows, L.rows);
         }
         dim3 grid(static_cast<unsigned>(std::min(max_rows, 128)), m);
-        if (backward) weight_norm_bwd_kernel<<<grid, 256, 0, stream>>>(wb);
-        else weight_norm_fwd_kernel<<<grid, 256, 0, stream>>>(wb);
+        if (backward) WCMC_LAUNCH(weight_norm_bwd_kernel, grid, 256, 0, stream, wb);
+        else WCMC_LAUNCH(weight_norm_fwd_kernel, grid, 256, 0, stream, wb);
         WCMC_LAUNCH_CHECK();
     }
     return WCMC_OK;

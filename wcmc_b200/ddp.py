@@ -16,6 +16,9 @@ import torch
 import torch.distributed as dist
 
 
+_DRY = os.environ.get("WCMC_EXCHANGE_DRY", "0") == "1"
+
+
 class PeerExchange:
     """A symmetric fp32 buffer (same size on every rank of `group`, every rank's copy mapped into every other rank's
     address space, one multicast mapping where the switch offers it) plus the in-place all-reduce kernel over it
@@ -47,6 +50,8 @@ class PeerExchange:
         """buf[offset:offset+n] <- scale * sum over ranks, on the current stream (n is rounded up to 4 floats)."""
         n4 = (int(n) + 3) // 4 * 4
         assert offset % 4 == 0 and offset + n4 <= self.capacity
+        if _DRY:       # measurement aid (WCMC_EXCHANGE_DRY=1): everything but the exchange itself, results are wrong
+            return self.buf[offset:offset + n]
         self._lib.grad_exchange(self.buf, self.multicast_ptr, self.peers_dev, self.flag_offset, offset, n4, self.rank,
                                 self.world, channel, scale)
         return self.buf[offset:offset + n]
@@ -106,8 +111,33 @@ class GradAllReduce:
                 raise RuntimeError(f"GradAllReduce(transport={self.transport!r}): symmetric memory unavailable: {err}")
             warnings.warn(f"GradAllReduce: symmetric peer memory unavailable ({err}); using NCCL all_reduce")
             px = None
+        if px is not None and self.transport == "auto" and px.multicast_ptr:
+            self._calibrate(px, n)
         self._px[channel] = px
         return px
+
+    def _calibrate(self, px, n):
+        """transport="auto" on a machine with a multicast mapping: time both variants of the kernel on this message
+        size (a collective: every rank runs the same launches) and keep the faster one -- the in-switch reduction wins
+        with many ranks, plain peer loads with two."""
+        mc, ms = px.multicast_ptr, []
+        for cand in (mc, 0):
+            px.multicast_ptr = cand
+            for _ in range(3):
+                px.all_reduce_(n, 1.0)
+            torch.cuda.synchronize()
+            dist.barrier(self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                px.all_reduce_(n, 1.0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1) / 10)
+        t = torch.tensor(ms, dtype=torch.float32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        px.multicast_ptr = mc if float(t[0]) <= float(t[1]) else 0
+        px.calibration_us = {"multimem": round(float(t[0]) * 1e3, 1), "peer": round(float(t[1]) * 1e3, 1)}
 
     def prepare(self, models):
         """Allocates the exchange buffers for all of `models`' parameters (a collective; needed before a CUDA-graph
@@ -115,13 +145,19 @@ class GradAllReduce:
         params = [p for m in models.values() for p in m.parameters()]
         if not self._use_peer(params):
             return
-        n = sum(p.numel() for p in params) + 4
+        n = self._slots(params) + 4
         for channel in (0, 1) if self.early is not None else (1,):
             self._exchange(channel, n)
 
     def peer_transport(self):
         px = [p for p in self._px.values() if p is not None]
-        return px[0].transport if px else "nccl"
+        return px[-1].transport if px else "nccl"
+
+    def describe(self):
+        """{channel: transport [+ calibration timings]} for logs / bench.py's config."""
+        return {("early" if c == 0 else "late"): ("nccl" if p is None else
+                                                  dict(transport=p.transport, **getattr(p, "calibration_us", {})))
+                for c, p in sorted(self._px.items())}
 
     def _flatten(self, grads):
         return torch.cat([g.reshape(-1) for g in grads])
@@ -132,8 +168,7 @@ class GradAllReduce:
         grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None]
         if not grads:
             return
-        n = sum(g.numel() for g in grads)
-        px = self._exchange(0, n) if self._use_peer(grads) else None
+        px = self._exchange(0, self._slots(grads)) if self._use_peer(grads) else None
         if px is None:
             flat = self._flatten(grads)
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -143,9 +178,27 @@ class GradAllReduce:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
-            torch.cat([g.reshape(-1) for g in grads], out=px.buf[:n])
-            flat = px.all_reduce_(n, 1.0 / self.world, channel=0)
-        self._early.append((None, flat, grads))
+            views, n = self._gather(px, grads)
+            px.all_reduce_(n, 1.0 / self.world, channel=0)
+        self._early.append((None, views, [p for m in models.values() for p in m.parameters() if p.grad is not None]))
+
+    @staticmethod
+    def _gather(px, tensors):
+        """The gradients (and the flag) into the symmetric buffer, every tensor on a 16-byte boundary -> (views, n).
+        Nothing is copied when they already live there (p.grad still holds last step's views and the backward pass
+        accumulated in place: `zero_grad(set_to_none=False)`)."""
+        views, at = [], 0
+        for t in tensors:
+            k = t.numel()
+            views.append(px.buf[at:at + k].view_as(t))
+            at += (k + 3) // 4 * 4
+        if any(v.data_ptr() != t.data_ptr() for v, t in zip(views, tensors)):
+            torch._foreach_copy_(views, list(tensors))
+        return views, at
+
+    @staticmethod
+    def _slots(tensors):
+        return sum((t.numel() + 3) // 4 * 4 for t in tensors)
 
     def drain(self):
         """Waits for and forgets reductions started by `early` whose step never reached `__call__` (gradient-only
@@ -157,11 +210,18 @@ class GradAllReduce:
             else:
                 torch.cuda.current_stream().wait_stream(self._side)
 
-    def _finish(self, flat, grads, scaled=False):
-        if not scaled:
-            flat.div_(self.world)
+    def _finish(self, flat, grads):
+        flat.div_(self.world)
         torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
         return flat.numel() * flat.element_size()
+
+    @staticmethod
+    def _adopt(views, params):
+        """Peer transport: the averaged gradients stay where the exchange left them -- every `p.grad` becomes a view
+        of the symmetric buffer (no copy back; clip + Adam read them there, the next backward pass replaces them)."""
+        for p, v in zip(params, views):
+            p.grad = v
+        return sum(v.numel() for v in views) * 4
 
     def __call__(self, models, ok=None):
         """Reduces what `early` has not taken yet and waits for the early part.  `ok` (optional 0-d bool tensor: this
@@ -170,33 +230,35 @@ class GradAllReduce:
         if self.world == 1:
             return ok
         early, self._early = self._early, []
-        done = {id(g) for _, _, gs in early for g in gs}
-        grads = [p.grad for m in models.values() for p in m.parameters() if p.grad is not None and id(p.grad) not in done]
+        done = {id(g) for _, _, gs in early for g in gs}      # parameters (peer transport) or gradients (nccl)
+        done |= {id(p) for m in models.values() for p in m.parameters() if p.grad is not None and id(p.grad) in done}
+        params = [p for m in models.values() for p in m.parameters() if p.grad is not None and id(p) not in done]
+        grads = [p.grad for p in params]
         nbytes = 0
         all_ok = None
         if grads or ok is not None:
-            parts = [g.reshape(-1) for g in grads]
-            if ok is not None:
-                parts.append((~ok).to(parts[0].dtype if parts else torch.float32).reshape(1))
-            n = sum(t.numel() for t in parts)
-            px = self._exchange(1, n) if self._use_peer(parts) else None
+            flag = [] if ok is None else [(~ok).to(torch.float32).reshape(1)]
+            px = self._exchange(1, self._slots(grads + flag)) if self._use_peer(grads + flag) else None
             if px is None:
-                flat = torch.cat(parts)
+                flat = torch.cat([g.reshape(-1) for g in grads] + flag)
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                if ok is not None:
+                    all_ok = flat[-1] == 0
+                    flat = flat[:-1]
+                if grads:
+                    nbytes += self._finish(flat, grads)
             else:
-                torch.cat(parts, out=px.buf[:n])
-                flat = px.all_reduce_(n, 1.0 / self.world, channel=1)
-            if ok is not None:
-                all_ok = flat[-1] == 0
-                flat = flat[:-1]
-            if grads:
-                nbytes += self._finish(flat, grads, scaled=px is not None)
+                views, n = self._gather(px, grads + flag)
+                px.all_reduce_(n, 1.0 / self.world, channel=1)
+                if ok is not None:
+                    all_ok = views.pop()[0] == 0
+                nbytes += self._adopt(views, params)
         for work, flat_e, grads_e in early:
             if work is not None:
                 work.wait()                       # the current stream waits for the collective
             else:
                 torch.cuda.current_stream().wait_stream(self._side)
-            nbytes += self._finish(flat_e, grads_e, scaled=work is None)
+            nbytes += self._adopt(flat_e, grads_e) if work is None else self._finish(flat_e, grads_e)
         self.bytes_last = nbytes
         return all_ok
 
