@@ -414,9 +414,9 @@ def main():
 
     # The synthetic batch repeats, so a long run over-fits it and, at the reference's lr 1e-4, eventually diverges -- in
     # fp32 as well (profiles/r02_long_run_800_steps.txt: backend and fp32 oracle side by side).  A run of many steps
-    # therefore puts the weights / Adam moments of the end of the warm-up back every RESET steps (three _foreach_copy_ launches inside
+    # therefore puts the weights / Adam moments of the end of the warm-up back every RESET steps (eager per-kernel pass included) (three _foreach_copy_ launches inside
     # the timed region: extra work, nothing skipped); runs of <= RESET steps never see it.
-    RESET = 200
+    RESET = 100
     state = {"n": 0, "live": None, "init": None}
 
     def snapshot():
@@ -425,12 +425,25 @@ def main():
             for st in o.state.values():
                 live += [st["exp_avg"], st["exp_avg_sq"]]
         state["live"], state["init"] = live, [t.detach().clone() for t in live]
+        steps = [st["step"] for o in optims.values() for st in o.state.values()]
+        state["steps"], state["t0"] = steps, (float(steps[0]) if steps else 0.0)
 
-    def step(batch):
+    def maybe_reset():
         state["n"] += 1
         if state["n"] % RESET == 0 and state["init"] is not None:
             with torch.no_grad():
                 torch._foreach_copy_(state["live"], state["init"])
+                # ... and Adam's step count with them (bias correction with a later count on early moments would
+                # take several times larger steps -- enough to overflow the 16-bit activations now and then)
+                fa = itf._fused()
+                if fa is not None:
+                    fa.set_step(state["t0"])
+                else:
+                    for t in state["steps"]:
+                        t.fill_(state["t0"])
+
+    def step(batch):
+        maybe_reset()
         if use_graph:
             graphed(batch)
         else:
@@ -442,12 +455,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, tail=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if tail is not None:
+            tail()          # whatever the loop still owes (the last step's deferred flag / loss read-back)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -461,7 +476,10 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms_step = timed(lambda: step(dev), args.steps)
+    # device-resident steps: the batch IS the graph's static input buffers (no staging copy); the finite flag of
+    # step i is looked at after step i+1 has been enqueued (GraphedTrainStep(check="deferred")), the last one in `tail`
+    resident = graphed.static if use_graph else dev
+    ms_step = timed(lambda: step(resident), args.steps, tail=(graphed.finish if use_graph else None))
     clk = clocks.stop() if rank == 0 else None
     window_s = ms_step * args.steps * 1e-3
 
@@ -469,6 +487,7 @@ def main():
     # kernels are the same ones the graph replays; this pass launches them eagerly so that each launch
     # can be bracketed by events.
     def eager_step():
+        maybe_reset()
         itf.preprocess(dev)
         itf.train_batch(dev)
     # one stream for this pass: with the diffuse / specular halves on two streams (wcmc_b200/streams.py) the event
@@ -494,14 +513,39 @@ def main():
 
     pf = DevicePrefetcher(host_batches())
 
+    # ... and every step's loss is read back: the running total goes to pinned host memory right behind the step and
+    # is looked at one step later (the host stays one step ahead of the GPU, as in the device-resident loop)
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_seen = {"n": 0, "pending": None, "last": 0.0}
+
+    def read_pending():
+        pend, loss_seen["pending"] = loss_seen["pending"], None
+        if pend is not None:
+            pend[0].synchronize()
+            loss_seen["last"] = float(loss_host[pend[1]])
+
     def e2e_step():
         batch = next(pf)
         step(batch)
         pf.release()
-        return float(itf.m_losses["m_l_total"])  # device -> host read of the step's loss
+        slot = loss_seen["n"] & 1
+        loss_seen["n"] += 1
+        loss_host[slot].copy_(itf.m_losses["m_l_total"].reshape(1), non_blocking=True)   # device -> host, 4 bytes
+        ev = torch.cuda.Event()
+        ev.record()
+        pend, loss_seen["pending"] = loss_seen["pending"], (ev, slot)
+        if pend is not None:
+            pend[0].synchronize()
+            loss_seen["last"] = float(loss_host[pend[1]])
+
+    def e2e_tail():
+        read_pending()
+        if use_graph:
+            graphed.finish()
 
     e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps, tail=e2e_tail)
+    assert loss_seen["last"] == loss_seen["last"], "non-finite running loss"
 
     if rank != 0:
         _leave(world, graphed)

@@ -734,6 +734,52 @@ def test_graphed_step_matches_eager(backend, oracle):
                 assert rel(pg, pe) < 5e-3
 
 
+def test_graphed_step_survives_an_eager_backward_between_replays(backend):
+    """An eager backward pass between two replays re-points every `p.grad`; if the optimiser's descriptors are then
+    re-read (`load_state_dict`, an lr change: FusedClipAdam.refresh) they must still name the gradient tensors the
+    captured kernels write.  Found with bench.py's long-run reset; twin runs (with / without the interleaved eager
+    pass, whose own update is undone) must stay bit-identical."""
+    from wcmc_b200.engine import GraphedTrainStep
+
+    def make():
+        torch.manual_seed(0)
+        models = _build(backend.KPCN, backend.PathNet, 34, False, 3)
+        for m in models.values():
+            m.cuda()
+        optims = {"optim_" + k: torch.optim.Adam(m.parameters(), lr=1e-4) for k, m in models.items()}
+        lf = {"l_diffuse": torch.nn.L1Loss(), "l_specular": torch.nn.L1Loss(), "l_recon": torch.nn.L1Loss(),
+              "l_test": backend.losses.RelativeMSE()}
+        itf = backend.itf.KPCNInterface(models, optims, lf, types.SimpleNamespace(model_name="t"), use_llpm_buf=False,
+                                        manif_learn=False, train_branches=True)
+        itf.to_train_mode()
+        return itf, models, optims
+
+    batch = to_cuda(make_batch(batch=2, spp=2, size=48, seed=32, paths=False))
+    other = to_cuda(make_batch(batch=2, spp=2, size=48, seed=33, paths=False))
+    runs = []
+    for interleave in (False, True):
+        itf, models, optims = make()
+        step = GraphedTrainStep(itf, batch)
+        step(batch)
+        if interleave:
+            # what an eager train_batch between two replays does, minus the update itself: zero_grad(set_to_none),
+            # a backward pass on another batch, and the fused optimiser re-reading its view of the model (this
+            # rewrites, in place, the pinned descriptors the captured graph copies in on every replay)
+            for p in step._params:
+                p.grad = None
+            out = models["dncnn"](other)
+            (out["radiance"].mean()).backward()
+            assert step._params[0].grad is not step._grads[0]
+            assert itf._fused() is step.fused
+            step.fused.refresh()
+            assert step.fused._key is not step._adam_key
+        step(batch)
+        step(batch)
+        runs.append(torch.cat([p.detach().flatten() for m in models.values() for p in m.parameters()]).clone())
+        step.release()
+    assert torch.equal(runs[0], runs[1])
+
+
 def test_full_frame_denoise_vs_oracle_and_tiling(backend, oracle):
     """wcmc_b200.inference.denoise_frame (configs[3] at a small frame): equals the oracle KPCN on the
     replicate-padded frame, and -- the property that justifies not tiling -- an interior 92x92 block

@@ -76,7 +76,10 @@ int wcmc_func_smem(const void* kernel, int bytes);
 //   * a kernel that allocates tensor memory triggers only AFTER the allocation (otherwise an early dependent could
 //     take the columns a late CTA of this grid still needs, while waiting for this grid: deadlock).
 // A kernel launched without the attribute, or after a kernel that never triggers (torch's), behaves as usual.
-// wcmc_tuning_set("pdl", 0) turns the attribute off.
+// OFF by default (wcmc_tuning_set("pdl", 1) turns the attribute on): in the two-stream step an early-resident
+// dependent holds the shared memory of its SM while it waits, which keeps the OTHER stream's ready kernel off that
+// SM -- measured 7.51 -> 7.72 ms per step (profiles/r02_pdl_ab.txt).  Without the attribute the two instructions
+// are no-ops.
 int wcmc_pdl_enabled();
 #ifdef __CUDACC__
 namespace wcmc {

@@ -26,6 +26,8 @@
 //
 // PAIR = true: the kernel runs as clusters of two CTAs on tcgen05 cta_group::2 (M = 256) -- see decode_item below and
 // DESIGN.md section 5 for why (the shared-memory operand feed, not the tensor pipe, bounds the single-CTA kernel).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace wcmc {
@@ -229,6 +231,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // PDL: barriers, tensor memory and descriptors are set up in the shadow of the previous kernel's tail; the
+    // dependents may be scheduled now that this CTA owns its TMEM columns; nothing below runs before the previous
+    // grid has completed
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int taps = p.ksize * p.ksize;
     const int region_w = 8 * p.mt;
@@ -625,6 +632,10 @@ static int g_conv_pair = 1;
 int wcmc_conv_set_pair(int v) { g_conv_pair = v ? 1 : 0; return 0; }
 static int g_conv_row_stages = 1;
 int wcmc_conv_set_row_stages(int v) { g_conv_row_stages = v ? 1 : 0; return 0; }
+static int g_conv_share = 1;       // wcmc_tuning_set("conv_share", n): every launch plans for 1/n of the SMs
+static int g_conv_share_ks = 7;
+int wcmc_conv_set_share(int v) { if (v < 1 || v > 8) return 1; g_conv_share = v; return 0; }
+int wcmc_conv_set_share_ks(int v) { g_conv_share_ks = v & 7; return 0; }
 static int g_conv_resident = 1;    // wcmc_tuning_set("conv_resident", 0 | 1): weights resident in shared memory when they fit
 int wcmc_conv_set_resident(int v) { g_conv_resident = v ? 1 : 0; return 0; }
 // measurement knobs of the launch-shape model (defaults = the values measured in round 1):
@@ -652,18 +663,19 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
         cfg.blockDim = dim3(kConvThreads);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = wcmc_pdl_enabled() ? 2 : 1;
         WCMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<PAIR, TPS, KA>, tmx, tmw, p));
         return WCMC_OK;
     }
-    conv_igemm_kernel<PAIR, TPS, KA><<<grid, kConvThreads, smem_bytes, stream>>>(tmx, tmw, p);
-    WCMC_LAUNCH_CHECK();
+    WCMC_LAUNCH((conv_igemm_kernel<PAIR, TPS, KA>), grid, kConvThreads, smem_bytes, stream, tmx, tmw, p);
     return WCMC_OK;
 }
 
@@ -703,7 +715,13 @@ static int conv2d_impl(const void* x, int x_dtype, int N, int H, int W, int x_cs
     if ((flags >> 8) & 0xFF) p.nt = ((flags >> 8) & 0xFF);   // test override: n tile
     WCMC_REQUIRE(p.nt % 16 == 0 && p.nt >= 16 && p.nt <= 128, WCMC_ESHAPE, "conv2d: bad n tile %d", p.nt);
     p.n_tiles = (cout_p + p.nt - 1) / p.nt;
-    const int sms = wcmc_num_sms();
+    // SMs this launch plans for: all of them, or (flags bits 24..27 = share, or the "conv_share" knob) 1/share of them
+    // when the caller runs `share` such launches side by side on different streams (the two branches / the two
+    // path-embedding networks of a step): two half-machine launches overlap each other's prologue, tail and partial
+    // last wave instead of serialising them.
+    const bool share_k = (g_conv_share_ks >> (ksize >> 1)) & 1;      // knob: which kernel sizes share (bit 0: 1x1, 1: 3x3, 2: 5x5)
+    const int share_req = ((flags >> 24) & 15) > 0 ? ((flags >> 24) & 15) : (share_k ? g_conv_share : 1);
+    const int sms = share_req > 1 ? std::max(2, (wcmc_num_sms() / share_req) & ~1) : wcmc_num_sms();
     // Launch shape.  Single CTA: two M tiles per region (B streamed once for 256 pixels) unless that leaves SMs
     // idle.  CTA pair (measured, profiles/r01e_pair_check.txt): worth it for the MMA-bound layers that fill the
     // machine; the 64- and 128-channel 3x3 U-Net layers are epilogue-bound and lose ~2 us to the cluster launch.  With the B operand already halved per CTA, one M

@@ -87,6 +87,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
+    pdl_wait();
 
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_planes * kWgAPlane +
                                                     p.b_planes * p.halo_w * p.halo_h * 128);
@@ -199,6 +201,7 @@ struct ReduceBatch {
 constexpr int kRedCi = 32;
 
 __global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceBatch rb) {
+    pdl_start();
     __shared__ float tile[kRedCi * 25 + 8];
     const wcmc_wgrad_reduce_desc& L = rb.d[blockIdx.y];
     const float sc = L.scale != nullptr ? __ldg(L.scale) : 1.f;
@@ -350,7 +353,7 @@ extern "C" int wcmc_conv2d_wgrad_partial(const void* x, int x_dtype, int N, int 
     }
     WCMC_FUNC_SMEM(conv_wgrad_kernel, kWgSmem);
     const int grid = p.m_tiles * p.ci_tiles * ((p.tap_groups - 1) * p.nsplit_a + p.nsplit_b);
-    conv_wgrad_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(tmdy, tmx, p);
+    WCMC_LAUNCH(conv_wgrad_kernel, grid, kWgThreads, kWgSmem, stream, tmdy, tmx, p);
     WCMC_LAUNCH_CHECK();
     desc_out->ws = p.ws;
     desc_out->dw = dw;
@@ -384,7 +387,7 @@ extern "C" int wcmc_wgrad_reduce_batch(const wcmc_wgrad_reduce_desc* host_descs,
             max_items = std::max(max_items, d.cout * ((d.cin + kRedCi - 1) / kRedCi));
         }
         dim3 grid(std::min(max_items, 148 * 4), m);
-        wgrad_reduce_batch_kernel<<<grid, 256, 0, stream>>>(rb);
+        WCMC_LAUNCH(wgrad_reduce_batch_kernel, grid, 256, 0, stream, rb);
         WCMC_LAUNCH_CHECK();
     }
     return WCMC_OK;

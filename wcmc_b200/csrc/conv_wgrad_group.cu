@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(kGgThreads, 1) conv_wgrad_group_kernel(const _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -587,7 +589,7 @@ extern "C" int wcmc_conv2d_wgrad_group(const wcmc_wgrad_layer* layers, int n, in
         }
         const int smem_bytes = smem_need + 1024;
         WCMC_FUNC_SMEM(conv_wgrad_group_kernel, kGgSmemBudget + 1024);
-        conv_wgrad_group_kernel<<<cta, kGgThreads, smem_bytes, stream>>>(P);
+        WCMC_LAUNCH(conv_wgrad_group_kernel, cta, kGgThreads, smem_bytes, stream, P);
         WCMC_LAUNCH_CHECK();
     }
     return wcmc_wgrad_reduce_batch(red.data(), n, stream_);

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kMlpThreads, 3)
 pathnet_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmp, const __grid_constant__ CUtensorMap tmx16,
                          const __grid_constant__ CUtensorMap tmh1, const __grid_constant__ CUtensorMap tmh2,
                          const __grid_constant__ CUtensorMap tmemb, const EmbedParams p) {
+    pdl_wait();                // the prologue below reads packed weights / issues TMA loads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -123,6 +124,7 @@ pathnet_embed_fwd_kernel(const __grid_constant__ CUtensorMap tmp, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
     const uint32_t tmem = *tmem_ptr;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const uint32_t idesc = make_idesc_f16(128, 64, 0, 0, p.dtype, p.dtype);
@@ -286,6 +288,7 @@ constexpr int kFinSmem = 4 * kTileBytes + 2 * 16384 + 2 * 4096 + 160 * 4 + 64 + 
 __global__ void __launch_bounds__(kMlpThreads, 2)
 pathnet_final_fwd_kernel(const __grid_constant__ CUtensorMap tme, const __grid_constant__ CUtensorMap tmpr,
                          const __grid_constant__ CUtensorMap tmh, const FinalParams p) {
+    pdl_wait();                // the prologue below reads packed weights / issues TMA loads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -322,6 +325,7 @@ pathnet_final_fwd_kernel(const __grid_constant__ CUtensorMap tme, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
     const uint32_t tmem = *tmem_ptr;
     const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const uint32_t idesc1 = make_idesc_f16(128, 128, 0, 0, p.dtype, p.dtype);
@@ -467,8 +471,7 @@ extern "C" int wcmc_pathnet_embed_fwd(const float* paths, int B, int S, int Cin,
     const int smem_bytes = emb_smem_bytes(Cin);
     WCMC_FUNC_SMEM(pathnet_embed_fwd_kernel, emb_smem_bytes(64));
     dim3 grid((HW + 127) / 128, B);
-    pathnet_embed_fwd_kernel<<<grid, kMlpThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-        tmp, tmx16, tmh1, tmh2, tmemb, p);
+    WCMC_LAUNCH(pathnet_embed_fwd_kernel, grid, kMlpThreads, smem_bytes, static_cast<cudaStream_t>(stream), tmp, tmx16, tmh1, tmh2, tmemb, p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -498,7 +501,7 @@ extern "C" int wcmc_pathnet_final_fwd(const void* emb, int emb_cs, int emb_coff,
     if (h && (rc = act_tmap(&tmh, h, 128, HW, static_cast<long>(B) * S))) return rc;
     WCMC_FUNC_SMEM(pathnet_final_fwd_kernel, kFinSmem);
     dim3 grid((HW + 127) / 128, B);
-    pathnet_final_fwd_kernel<<<grid, kMlpThreads, kFinSmem, static_cast<cudaStream_t>(stream)>>>(tme, tmpr, tmh, p);
+    WCMC_LAUNCH(pathnet_final_fwd_kernel, grid, kMlpThreads, kFinSmem, static_cast<cudaStream_t>(stream), tme, tmpr, tmh, p);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

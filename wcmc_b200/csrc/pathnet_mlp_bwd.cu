@@ -97,6 +97,7 @@ template <int OP>   // OP = outc_p (16 or 32): sizes the per-thread dz2 / db2 re
 __global__ void __launch_bounds__(kBwdThreads, 1)
 pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_constant__ CUtensorMap tme,
                          const __grid_constant__ CUtensorMap tmpr, const FinalBwdParams p) {
+    pdl_wait();                // the prologue below reads packed weights / issues TMA loads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* w1t = smem;                 // plane c: cout in [64c, 64c+64)
@@ -138,6 +139,7 @@ pathnet_final_bwd_kernel(const __grid_constant__ CUtensorMap tmh, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
     const uint32_t tmem = *tmem_ptr;
     // TMEM columns: [0,128) / [128,256) data gradients of group 0 / 1; [256,384) dW1; [384,448) db1 (ones block);
     // [448,512) dW2^T
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_constant__ CUtensorMap tmem_map,
                          const __grid_constant__ CUtensorMap tmh2, const __grid_constant__ CUtensorMap tmh1,
                          const __grid_constant__ CUtensorMap tmx, const EmbedBwdParams p) {
+    pdl_wait();                // the prologue below reads packed weights / issues TMA loads
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* w3t = smem;                 // [64 rows][64] = 8 KB
@@ -478,6 +481,7 @@ pathnet_embed_bwd_kernel(const __grid_constant__ CUtensorMap tmde, const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_launch_dependents();   // after the TMEM allocation (common.cuh: PDL rules)
     const uint32_t tmem = *tmem_ptr;
     // TMEM columns: [0,64) / [64,128) data gradients of group 0 / 1; then per layer L = 3, 2, 1 a 128-column block
     // [128 + 128 i, +64) dW_L (lanes 0..63 = cout), [+64, +128) ones block (column 0 = db_L)
@@ -716,6 +720,7 @@ struct SlabReduceParams {
 // combine through shared memory.  (The first version -- 32 CTAs, one thread per element walking all 148 slabs --
 // took 196 us per call: 8 k threads cannot cover 12 MB of latency-bound strided reads.)
 __global__ void __launch_bounds__(256) slab_reduce_kernel(const SlabReduceParams p) {
+    pdl_start();
     __shared__ float red[4][64];
     const float sc = p.scale != nullptr ? __ldg(p.scale) : 1.f;
     const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -801,8 +806,8 @@ extern "C" int wcmc_pathnet_final_bwd(const float* g, const float* out, const fl
     if ((rc = bwd_act_tmap(&tmpr, prop, prop_cs, HW, B))) return rc;
     WCMC_FUNC_SMEM(pathnet_final_bwd_kernel<16>, kFinSmem);
     WCMC_FUNC_SMEM(pathnet_final_bwd_kernel<32>, kFinSmem);
-    if (outc_p == 16) pathnet_final_bwd_kernel<16><<<grid, kBwdThreads, kFinSmem, stream>>>(tmh, tme, tmpr, p);
-    else pathnet_final_bwd_kernel<32><<<grid, kBwdThreads, kFinSmem, stream>>>(tmh, tme, tmpr, p);
+    if (outc_p == 16) WCMC_LAUNCH((pathnet_final_bwd_kernel<16>), grid, kBwdThreads, kFinSmem, stream, tmh, tme, tmpr, p);
+    else WCMC_LAUNCH((pathnet_final_bwd_kernel<32>), grid, kBwdThreads, kFinSmem, stream, tmh, tme, tmpr, p);
     WCMC_LAUNCH_CHECK();
     SlabReduceParams r;
     r.partial = p.partial; r.nslabs = grid; r.slab = kFinSlab; r.scale = inv_scale; r.nseg = 4;
@@ -810,7 +815,7 @@ extern "C" int wcmc_pathnet_final_bwd(const float* g, const float* out, const fl
     r.seg[1] = SlabSeg{db1, 128 * 128, 1, 128, 128};
     r.seg[2] = SlabSeg{dw2, 128 * 128 + 128, outc, 128, 128};
     r.seg[3] = SlabSeg{db2, 128 * 128 + 128 + 32 * 128, 1, 32, outc};
-    slab_reduce_kernel<<<296, 256, 0, stream>>>(r);
+    WCMC_LAUNCH(slab_reduce_kernel, 296, 256, 0, stream, r);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }
@@ -846,7 +851,7 @@ extern "C" int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, cons
     if ((rc = bwd_act_tmap(&tmh1, h1, 64, HW, images))) return rc;
     if ((rc = bwd_act_tmap(&tmx, x16, 64, HW, images))) return rc;
     WCMC_FUNC_SMEM(pathnet_embed_bwd_kernel, kEmbSmem);
-    pathnet_embed_bwd_kernel<<<grid, kBwdThreads, kEmbSmem, stream>>>(tmde, tmem_map, tmh2, tmh1, tmx, p);
+    WCMC_LAUNCH(pathnet_embed_bwd_kernel, grid, kBwdThreads, kEmbSmem, stream, tmde, tmem_map, tmh2, tmh1, tmx, p);
     WCMC_LAUNCH_CHECK();
     SlabReduceParams r;
     r.partial = p.partial; r.nslabs = grid; r.slab = kEmbSlab; r.scale = inv_scale; r.nseg = 6;
@@ -857,7 +862,7 @@ extern "C" int wcmc_pathnet_embed_bwd(const void* d_emb, const void* d_red, cons
     r.seg[3] = SlabSeg{db2, blk + 64 * 64, 1, 64, 64};
     r.seg[4] = SlabSeg{dw1, 2 * blk, 64, 64, cin};
     r.seg[5] = SlabSeg{db1, 2 * blk + 64 * 64, 1, 64, 64};
-    slab_reduce_kernel<<<296, 256, 0, stream>>>(r);
+    WCMC_LAUNCH(slab_reduce_kernel, 296, 256, 0, stream, r);
     WCMC_LAUNCH_CHECK();
     return WCMC_OK;
 }

@@ -106,7 +106,7 @@ int wcmc_encode_tmap(CUtensorMap* map, int dtype, const void* base, int rank, co
     return WCMC_OK;
 }
 
-static int g_pdl = 1;
+static int g_pdl = 0;   // measured: slower inside the two-stream step (profiles/r02_pdl_ab.txt); wcmc_tuning_set("pdl", 1) enables it
 int wcmc_pdl_enabled() { return g_pdl; }
 
 // Tuning hooks for the micro-benchmarks under tools/ (never used by the product path).
@@ -118,6 +118,8 @@ int wcmc_conv_set_model(int which, int v);  // conv_igemm.cu
 int wcmc_wgrad_group_set(int which, int v); // conv_wgrad_group.cu
 int wcmc_conv_set_resident(int v);          // conv_igemm.cu
 int wcmc_exchange_set_blocks(int v);        // grad_exchange.cu
+int wcmc_conv_set_share(int v);             // conv_igemm.cu
+int wcmc_conv_set_share_ks(int v);          // conv_igemm.cu
 extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "ka_tile_w") == 0 && wcmc_ka_set_tile(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_uniform") == 0) return wcmc_wgrad_set_uniform(value);
@@ -126,6 +128,8 @@ extern "C" int wcmc_tuning_set(const char* name, int value) {
     if (name != nullptr && strcmp(name, "conv_pair_min_clk") == 0 && wcmc_conv_set_model(0, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_item_clk") == 0 && wcmc_conv_set_model(1, value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "conv_resident") == 0) return wcmc_conv_set_resident(value);
+    if (name != nullptr && strcmp(name, "conv_share") == 0 && wcmc_conv_set_share(value) == 0) return WCMC_OK;
+    if (name != nullptr && strcmp(name, "conv_share_ks") == 0) return wcmc_conv_set_share_ks(value);
     if (name != nullptr && strcmp(name, "pdl") == 0) { g_pdl = value ? 1 : 0; return WCMC_OK; }
     if (name != nullptr && strcmp(name, "exchange_blocks") == 0 && wcmc_exchange_set_blocks(value) == 0) return WCMC_OK;
     if (name != nullptr && strcmp(name, "wgrad_group_pack") == 0) return wcmc_wgrad_group_set(0, value);

@@ -332,7 +332,13 @@ class KPCNInterface(BaseInterface):
         for k in loss_dict:
             if "m_" + k not in self.m_losses:
                 self.m_losses["m_" + k] = torch.tensor(0.0, device=loss_dict[k].device)
-            self.m_losses["m_" + k] += loss_dict[k]
+        acc = [self.m_losses["m_" + k] for k in loss_dict]
+        if acc and all(a.is_cuda for a in acc):      # one launch for the six running sums
+            with torch.no_grad():
+                torch._foreach_add_(acc, [loss_dict[k].detach().reshape(a.shape) for k, a in zip(loss_dict, acc)])
+        else:
+            for k in loss_dict:
+                self.m_losses["m_" + k] += loss_dict[k]
 
     def _logging(self, loss_dict):
         self._assert_finite(loss_dict)

@@ -3,9 +3,9 @@
 One step of `KPCNInterface.train_batch` launches ~400 kernels from Python; at B=8 the GPU work is
 ~12 ms and the host needs longer than that to enqueue it.  The shapes of a training run are fixed
 (batch, spp bucket, patch size), so the forward + two backward passes are captured once into a CUDA
-graph and replayed: per step the host copies the batch into the graph's static input buffers,
-replays, checks the finite flags (the step's single host sync, as in support/interfaces.py) and
-runs gradient all-reduce / clipping / Adam eagerly.
+graph and replayed: per step the host copies the batch into the graph's static input buffers (one launch; nothing
+when the batch already lives there) and replays -- gradient exchange, clipping and Adam are part of the graph, and
+the finite flag of a step is looked at one replay later, so the GPU never waits for the host (see GraphedTrainStep).
 
 Semantics are those of `KPCNInterface.train_batch` (/root/reference/support/interfaces.py:122-192); the
 every-1000-iterations PNG dump of the p-buffers is skipped.  Pairing permutations of the path-disentangling
@@ -23,8 +23,22 @@ from . import ddp as _ddp
 
 
 class GraphedTrainStep:
-    def __init__(self, itf, example_batch, warmup=3):
+    """check="deferred" (default): the finite flag of replay i is copied to pinned host memory asynchronously and looked
+    at after replay i+1 has been enqueued, so the GPU never waits for the host between steps (the per-step sync +
+    Python + graph launch cost ~0.25 ms of idle GPU per 7.4 ms step).  A non-finite step still skips its own update ON
+    THE DEVICE (the flag predicates clip + Adam inside the graph); the RuntimeError of
+    /root/reference/support/interfaces.py:255-257 surfaces one call later, or in `finish()` / `release()`.
+    check="immediate" keeps the reference's timing of the error (one host sync per step).
+
+    A batch whose tensors ARE `self.static[...]` is used in place (no staging copy)."""
+
+    def __init__(self, itf, example_batch, warmup=3, check="deferred"):
+        assert check in ("deferred", "immediate")
         self.itf = itf
+        self.check = check
+        self._pending = None       # (event, slot, step index) of the replay whose flag has not been looked at yet
+        self._flag_host = [torch.ones(1, dtype=torch.bool).pin_memory() for _ in range(2)]
+        self._n = 0
         lm = itf.loss_funcs.get("l_manif")
         self.stage = None
         if itf.manif_learn and getattr(lm, "rng", "cpu") != "device":
@@ -95,30 +109,77 @@ class GraphedTrainStep:
                     self.flags = ok
                 self.ok_i32 = ok.to(torch.int32).reshape(1)
                 self.fused.step(clip=1.0, ok_flag=self.ok_i32, count=False)
+        # the gradient tensors the captured kernels write and the captured Adam reads: an eager backward pass between
+        # replays (validation with gradients, a per-kernel timing pass) re-points p.grad; __call__ puts these back so
+        # that anything that re-reads the optimiser's view of the model (FusedClipAdam.refresh) sees the graph's own
+        self._params = [p for m in itf.models.values() for p in m.parameters()]
+        self._grads = [p.grad for p in self._params]
+        self._adam_key = self.fused._key if self.fused is not None else None
+
+    def _look(self, pending):
+        ev, slot, n = pending
+        ev.synchronize()
+        if not bool(self._flag_host[slot]):
+            raise RuntimeError("Infinite loss at train time. (graph replay %d; its update was skipped on the device)" % n)
+
+    def finish(self):
+        """Looks at the flag of the last replay (deferred checking keeps one outstanding)."""
+        pending, self._pending = self._pending, None
+        if pending is not None:
+            self._look(pending)
 
     def release(self):
         """Drops the captured graph and its static buffers (call before tearing a process group down: the graph
-        holds the NCCL kernels of the in-graph gradient all-reduce)."""
+        holds the kernels of the in-graph gradient exchange)."""
         torch.cuda.synchronize()
-        if self.graph is not None:
-            self.graph.reset()
-        self.graph = None
-        self.loss = self.flags = None
+        try:
+            self.finish()
+        finally:
+            if self.graph is not None:
+                self.graph.reset()
+            self.graph = None
+            self.loss = self.flags = None
+            self._params = self._grads = []
 
     def __call__(self, batch):
         itf = self.itf
         itf.preprocess(batch)
+        dst, src = [], []
         for k, v in batch.items():
-            if k in self.static:
-                self.static[k].copy_(v, non_blocking=True)
+            if k in self.static and v is not self.static[k]:
+                dst.append(self.static[k])
+                src.append(v)
+        if src and all(v.is_cuda and v.dtype == d.dtype for v, d in zip(src, dst)):
+            torch._foreach_copy_(dst, src)            # one launch for the whole batch
+        else:
+            for d, v in zip(dst, src):
+                d.copy_(v, non_blocking=True)
+        for p, g in zip(self._params, self._grads):
+            if p.grad is not g:
+                p.grad = g
         if self.fused is not None:
             self.fused.refresh_if_changed()   # lr schedule / load_state_dict since the last replay
+            if self.fused._key is not self._adam_key:
+                # an EAGER optimiser step since the last replay rebuilt the descriptors (which the graph re-reads
+                # from pinned memory on every replay) for that pass's gradient tensors: point them back at the graph's
+                self.fused.refresh()
+                self._adam_key = self.fused._key
         if self.stage is not None:
             self.stage.begin_step()           # this step's pairing permutations from the CPU generator
         self.graph.replay()
+        n, self._n = self._n, self._n + 1
         if self.fused is not None:
-            if not bool(self.flags):     # the single host sync of the step; the update was skipped on the device
-                raise RuntimeError("Infinite loss at train time.")
+            if self.check == "immediate":
+                if not bool(self.flags):     # the single host sync of the step; the update was skipped on the device
+                    raise RuntimeError("Infinite loss at train time.")
+            else:
+                slot = n & 1
+                self._flag_host[slot].copy_(self.flags.reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending, self._pending = self._pending, (ev, slot, n)
+                if pending is not None:
+                    self._look(pending)      # the PREVIOUS replay's flag: the GPU is already busy with this one
             itf._accumulate(self.loss)
             self.fused.note_step()
             return self.loss

@@ -9,6 +9,8 @@ import threading
 
 import torch
 
+from . import streams as _streams
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwcmc.so")
 
@@ -359,6 +361,9 @@ def pack_weights_batch(specs, dtype=torch.bfloat16, dgrad=True):
     return out
 
 
+SHARE_STREAMS = os.environ.get("WCMC_CONV_SHARE", "1") != "0"
+
+
 def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype=None, x_coff=0, mask=None,
            mask_coff=0, slope=0.0, flags=0, cin=None, cout=None, colsum=None, colsum_scale=None, alg_hw=None):
     """x (N,H,W,Cs) 16-bit NHWC; w_packed (cout_p, k*k, cin_p) 16-bit; returns the NHWC output
@@ -379,6 +384,8 @@ def conv2d(x, w_packed, bias, ksize, pad, act=0, out=None, out_coff=0, out_dtype
     if mask is not None:
         assert tuple(_h16(mask).shape[:3]) == (n, ho, wo)
     ah, aw = alg_hw or (ho, wo)
+    if SHARE_STREAMS and not (flags >> 24) & 15:
+        flags |= _streams.share() << 24      # two halves side by side on two streams: plan for half of the SMs each
     _run(lib.wcmc_conv2d, "conv2d_k%d" % ksize, 2.0 * n * ah * aw * ksize * ksize * (cin or cin_p) * (cout or cout_p),
          x.data_ptr(), _dt(x), n, h, w, xcs, x_coff, cin_p, w_packed.data_ptr(), _dt(w_packed), cout_p, _p(bias),
          ksize, pad, out.data_ptr(), _dt(out), out.shape[3], out_coff, act, _p(mask),

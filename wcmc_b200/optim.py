@@ -195,6 +195,18 @@ class FusedClipAdam:
         if self._steps:
             torch._foreach_add_(self._steps, 1.0)
 
+    def set_step(self, t):
+        """Puts the update count of every parameter back to `t` (torch's `step` scalars and the device counter the
+        kernel's bias correction reads) -- for callers that restore weights and moments to an earlier point."""
+        t = int(t)
+        for o in self.optims:
+            for st in o.state.values():
+                if "step" in st:
+                    st["step"].fill_(float(t))
+        if self.t_dev is not None:
+            self.t_dev.fill_(t)
+        self.t = t
+
     def nonfinite_count(self):
         """Gradient elements skipped so far because they were NaN / inf (host sync)."""
         return int(self.nonfinite.item())

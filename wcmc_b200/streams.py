@@ -54,6 +54,17 @@ def fork(name):
         yield
 
 
+def share():
+    """How many such launches run side by side: 2 on a side stream of a fork (the other half's kernels are in flight on
+    its sibling -- also during the backward pass, which autograd runs on the forward pass's streams), else 1.  The
+    persistent convolution launches then plan for half of the SMs each (lib.conv2d, flags bits 24..27), so that the two
+    halves overlap each other's prologue / tail / partial last wave instead of taking the whole machine in turns."""
+    if not ENABLED or not _side or not torch.cuda.is_available():
+        return 1
+    cur = torch.cuda.current_stream()
+    return 2 if any(cur == st for st in _side.values()) else 1
+
+
 def join():
     lst = _open()
     while lst:
