@@ -738,7 +738,7 @@ def test_graphed_step_survives_an_eager_backward_between_replays(backend):
     """An eager backward pass between two replays re-points every `p.grad`; if the optimiser's descriptors are then
     re-read (`load_state_dict`, an lr change: FusedClipAdam.refresh) they must still name the gradient tensors the
     captured kernels write.  Found with bench.py's long-run reset; twin runs (with / without the interleaved eager
-    pass, whose own update is undone) must stay bit-identical."""
+    pass, which takes no update of its own) must follow the same trajectory."""
     from wcmc_b200.engine import GraphedTrainStep
 
     def make():
@@ -774,10 +774,15 @@ def test_graphed_step_survives_an_eager_backward_between_replays(backend):
             step.fused.refresh()
             assert step.fused._key is not step._adam_key
         step(batch)
+        # the descriptors name the graph's own gradient tensors again, and p.grad is pinned back
+        want = [g.data_ptr() for g in step._grads if g is not None]
+        assert [e[1] for e in step.fused._key] == want
+        assert all(p.grad is g for p, g in zip(step._params, step._grads))
         step(batch)
         runs.append(torch.cat([p.detach().flatten() for m in models.values() for p in m.parameters()]).clone())
         step.release()
-    assert torch.equal(runs[0], runs[1])
+    # same trajectory up to the order of the fp32 atomics of the bias gradients (cf. test_graphed_step_matches_eager)
+    assert rel(runs[1], runs[0]) < 2e-3
 
 
 def test_full_frame_denoise_vs_oracle_and_tiling(backend, oracle):

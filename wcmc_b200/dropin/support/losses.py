@@ -17,7 +17,8 @@ from wcmc_b200 import lib
 __all__ = ["GlobalRelativeSimilarityLoss", "FeatureMSE", "RelativeMSE"]
 
 
-_PERM_STATE = {}    # device index -> int64 (2,) [draw counter, ticket] of wcmc_random_permutation
+_PERM_STATE = {}    # device index -> int64 (2,) [draw counter, ticket] of wcmc_random_permutation (the launch's
+                    # ticket is not re-entrant: every draw of a device goes through ONE stream, the loss's)
 
 
 def _randperm(n, device, rng):
