@@ -376,10 +376,14 @@ def main():
     from wcmc_b200 import ddp, dropin, lib
     from wcmc_b200.synth import make_batch
     torch.cuda.set_device(local)
+    numa_cpus = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dropin.install()
     lib.init(local)
+    if world > 1 and os.environ.get("WCMC_NUMA_BIND", "1") != "0":
+        from wcmc_b200.engine import bind_host_to_gpu
+        numa_cpus = bind_host_to_gpu(local)      # before any pinned allocation: first touch on the GPU's node
     from sbmc import KPCN
     from support.interfaces import KPCNInterface
     from support.losses import FeatureMSE, RelativeMSE
@@ -573,7 +577,8 @@ def main():
                         "nccl": "nccl all-reduce"}[sync.peer_transport()],
                        "; dncnn's half overlapped with the path-embedding networks' backward"
                        if sync.early is not None else ", after both backward passes")),
-                   "grad_exchange_channels": None if world == 1 else sync.describe()},
+                   "grad_exchange_channels": None if world == 1 else sync.describe(),
+                   "host_cores_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus)},
         "e2e": {"value": batch_per_gpu * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,

@@ -118,8 +118,8 @@ class GradAllReduce:
 
     def _calibrate(self, px, n):
         """transport="auto" on a machine with a multicast mapping: time both variants of the kernel on this message
-        size (a collective: every rank runs the same launches) and keep the faster one -- the in-switch reduction wins
-        with many ranks, plain peer loads with two."""
+        size (a collective: every rank runs the same launches) and keep the multicast one unless peer loads are
+        clearly (25 %) faster -- the in-switch reduction wins with many ranks, plain peer loads with two."""
         mc, ms = px.multicast_ptr, []
         for cand in (mc, 0):
             px.multicast_ptr = cand
@@ -136,7 +136,11 @@ class GradAllReduce:
             ms.append(e0.elapsed_time(e1) / 10)
         t = torch.tensor(ms, dtype=torch.float32, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        px.multicast_ptr = mc if float(t[0]) <= float(t[1]) else 0
+        # ties go to the multicast variant: its CTAs (64 x 256 threads x 34 registers) fit next to ANY of the step's
+        # persistent kernels, the peer variant's (128 x 256 x <= 58) do not fit next to the 544-thread path-network
+        # backward kernels and hold those off their SMs while an exchange is in flight (4 GPUs, in the step:
+        # 7.147 ms multimem against 7.204 ms peer although peer is 2 % faster alone)
+        px.multicast_ptr = mc if float(t[0]) <= 1.25 * float(t[1]) else 0
         px.calibration_us = {"multimem": round(float(t[0]) * 1e3, 1), "peer": round(float(t[1]) * 1e3, 1)}
 
     def prepare(self, models):

@@ -190,6 +190,31 @@ class GraphedTrainStep:
         return self.loss
 
 
+def bind_host_to_gpu(index):
+    """Restricts this process to the CPU cores NVML reports as local to GPU `index` (torch's device index).  With one
+    process per GPU on a two-socket host, pinned staging buffers are then first-touched on the GPU's own NUMA node and
+    the per-step host -> device copies do not cross the socket interconnect (8 ranks x 197 MB per step).  Returns the
+    core list, or None when NVML / the affinity call is not available (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:                          # noqa: BLE001 -- older bindings take str
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:                              # noqa: BLE001 -- best effort, never fatal
+        return None
+
+
 class DevicePrefetcher:
     """Double-buffered host -> device staging of training batches on a copy stream, so the PCIe
     transfer of batch i+1 overlaps the compute of batch i (the reference's loop does a blocking
