@@ -145,6 +145,70 @@ def _worker(rank, world, port, out_dir):
     gathered = [torch.empty_like(w2) for _ in range(world)]
     dist.all_gather(gathered, w2)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged after the overlapped step"
+    # ---- the same step through the SYMMETRIC-BUFFER host logic of the NVSwitch transport (16-byte slots, two channels,
+    # the flag riding in the late exchange, p.grad adopting views of the buffer) with a stand-in for the kernel: a
+    # CPU buffer reduced by gloo, same interface as ddp.PeerExchange ----
+    class FakeExchange:
+        transport, multicast_ptr = "peer", 0
+
+        def __init__(self, n):
+            self.capacity = (n + 3) // 4 * 4
+            self.buf = torch.full((self.capacity,), float("nan"))     # padding words are never read
+            self.calls = []
+
+        def all_reduce_(self, n, scale=1.0, channel=0, offset=0):
+            assert n % 4 == 0 and offset == 0 and n <= self.capacity
+            self.calls.append((channel, n))
+            region = torch.nan_to_num(self.buf[:n])                   # the pad words may hold anything
+            dist.all_reduce(region)
+            self.buf[:n] = region * scale
+            return self.buf[:n]
+
+    class PeerLogic(ddp.GradAllReduce):
+        def _use_peer(self, grads):
+            return True
+
+        def _exchange(self, channel, n):
+            px = self._px.get(channel)
+            if px is None or px.capacity < n:
+                px = self._px[channel] = FakeExchange(n)
+            return px
+
+    itf.grad_sync = None
+    itf.preprocess(batch)
+    torch.manual_seed(11 + rank)
+    itf.train_batch(batch, grad_hook_mode=True)
+    g_local3 = _flat(models, grad=True).clone()
+    g_all3 = [torch.empty_like(g_local3) for _ in range(world)]
+    dist.all_gather(g_all3, g_local3)
+    peer = PeerLogic()
+    box = {}
+
+    def hook3(ms):
+        box["ok"] = peer(ms, ok=torch.tensor(True))
+        box["g"] = _flat(ms, grad=True).clone()
+    itf.grad_sync = type("Hook", (), {"early": staticmethod(peer.early), "drain": staticmethod(peer.drain), "world": world,
+                                      "__call__": lambda self, ms: hook3(ms)})()
+    itf.preprocess(batch)
+    torch.manual_seed(11 + rank)
+    itf.train_batch(batch)
+    torch.testing.assert_close(box["g"], torch.stack(g_all3).mean(0), rtol=1e-6, atol=1e-9)
+    assert bool(box["ok"]), "all ranks finite -> combined flag true"
+    assert [c for c, _ in peer._px[0].calls] == [0] and [c for c, _ in peer._px[1].calls] == [1]
+    # every gradient is now a 16-byte-aligned view of its channel's buffer (no copy back)
+    for name, m in models.items():
+        px = peer._px[0 if name == "dncnn" else 1]
+        lo, hi = px.buf.data_ptr(), px.buf.data_ptr() + px.buf.numel() * 4
+        for p_ in m.parameters():
+            if p_.grad is not None:
+                assert lo <= p_.grad.data_ptr() < hi and (p_.grad.data_ptr() - lo) % 16 == 0
+    # a rank with a non-finite loss makes every rank skip: the flag element is summed with the gradients
+    bad = peer({k: m for k, m in models.items()}, ok=torch.tensor(rank != 1))
+    assert not bool(bad)
+    w3 = _flat(models)
+    gathered = [torch.empty_like(w3) for _ in range(world)]
+    dist.all_gather(gathered, w3)
+    assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged after the symmetric-buffer step"
     # expected update: Adam on clip(mean gradient)
     torch.save({"w0": w0, "w1": w1, "g": seen["g"]}, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()

@@ -9,6 +9,7 @@ the reference's step order requires it: after both backward passes, before clip_
 Adam (support/interfaces.py:237-238 -> :261 -> :271).  A stock DistributedDataParallel wrapper
 does not fit: each of the two backward passes touches only half of `dncnn`'s parameters.
 """
+import contextlib
 import os
 import warnings
 
@@ -178,13 +179,26 @@ class GradAllReduce:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._early.append((work, flat, grads))
             return
+        with self._aside(grads[0]):
+            views, n = self._gather(px, grads)
+            px.all_reduce_(n, 1.0 / self.world, channel=0)
+        self._early.append((None, views, [p for m in models.values() for p in m.parameters() if p.grad is not None]))
+
+    @contextlib.contextmanager
+    def _aside(self, ref):
+        """The early exchange's own stream (forked from the current one); nothing to fork for CPU tensors."""
+        if not ref.is_cuda:
+            yield
+            return
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
-            views, n = self._gather(px, grads)
-            px.all_reduce_(n, 1.0 / self.world, channel=0)
-        self._early.append((None, views, [p for m in models.values() for p in m.parameters() if p.grad is not None]))
+            yield
+
+    def _rejoin(self):
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     @staticmethod
     def _gather(px, tensors):
@@ -212,7 +226,7 @@ class GradAllReduce:
             if work is not None:
                 work.wait()
             else:
-                torch.cuda.current_stream().wait_stream(self._side)
+                self._rejoin()
 
     def _finish(self, flat, grads):
         flat.div_(self.world)
@@ -261,7 +275,7 @@ class GradAllReduce:
             if work is not None:
                 work.wait()                       # the current stream waits for the collective
             else:
-                torch.cuda.current_stream().wait_stream(self._side)
+                self._rejoin()
             nbytes += self._adopt(flat_e, grads_e) if work is None else self._finish(flat_e, grads_e)
         self.bytes_last = nbytes
         return all_ok
