@@ -571,6 +571,11 @@ def main():
                          % (h2d_bytes / 1e6, 700.0),
                    "precision": "fp16 operands (loss-scaled gradients), fp32 accumulate / master weights / losses",
                    "perm_rng": args.perm_rng, "cuda_graph": bool(use_graph), "branch_streams": bool(streams.ENABLED),
+                   "step_sync": ("finite flag of step i read after step i+1 is enqueued (a non-finite step skips its update "
+                                 "on the device); the last flag is read inside the timed region; the device-resident loop "
+                                 "feeds the graph's static input buffers in place" if use_graph else "one host sync per step"),
+                   "e2e_readback": "running loss copied to pinned host memory behind every step, read one step later; "
+                                   "the last one inside the timed region",
                    "grad_exchange": (None if world == 1 else "%s in the step graph%s" % (
                        {"multimem": "own two-shot kernel over the NVSwitch multicast mapping (multimem.ld_reduce / st)",
                         "peer": "own two-shot kernel over NVLink peer loads / stores",
