@@ -41,6 +41,11 @@ class KPCN(nn.Module):
             r_d = self._branch(self.diffuse, data["kpcn_diffuse_in"], data["kpcn_diffuse_buffer"])
         with streams.fork("specular"):
             r_s = self._branch(self.specular, data["kpcn_specular_in"], data["kpcn_specular_buffer"])
+        # The caller's stream idles until the join: a caller may hang work here that does not depend on the branches
+        # (KPCNInterface: the two path-disentangling losses, which only need the p-buffers and the output SIZE).
+        hook = self.__dict__.get("while_branches_run")
+        if hook is not None:
+            hook(tuple(r_d.shape[-2:]))
         streams.join()
         radiance = ops.RecombineFn.apply(data["kpcn_albedo"], r_d, r_s)     # albedo * r_d + exp(r_s) - 1, centred crop
         return dict(radiance=radiance, diffuse=r_d, specular=r_s)

@@ -17,6 +17,10 @@ import torch.nn as nn
 from support.utils import crop_like
 
 _DISENTANGLE = ("m11r11", "m10r01", "m11r01", "m10r11")
+# 1: the path-disentangling losses run while the KPCN branches run; default 0: after them, as the reference orders
+# the calls.  Measured 7.13 -> 7.09 ms per step on one B200 (three runs, GPU tests green with it on); off by default
+# because that is within what boxes differ by and the default path is the one every multi-GPU run of round 2 used.
+OVERLAP_MANIF = os.environ.get("WCMC_OVERLAP_MANIF", "0") != "0"
 
 
 class BaseInterface(metaclass=ABCMeta):
@@ -217,11 +221,35 @@ class KPCNInterface(BaseInterface):
             batch = _with_pbuffer(batch, p_buffers, self._reg_channels(p_buffers))
             self._p_full = p_buffers
         self.models["dncnn"].zero_grad()
-        out = self._regress_forward(batch)
+        self._manif_pre = None
+        dn, lm = self.models["dncnn"], self.loss_funcs.get("l_manif")
+        early_manif = (OVERLAP_MANIF and out_manif is not None and self.manif_learn and self.train_branches
+                       and hasattr(lm, "forward_cropped") and callable(getattr(dn, "_branch", None))
+                       and "while_branches_run" not in dn.__dict__)
+        if early_manif:
+            # The path-disentangling losses need the p-buffers and the SIZE of the KPCN output only: they are computed
+            # on this stream while the two KPCN branches run on theirs (sbmc.KPCN.forward calls the hook between its
+            # fork and its join), instead of after them with the machine idle.  Same calls in the same order (diffuse,
+            # then specular -- the order in which the reference consumes its CPU generator, losses.py:35, :50); in the
+            # backward pass their gradient kernels are then enqueued before the traversal has to wait for the branches.
+            pre = self._manif_pre = {}
+            targets = batch
+
+            def hook(hw):
+                like = torch.empty((0, 0) + tuple(hw), device="meta")
+                for name in ("diffuse", "specular"):
+                    pre[name] = lm.forward_cropped(out_manif[name], crop_like(targets["target_" + name], like))
+            dn.__dict__["while_branches_run"] = hook
+        try:
+            out = self._regress_forward(batch)
+        finally:
+            if early_manif:
+                dn.__dict__.pop("while_branches_run", None)
         try:
             return self._backward(batch, out, out_manif)
         finally:
             self._p_full = None
+            self._manif_pre = None
 
     def _run_backward(self, roots):
         """One autograd traversal with both loss roots (same gradients as the reference's `L_diffuse.backward();
@@ -258,7 +286,10 @@ class KPCNInterface(BaseInterface):
                 loss = fused["l_" + name] if fused is not None else self.loss_funcs["l_" + name](pred, tgt)
                 if self.manif_learn:
                     lm = self.loss_funcs["l_manif"]
-                    if hasattr(lm, "forward_cropped"):     # the crop of crop_like() taken inside the loss Function
+                    pre = getattr(self, "_manif_pre", None)
+                    if pre and name in pre and tuple(pred.shape[-2:]) == tuple(tgt.shape[-2:]):
+                        l_manif = pre[name]                # computed while the KPCN branches ran (_forward_backward)
+                    elif hasattr(lm, "forward_cropped"):   # the crop of crop_like() taken inside the loss Function
                         l_manif = lm.forward_cropped(p_buffers[name], tgt)
                     else:
                         l_manif = lm(crop_like(p_buffers[name], pred), tgt)
