@@ -367,3 +367,119 @@ print("OK")
 ''' % (root, str(tmp_path))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-1500:], r.stderr[-2500:])
+
+
+class _TinyBackbone(torch.nn.Module):
+    """Stand-in for the single path-embedding network of train_sbmc.py: dict -> (B,S,C,H,W)."""
+
+    def __init__(self, ic, outc):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(ic, outc, 1)
+
+    def forward(self, samples):
+        p = samples["paths"]
+        b, s, c, h, w = p.shape
+        return torch.relu(self.conv(p.reshape(b * s, c, h, w))).reshape(b, s, -1, h, w)
+
+
+class _TinyMultisteps(torch.nn.Module):
+    """Stand-in for sbmc.Multisteps: per-sample features + radiance -> a (B,3,h,w) image, valid 3x3 conv (so that
+    crop_like has something to crop)."""
+
+    def __init__(self, n_feat):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(n_feat + 3, 3, 3)
+
+    def forward(self, batch):
+        x = torch.cat([batch["features"], batch["radiance"]], 2).mean(1)
+        return self.conv(x)
+
+
+def itf_clip(which):
+    return 1000.0 if which == "SBMCInterface" else 250.0
+
+
+def _sbmc_batch(seed, llpm):
+    g = torch.Generator().manual_seed(seed)
+    b, s, h, w, f = 2, 3, 20, 20, 7
+    batch = {"target_image": torch.rand(b, 3, h, w, generator=g), "radiance": torch.rand(b, s, 3, h, w, generator=g),
+             "features": torch.rand(b, s, f, h, w, generator=g)}
+    if llpm:
+        batch["paths"] = torch.rand(b, s, 36, h, w, generator=g)
+    return batch, f
+
+
+@pytest.mark.parametrize("cfg", [dict(use_llpm_buf=True, manif_learn=True, disentangle="m11r11"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentangle="m10r01"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentangle="m11r01"),
+                                 dict(use_llpm_buf=True, manif_learn=True, disentangle="m10r11"),
+                                 dict(use_llpm_buf=True, manif_learn=False),
+                                 dict(use_llpm_buf=False, manif_learn=False)],
+                         ids=lambda c: "-".join("%s=%s" % kv for kv in c.items()))
+@pytest.mark.parametrize("which", ["SBMCInterface", "LBMCInterface"])
+def test_sbmc_interface_matches_reference_class(both, cfg, which):
+    """SBMCInterface / LBMCInterface (/root/reference/support/interfaces.py:336-523, :753-839) with stand-in backbone /
+    Multisteps modules: same losses, gradients (after clip_grad_norm_; the inputs are scaled so that the LBMC clip of
+    250 actually bites), parameters after the step, validate outputs and epoch summary."""
+    llpm = cfg["use_llpm_buf"]
+    outc = 4
+    half = cfg.get("disentangle", "m11r11") in ("m10r01", "m11r01")
+    batch, f = _sbmc_batch(5, llpm)
+    batch["target_image"] = batch["target_image"] * 3000.0      # large residuals -> gradient norms above both clips
+    n_feat = f + ((outc // 2 if half else outc) + 1 if llpm else 0)
+
+    def run(cls):
+        torch.manual_seed(0)
+        models = {"dncnn": _TinyMultisteps(n_feat)}
+        if llpm:
+            models["backbone"] = _TinyBackbone(36, outc)
+        lf = {"l_recon": torch.nn.MSELoss(), "l_test": both.RelativeMSE()}     # MSE: its gradient grows with the residual
+        if cfg["manif_learn"]:
+            lf["l_manif"] = _TinyManifLoss()
+        optims = {"optim_" + k: torch.optim.SGD(m.parameters(), lr=1e-6) for k, m in models.items()}   # SGD: the update
+        itf = cls(models, optims, lf, types.SimpleNamespace(model_name="t"), w_manif=0.1, **cfg)       # shows the clip
+        itf.to_train_mode()
+        itf.preprocess(batch)
+        itf.train_batch(batch)
+        gn = torch.sqrt(sum(p.grad.pow(2).sum() for p in models["dncnn"].parameters()))
+        assert abs(float(gn) - itf_clip(which)) < 1e-2 * itf_clip(which), "the gradient-norm clip did not bite"
+        res = dict(losses={k: v.clone() for k, v in itf.m_losses.items()}, iters=itf.iters,
+                   grads=[None if p.grad is None else p.grad.clone() for m in models.values() for p in m.parameters()],
+                   params=[p.detach().clone() for m in models.values() for p in m.parameters()])
+        itf.to_eval_mode()
+        with torch.no_grad():
+            res["out"], res["pb"] = itf.validate_batch(batch)
+        res["m_val"] = itf.m_losses["m_val"].clone()
+        res["summary"] = itf.get_epoch_summary("eval", 1.0)
+        res["str"] = str(itf)
+        return res
+
+    ours, ref = run(getattr(both.ours, which)), run(getattr(both.ref, which))
+    assert list(ours["losses"]) == list(ref["losses"]) and ours["iters"] == ref["iters"] and ours["str"] == ref["str"]
+    for k in ref["losses"]:
+        torch.testing.assert_close(ours["losses"][k], ref["losses"][k], rtol=1e-6, atol=1e-8, msg=k)
+    for x, y in zip(ours["grads"], ref["grads"]):
+        assert (x is None) == (y is None)
+        if x is not None:
+            torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-9)
+    for x, y in zip(ours["params"], ref["params"]):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(ours["out"], ref["out"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(ours["m_val"], ref["m_val"], rtol=1e-6, atol=1e-8)
+    assert abs(ours["summary"] - ref["summary"]) < 1e-7
+    assert (ours["pb"] is None) == (ref["pb"] is None)
+    if ref["pb"] is not None:
+        torch.testing.assert_close(ours["pb"], ref["pb"], rtol=1e-6, atol=1e-8)
+
+
+def test_sbmc_interface_names_the_non_finite_term(both):
+    batch, f = _sbmc_batch(6, False)
+    models = {"dncnn": _TinyMultisteps(f)}
+    optims = {"optim_dncnn": torch.optim.Adam(models["dncnn"].parameters(), lr=1e-3)}
+    itf = both.ours.SBMCInterface(models, optims, {"l_recon": torch.nn.L1Loss(), "l_test": both.RelativeMSE()},
+                                  types.SimpleNamespace(model_name="t"))
+    itf.to_train_mode()
+    bad = dict(batch, target_image=batch["target_image"] * float("nan"))
+    itf.preprocess(bad)
+    with pytest.raises(RuntimeError, match="l_total: Non-finite loss at train time."):
+        itf.train_batch(bad)

@@ -551,3 +551,180 @@ class KPCNPreInterface(KPCNInterface):
         for name in self.models:
             if self._trained(name):
                 self.optims["optim_" + name].step()
+
+
+class SBMCInterface(BaseInterface):
+    """Step orchestration for a sample-based backbone (sbmc.Multisteps) with ONE path-embedding network
+    (/root/reference/support/interfaces.py:336-523; used by train_sbmc.py).  Host logic only: the backbone is whatever
+    module the caller passes (its kernels are outside this package's hot path); the path-embedding network, the
+    path-disentangling loss and RelativeMSE are this package's, so a `models['backbone'] = PathNet(...)` runs on the
+    B200 kernels.  Same public surface and `m_losses` keys as the reference class.  Differences, host-side only:
+    one finite check (one device -> host sync) per step instead of one per loss term, and the `grad_sync` hook of
+    KPCNInterface between the backward pass and the gradient-norm clipping (:466)."""
+
+    CLIP_NORM = 1000
+
+    def __init__(self, models, optims, loss_funcs, args, visual=False, use_llpm_buf=False, manif_learn=False,
+                 w_manif=0.1, use_sbmc_buf=True, disentangle="m11r11"):
+        if manif_learn:
+            assert "backbone" in models, "argument `models` dictionary should contain `'backbone'` key."
+        assert "dncnn" in models, "argument `models` dictionary should contain `'dncnn'` key."
+        if manif_learn:
+            assert "l_manif" in loss_funcs
+        assert "l_recon" in loss_funcs
+        assert "l_test" in loss_funcs
+        assert disentangle in _DISENTANGLE
+        super().__init__(models, optims, loss_funcs, args, visual, use_llpm_buf, manif_learn, w_manif)
+        self.disentangle = disentangle
+        self.use_sbmc_buf = use_sbmc_buf
+        self.grad_sync = None
+
+    def __str__(self):
+        return "SBMCInterface"
+
+    def to_train_mode(self):
+        for name, model in self.models.items():
+            model.train()
+            assert "optim_" + name in self.optims, "`optim_%s`: an optimization algorithm is not defined." % name
+
+    def to_eval_mode(self):
+        for model in self.models.values():
+            model.eval()
+        self.m_losses["m_val"] = torch.tensor(0.0)
+
+    def preprocess(self, batch=None):
+        for key in ("target_image", "radiance", "features"):
+            assert key in batch
+        if self.use_llpm_buf:
+            assert "paths" in batch
+        self.iters += 1
+
+    def _manifold_forward(self, batch):
+        return self.models["backbone"](batch)
+
+    def _regress_forward(self, batch):
+        return self.models["dncnn"](batch)
+
+    def _with_pbuffer(self, batch, p_reg):
+        """features <- [features | p | var_S(p).mean(C) / S broadcast over the samples] per sample (:385-394)."""
+        s = p_reg.shape[1]
+        var = (p_reg.var(1).mean(1, keepdim=True) / s).detach()
+        var = var.unsqueeze(1).expand(-1, s, -1, -1, -1)
+        return {"target_image": batch["target_image"], "radiance": batch["radiance"],
+                "features": torch.cat([batch["features"], p_reg, var], 2)}
+
+    def _split(self, p_buffer):
+        """-> (p fed to the regression, p fed to the manifold loss)   (:371-383)"""
+        c = p_buffer.shape[2]
+        assert c >= 2
+        lo, hi = p_buffer[:, :, :c // 2], p_buffer[:, :, c // 2:]
+        return (lo if self.disentangle in ("m10r01", "m11r01") else p_buffer,
+                hi if self.disentangle in ("m10r01", "m10r11") else p_buffer)
+
+    def train_batch(self, batch, grad_hook_mode=False):
+        out_manif = None
+        if self.use_llpm_buf:
+            self.models["backbone"].zero_grad()
+            p_buffer = self._manifold_forward(batch)
+            if self.iters % 1000 == 1:
+                self._dump(p_buffer)
+            p_reg, out_manif = self._split(p_buffer)
+            batch = self._with_pbuffer(batch, p_reg)
+        self.models["dncnn"].zero_grad()
+        out = self._regress_forward(batch)
+        loss_dict = self._backward(batch, out, out_manif)
+        if grad_hook_mode:      # gradients only
+            return
+        self._logging(loss_dict)
+        self._optimization()
+
+    def _dump(self, p_buffer):
+        out_dir = "../LLPM_results"
+        if not os.path.isdir(out_dir):
+            return
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            return
+        img = p_buffer.detach()[0, :, :3].mean(0).clamp(0.0, 1.0).permute(1, 2, 0).cpu().numpy()
+        plt.imsave("%s/pbuf_%s.png" % (out_dir, self.args.model_name), img)
+
+    def _backward(self, batch, out, p_buffer):
+        losses = {}
+        tgt = crop_like(batch["target_image"], out)
+        l_total = self.loss_funcs["l_recon"](out, tgt)
+        if self.manif_learn:
+            l_manif = self.loss_funcs["l_manif"](crop_like(p_buffer, out), tgt)
+            losses["l_manif"] = l_manif.detach()
+            # the reference takes `.detach()` of the reconstruction loss and THEN adds the weighted manifold term in
+            # place (:440-443): the detached view shares storage, so its logged `l_recon` includes that term too
+            l_total = l_total + l_manif * self.w_manif
+            losses["l_recon"] = l_total.detach()
+        losses["l_total"] = l_total.detach()
+        l_total.backward()
+        with torch.no_grad():
+            losses["rmse"] = self.loss_funcs["l_test"](out, tgt).detach()
+        return losses
+
+    def _logging(self, loss_dict):
+        keys = list(loss_dict)
+        finite = torch.isfinite(torch.stack([loss_dict[k].reshape(()) for k in keys]))
+        if not bool(finite.all()):            # the step's one host sync; name the first offending term like :460
+            bad = keys[int((~finite).nonzero()[0])]
+            raise RuntimeError("%s: Non-finite loss at train time." % bad)
+        if self.grad_sync is not None:
+            self.grad_sync(self.models)
+        for name, model in self.models.items():
+            actual = nn.utils.clip_grad_norm_(model.parameters(), max_norm=self.CLIP_NORM)
+            if actual > self.CLIP_NORM:
+                print("Clipped %s gradients %f -> %f" % (name, self.CLIP_NORM, actual))
+        for k in keys:
+            if "m_" + k not in self.m_losses:
+                self.m_losses["m_" + k] = torch.tensor(0.0, device=loss_dict[k].device)
+            self.m_losses["m_" + k] += loss_dict[k]
+
+    def _optimization(self):
+        for name in self.models:
+            self.optims["optim_" + name].step()
+
+    def validate_batch(self, batch):
+        p_buffer = None
+        if self.use_llpm_buf:
+            p_buffer = self._manifold_forward(batch)
+            assert p_buffer.shape[2] >= 2
+            if self.disentangle in ("m10r01", "m11r01"):
+                p_buffer = p_buffer[:, :, :p_buffer.shape[2] // 2]
+            batch = self._with_pbuffer(batch, p_buffer)
+        out = self._regress_forward(batch)
+        tgt = crop_like(batch["target_image"], out)
+        l_total = self.loss_funcs["l_test"](out, tgt)
+        if self.m_losses["m_val"].device != l_total.device:
+            self.m_losses["m_val"] = self.m_losses["m_val"].to(l_total.device)
+        self.m_losses["m_val"] += l_total.detach()
+        return out, p_buffer
+
+    def get_epoch_summary(self, mode, norm):
+        if mode == "train":
+            print("[][][]", end=" ")
+            for key in self.m_losses:
+                if key == "m_val":
+                    continue
+                print("%s: %.3fE-3" % (key, self.m_losses[key] / (norm * 2) * 1000), end="\t")
+                self.m_losses[key] = torch.tensor(0.0, device=self.m_losses[key].device)
+            print("")
+            return -1.0
+        return self.m_losses["m_val"].item() / (norm * 2)
+
+
+class LBMCInterface(SBMCInterface):
+    """The layer-based backbone's variant (/root/reference/support/interfaces.py:753-839; train_lbmc.py): the same step
+    with a tighter gradient-norm clip (0.25 * 1000, :826) and a constructor without `visual` / `use_sbmc_buf`."""
+
+    CLIP_NORM = 0.25 * 1000
+
+    def __init__(self, models, optims, loss_funcs, args, use_llpm_buf=False, manif_learn=False, w_manif=0.1,
+                 disentangle="m11r11"):
+        super().__init__(models, optims, loss_funcs, args, False, use_llpm_buf, manif_learn, w_manif, False, disentangle)
+
+    def __str__(self):
+        return "LBMCInterface"
