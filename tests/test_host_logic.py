@@ -270,3 +270,33 @@ def test_bench_kernel_summary_from_profile():
     # an empty profile (no conv launches) must not divide by zero
     r0, m0, k0 = bench.summarize_kernels({}, steps, pk, "fallback")
     assert r0["achieved"] == 0.0 and m0 == [] and k0 == {}
+
+
+def test_exchange_host_helpers_without_a_gpu():
+    """Host-side pieces of the multi-GPU path that need no device: 16-byte gradient slots, in-place detection,
+    half-machine planning only on forked side streams, NUMA binding as a best-effort no-op."""
+    import types
+
+    import torch
+
+    from wcmc_b200 import ddp, streams
+    from wcmc_b200 import dropin
+    dropin.install()
+    from wcmc_b200.engine import bind_host_to_gpu
+    assert streams.share() == 1                          # no CUDA, no fork: the whole machine
+    assert bind_host_to_gpu(0) is None                   # no NVML device here: nothing changes, nothing raises
+    ts = [torch.arange(5.0), torch.arange(3.0).reshape(3, 1), torch.arange(8.0)]
+    assert ddp.GradAllReduce._slots(ts) == 8 + 4 + 8
+    px = types.SimpleNamespace(buf=torch.full((32,), -1.0))
+    views, n = ddp.GradAllReduce._gather(px, ts)
+    assert n == 20 and [v.data_ptr() - px.buf.data_ptr() for v in views] == [0, 32, 48]    # 16-byte slots
+    assert all(torch.equal(v, t) for v, t in zip(views, ts)) and float(px.buf[5]) == -1.0   # pad words untouched
+    # gradients that already live in the buffer (zero_grad(set_to_none=False) + in-place accumulation): no copy
+    px.buf[0] = 42.0
+    again, _ = ddp.GradAllReduce._gather(px, views)
+    assert float(again[0][0]) == 42.0
+    sync = ddp.GradAllReduce(transport="nccl")
+    assert sync.world == 1 and sync.describe() == {} and sync.peer_transport() == "nccl"
+    import pytest
+    with pytest.raises(AssertionError):
+        ddp.GradAllReduce(transport="carrier-pigeon")
